@@ -1,0 +1,362 @@
+"""CPU oracle for the HSI-DMGASR inference hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, in plain fp32 PyTorch on the CPU and in a *functional* style over flat
+``state_dict`` mappings, the algorithm of the reference's hot path:
+
+  * beta schedules + schedule buffers      reference model/sr3_modules/diffusion.py:11-49, 93-140
+  * noise-level embedding, UNet forward    reference model/sr3_modules/unet.py:18-31, 34-50, 80-159, 162-263
+  * p_mean_variance / p_sample / loop      reference model/sr3_modules/diffusion.py:142-201
+  * GAE group layout / encode / decode     reference AE.py:256-324, common.py:163-182, 231-271
+  * MPSNR / SAM                            reference eval_hsi.py:47-65, 110-121
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` may import it; it is the checker, never the product.  The product package
+(``hsi_dmgasr_b200``) does not import anything from ``oracle/`` and has no CPU fallback.
+
+Pinning: the reference ships no tests or golden vectors, so this oracle is pinned
+against outputs of the *unmodified reference modules* imported in the build container; the generating
+script is ``oracle/make_golden.py`` and the vectors live in ``tests/golden/``
+(``tests/test_oracle_golden.py`` checks them on every CPU run).  The dense arithmetic itself
+(conv / group_norm / softmax / matmul) lives in PyTorch ATen, exactly as it does for the reference.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+
+# --------------------------------------------------------------------------------------------------
+# schedule  (diffusion.py:11-49, 93-140)
+# --------------------------------------------------------------------------------------------------
+def beta_schedule(schedule: str, n_timestep: int, linear_start: float = 1e-4, linear_end: float = 2e-2,
+                  cosine_s: float = 8e-3) -> np.ndarray:
+    """float64 betas; one branch per schedule name of diffusion.py:19-49."""
+    T = int(n_timestep)
+    if schedule == "quad":
+        b = np.linspace(linear_start ** 0.5, linear_end ** 0.5, T, dtype=np.float64) ** 2
+    elif schedule == "linear":
+        b = np.linspace(linear_start, linear_end, T, dtype=np.float64)
+    elif schedule in ("warmup10", "warmup50"):
+        frac = 0.1 if schedule == "warmup10" else 0.5
+        b = linear_end * np.ones(T, dtype=np.float64)
+        w = int(T * frac)
+        b[:w] = np.linspace(linear_start, linear_end, w, dtype=np.float64)
+    elif schedule == "const":
+        b = linear_end * np.ones(T, dtype=np.float64)
+    elif schedule == "jsd":
+        b = 1.0 / np.linspace(T, 1, T, dtype=np.float64)
+    elif schedule == "cosine":
+        # the reference evaluates this branch with torch float64 ops (diffusion.py:36-45)
+        s = torch.arange(T + 1, dtype=torch.float64) / T + cosine_s
+        a = torch.cos(s / (1 + cosine_s) * math.pi / 2).pow(2)
+        a = a / a[0]
+        b = (1 - a[1:] / a[:-1]).clamp(max=0.999).numpy()
+    else:
+        raise NotImplementedError(schedule)
+    return np.asarray(b, dtype=np.float64)
+
+
+def schedule_tables(betas: np.ndarray) -> Dict[str, np.ndarray]:
+    """The 12 fp32 buffers + the float64 noise-level table of diffusion.py:93-140."""
+    betas = np.asarray(betas, dtype=np.float64)
+    alphas = 1.0 - betas
+    ac = np.cumprod(alphas, axis=0)
+    ac_prev = np.append(1.0, ac[:-1])
+    post_var = betas * (1.0 - ac_prev) / (1.0 - ac)
+    f32 = lambda a: np.asarray(a, dtype=np.float32)
+    return {
+        "betas": f32(betas),
+        "alphas_cumprod": f32(ac),
+        "alphas_cumprod_prev": f32(ac_prev),
+        "sqrt_alphas_cumprod": f32(np.sqrt(ac)),
+        "sqrt_one_minus_alphas_cumprod": f32(np.sqrt(1.0 - ac)),
+        "log_one_minus_alphas_cumprod": f32(np.log(1.0 - ac)),
+        "sqrt_recip_alphas_cumprod": f32(np.sqrt(1.0 / ac)),
+        "sqrt_recipm1_alphas_cumprod": f32(np.sqrt(1.0 / ac - 1)),
+        "posterior_variance": f32(post_var),
+        "posterior_log_variance_clipped": f32(np.log(np.maximum(post_var, 1e-20))),
+        "posterior_mean_coef1": f32(betas * np.sqrt(ac_prev) / (1.0 - ac)),
+        "posterior_mean_coef2": f32((1.0 - ac_prev) * np.sqrt(alphas) / (1.0 - ac)),
+        # float64, length T+1; entry t+1 is the noise level fed to the UNet at loop index t
+        "sqrt_alphas_cumprod_prev": np.sqrt(np.append(1.0, ac)),
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# UNet  (unet.py)
+# --------------------------------------------------------------------------------------------------
+def unet_topology(inner_channel: int, channel_mults: Sequence[int], attn_res: Sequence[int], res_blocks: int,
+                  image_size: int):
+    """Module list implied by UNet.__init__ (unet.py:190-236).
+
+    Returns (downs, mid, ups); each entry is ("conv",) | ("res", cin, cout, attn) | ("down", c) | ("up", c).
+    ``attn`` is decided against the *config* image_size, not the runtime size (unet.py:195,200).
+    """
+    attn_res = list(attn_res) if attn_res is not None else []
+    pre = inner_channel
+    feat = [pre]
+    now = image_size
+    downs = [("conv",)]
+    L = len(channel_mults)
+    for i in range(L):
+        cm = inner_channel * channel_mults[i]
+        for _ in range(res_blocks):
+            downs.append(("res", pre, cm, now in attn_res))
+            feat.append(cm)
+            pre = cm
+        if i != L - 1:
+            downs.append(("down", pre))
+            feat.append(pre)
+            now //= 2
+    mid = [("res", pre, pre, True), ("res", pre, pre, False)]
+    ups = []
+    for i in reversed(range(L)):
+        cm = inner_channel * channel_mults[i]
+        for _ in range(res_blocks + 1):
+            ups.append(("res", pre + feat.pop(), cm, now in attn_res))
+            pre = cm
+        if i >= 1:
+            ups.append(("up", pre))
+            now *= 2
+    return downs, mid, ups
+
+
+def noise_embedding(sd: SD, level: torch.Tensor, dim: int) -> torch.Tensor:
+    """PositionalEncoding + 2-layer MLP (unet.py:18-31, 182-187). level: [N,1] -> [N,1,dim]."""
+    half = dim // 2
+    step = torch.arange(half, dtype=level.dtype) / half
+    enc = level.unsqueeze(1) * torch.exp(-math.log(1e4) * step.unsqueeze(0))
+    enc = torch.cat([torch.sin(enc), torch.cos(enc)], dim=-1)
+    h = F.linear(enc, sd["noise_level_mlp.1.weight"], sd["noise_level_mlp.1.bias"])
+    h = h * torch.sigmoid(h)
+    return F.linear(h, sd["noise_level_mlp.3.weight"], sd["noise_level_mlp.3.bias"])
+
+
+def _gn_swish_conv(sd: SD, p: str, x: torch.Tensor, groups: int) -> torch.Tensor:
+    """Block = GroupNorm -> Swish -> (Dropout=identity in eval) -> Conv3x3 (unet.py:80-91)."""
+    h = F.group_norm(x, groups, sd[p + ".block.0.weight"], sd[p + ".block.0.bias"], eps=1e-5)
+    h = h * torch.sigmoid(h)
+    return F.conv2d(h, sd[p + ".block.3.weight"], sd[p + ".block.3.bias"], padding=1)
+
+
+def _res_block(sd: SD, p: str, x: torch.Tensor, temb: torch.Tensor, groups: int) -> torch.Tensor:
+    """ResnetBlock.forward (unet.py:105-111) with use_affine_level=False (unet.py:49)."""
+    h = _gn_swish_conv(sd, p + ".block1", x, groups)
+    nb = F.linear(temb, sd[p + ".noise_func.noise_func.0.weight"], sd[p + ".noise_func.noise_func.0.bias"])
+    h = h + nb.view(x.shape[0], -1, 1, 1)
+    h = _gn_swish_conv(sd, p + ".block2", h, groups)
+    if (p + ".res_conv.weight") in sd:
+        x = F.conv2d(x, sd[p + ".res_conv.weight"], sd[p + ".res_conv.bias"])
+    return h + x
+
+
+def _self_attention(sd: SD, p: str, x: torch.Tensor, groups: int) -> torch.Tensor:
+    """SelfAttention.forward with n_head=1 (unet.py:124-143)."""
+    n, c, hh, ww = x.shape
+    nrm = F.group_norm(x, groups, sd[p + ".norm.weight"], sd[p + ".norm.bias"], eps=1e-5)
+    qkv = F.conv2d(nrm, sd[p + ".qkv.weight"], None)
+    q, k, v = qkv.view(n, 3, c, hh * ww).unbind(1)             # channel chunks [0:C],[C:2C],[2C:3C]
+    att = torch.softmax(torch.einsum("ncs,nct->nst", q, k) / math.sqrt(c), dim=-1)
+    o = torch.einsum("nst,nct->ncs", att, v).reshape(n, c, hh, ww)
+    o = F.conv2d(o, sd[p + ".out.weight"], sd[p + ".out.bias"])
+    return o + x
+
+
+def unet_forward(sd: SD, cfg: dict, x: torch.Tensor, level: torch.Tensor,
+                 taps: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+    """UNet.forward (unet.py:239-263). ``sd`` keys are relative to ``denoise_fn.``; x [N,Cin,H,W], level [N,1]."""
+    groups = cfg.get("norm_groups") or 32
+    downs, mid, ups = unet_topology(cfg["inner_channel"], cfg["channel_multiplier"], cfg["attn_res"],
+                                    cfg["res_blocks"], cfg["image_size"])
+    temb = noise_embedding(sd, level, cfg["inner_channel"])
+
+    def run_res(prefix, spec, h):
+        h = _res_block(sd, prefix + ".res_block", h, temb, groups)
+        if spec[3]:
+            h = _self_attention(sd, prefix + ".attn", h, groups)
+        return h
+
+    feats: List[torch.Tensor] = []
+    h = x
+    for i, spec in enumerate(downs):
+        if spec[0] == "conv":
+            h = F.conv2d(h, sd["downs.0.weight"], sd["downs.0.bias"], padding=1)
+        elif spec[0] == "res":
+            h = run_res(f"downs.{i}", spec, h)
+        else:
+            h = F.conv2d(h, sd[f"downs.{i}.conv.weight"], sd[f"downs.{i}.conv.bias"], stride=2, padding=1)
+        feats.append(h)
+        if taps is not None:
+            taps[f"downs.{i}"] = h
+    for i, spec in enumerate(mid):
+        h = run_res(f"mid.{i}", spec, h)
+        if taps is not None:
+            taps[f"mid.{i}"] = h
+    for i, spec in enumerate(ups):
+        if spec[0] == "res":
+            h = run_res(f"ups.{i}", spec, torch.cat((h, feats.pop()), dim=1))
+        else:
+            h = F.interpolate(h, scale_factor=2, mode="nearest")
+            h = F.conv2d(h, sd[f"ups.{i}.conv.weight"], sd[f"ups.{i}.conv.bias"], padding=1)
+        if taps is not None:
+            taps[f"ups.{i}"] = h
+    return _gn_swish_conv(sd, "final_conv", h, groups)
+
+
+# --------------------------------------------------------------------------------------------------
+# sampling  (diffusion.py:142-201)
+# --------------------------------------------------------------------------------------------------
+def posterior_step(tab: Dict[str, np.ndarray], t: int, x_t: torch.Tensor, eps: torch.Tensor,
+                   noise: Optional[torch.Tensor]) -> torch.Tensor:
+    """predict_start_from_noise -> clamp -> q_posterior -> add noise (diffusion.py:142-175)."""
+    f = lambda k: torch.tensor(tab[k][t], dtype=torch.float32)
+    x0 = f("sqrt_recip_alphas_cumprod") * x_t - f("sqrt_recipm1_alphas_cumprod") * eps
+    x0 = x0.clamp(-1.0, 1.0)
+    mean = f("posterior_mean_coef1") * x0 + f("posterior_mean_coef2") * x_t
+    if noise is None:
+        noise = torch.zeros_like(x_t)
+    return mean + noise * (0.5 * f("posterior_log_variance_clipped")).exp()
+
+
+def sample_loop(sd: SD, cfg: dict, tab: Dict[str, np.ndarray], cond: torch.Tensor, x_T: torch.Tensor,
+                step_noise, continous: bool = False, record=None) -> torch.Tensor:
+    """Conditional branch of p_sample_loop (diffusion.py:188-201).
+
+    ``step_noise(i)`` returns the N(0,1) tensor used at loop index i (i = T-1 .. 1); index 0 uses zeros.
+    Returns what the reference returns: ``ret_img`` (continous) or ``ret_img[-1]`` (a 3-D tensor).
+    """
+    T = len(tab["betas"])
+    inter = 1 | (T // 10)
+    img = x_T
+    ret = cond
+    n = cond.shape[0]
+    for i in reversed(range(T)):
+        level = torch.full((n, 1), float(tab["sqrt_alphas_cumprod_prev"][i + 1]), dtype=torch.float32)
+        eps = unet_forward(sd, cfg, torch.cat([cond, img], dim=1), level)
+        img = posterior_step(tab, i, img, eps, step_noise(i) if i > 0 else None)
+        if record is not None:
+            record(i, eps, img)
+        if i % inter == 0:
+            ret = torch.cat([ret, img], dim=0)
+    return ret if continous else ret[-1]
+
+
+# --------------------------------------------------------------------------------------------------
+# GAE  (AE.py:145-324, common.py:163-182, 231-271)
+# --------------------------------------------------------------------------------------------------
+def gae_groups(n_colors: int, n_subs: int, n_ovls: int):
+    """Group start/end indices (AE.py:264-280)."""
+    G = math.ceil((n_colors - n_ovls) / (n_subs - n_ovls))
+    start, end = [], []
+    for g in range(G):
+        s = (n_subs - n_ovls) * g
+        e = s + n_subs
+        if e > n_colors:
+            e = n_colors
+            s = n_colors - n_subs
+        start.append(s)
+        end.append(e)
+    return G, start, end
+
+
+def _lrelu(x):
+    return F.leaky_relu(x, 0.01)
+
+
+def _branch(sd: SD, p: str, x: torch.Tensor, n_blocks: int, res_scale: float = 0.1) -> torch.Tensor:
+    """BranchUnit(use_tail=False, up_scale=1) = head conv -> SSPN(n_blocks x SSB) + skip (AE.py:120-165)."""
+    y = F.conv2d(x, sd[p + ".head.weight"], sd[p + ".head.bias"], padding=1)
+    h = y
+    for b in range(n_blocks):
+        q = f"{p}.body.net.{b}"
+        # ResBlock k=3 (common.py:163-182): x + s*conv(act(conv(x)))
+        r = F.conv2d(h, sd[q + ".spa.body.0.weight"], sd[q + ".spa.body.0.bias"], padding=1)
+        r = F.conv2d(_lrelu(r), sd[q + ".spa.body.2.weight"], sd[q + ".spa.body.2.bias"], padding=1)
+        h = r * res_scale + h
+        # ResAttentionBlock k=1 + CALayer(reduction 3) (common.py:231-271)
+        r = F.conv2d(h, sd[q + ".spc.body.0.weight"], sd[q + ".spc.body.0.bias"])
+        r = F.conv2d(_lrelu(r), sd[q + ".spc.body.2.weight"], sd[q + ".spc.body.2.bias"])
+        w = r.mean(dim=(2, 3), keepdim=True)
+        w = F.relu(F.conv2d(w, sd[q + ".spc.body.3.conv_du.0.weight"], sd[q + ".spc.body.3.conv_du.0.bias"]))
+        w = torch.sigmoid(F.conv2d(w, sd[q + ".spc.body.3.conv_du.2.weight"], sd[q + ".spc.body.3.conv_du.2.bias"]))
+        h = (r * w) * res_scale + h
+    return h + y
+
+
+def _count_blocks(sd: SD, p: str) -> int:
+    n = 0
+    while f"{p}.body.net.{n}.spa.body.0.weight" in sd:
+        n += 1
+    return n
+
+
+def gae_coder(sd: SD, which: str, x: torch.Tensor) -> torch.Tensor:
+    """Encoder.forward / Decoder.forward (AE.py:195-199, 236-242): final(branch(x))."""
+    h = _branch(sd, which + ".branch", x, _count_blocks(sd, which + ".branch"))
+    return F.conv2d(h, sd[which + ".final.weight"], sd[which + ".final.bias"], padding=1)
+
+
+def gae_encode(sd: SD, geom: dict, x: torch.Tensor) -> List[torch.Tensor]:
+    """GAE.encode (AE.py:310-324) without the hard-coded 'cuda:0'."""
+    _, start, end = gae_groups(geom["n_colors"], geom["n_subs"], geom["n_ovls"])
+    return [gae_coder(sd, "Encoder", x[:, s:e]) for s, e in zip(start, end)]
+
+
+def gae_decode(sd: SD, geom: dict, x: torch.Tensor, z_list: Sequence[torch.Tensor]) -> torch.Tensor:
+    """GAE.decode (AE.py:283-308): overlap-accumulate, divide by band count, residual trunk."""
+    b, c, h, w = x.shape
+    _, start, end = gae_groups(geom["n_colors"], geom["n_subs"], geom["n_ovls"])
+    y = torch.zeros(b, c, h, w)
+    cnt = torch.zeros(c)
+    for g, (s, e) in enumerate(zip(start, end)):
+        y[:, s:e] += gae_coder(sd, "Decoder", z_list[g])
+        cnt[s:e] = cnt[s:e] + 1
+    y = y / cnt.unsqueeze(1).unsqueeze(2)
+    t = _branch(sd, "trunk", y, _count_blocks(sd, "trunk"))
+    t = F.conv2d(t, sd["final.weight"], sd["final.bias"], padding=1)
+    return t + y
+
+
+# --------------------------------------------------------------------------------------------------
+# val driver (sr_gae.py:456-475) and metrics (eval_hsi.py:47-65, 110-121)
+# --------------------------------------------------------------------------------------------------
+def sr_cube(unet_sd: SD, cfg: dict, tab, gae_sd: SD, geom: dict, sr: torch.Tensor, x_T: Sequence[torch.Tensor],
+            step_noise) -> torch.Tensor:
+    """One cube through encode -> per-group sampling (groups sequential, batch 1) -> decode -> clamp[0,1].
+
+    ``x_T[g]`` / ``step_noise(g, i)`` is the group-major noise tape of SURVEY.md 8d.
+    """
+    assert sr.shape[0] == 1
+    zs = gae_encode(gae_sd, geom, sr)
+    outs = []
+    for g, z in enumerate(zs):
+        r = sample_loop(unet_sd, cfg, tab, z, x_T[g], lambda i, g=g: step_noise(g, i), continous=False)
+        outs.append(r.unsqueeze(0))
+    return gae_decode(gae_sd, geom, sr, outs).clamp(0.0, 1.0)
+
+
+def mpsnr(x_true: np.ndarray, x_pred: np.ndarray, data_range: float = 1.0) -> float:
+    """compare_mpsnr over HWC arrays; skimage's PSNR is 10*log10(R^2/MSE) with float64 MSE."""
+    a = x_true.astype(np.float32).astype(np.float64)
+    b = x_pred.astype(np.float32).astype(np.float64)
+    mse = ((a - b) ** 2).mean(axis=(0, 1))
+    return float(np.mean(10.0 * np.log10(data_range ** 2 / mse)))
+
+
+def sam_deg(x_true: np.ndarray, x_pred: np.ndarray) -> float:
+    """compare_sam over HWC arrays: mean spectral angle (degrees) over pixels with non-zero norms."""
+    a = x_true.astype(np.float32).reshape(-1, x_true.shape[2])
+    b = x_pred.astype(np.float32).reshape(-1, x_pred.shape[2])
+    na = np.linalg.norm(a, axis=1)
+    nb = np.linalg.norm(b, axis=1)
+    ok = (na != 0) & (nb != 0)
+    cos = (a[ok] * b[ok]).sum(axis=1) / (na[ok] * nb[ok])
+    # the reference lets arccos produce nan for |cos|>1 by rounding; clip only by 1 ulp to stay defined
+    ang = np.arccos(np.clip(cos, -1.0, 1.0))
+    return float(ang.sum() / ok.sum() * 180.0 / np.pi)

@@ -1,0 +1,112 @@
+"""Pins oracle/hsidm_oracle.py against vectors produced by the unmodified reference (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from hsi_dmgasr_b200 import synth
+from oracle import hsidm_oracle as O
+from tests.cfgs import GAE_CASES, SMALL, UNET_CASES
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def rand(shape, seed):
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape, dtype=np.float32))
+
+
+@pytest.mark.parametrize("name,T", [("cosine", 20), ("cosine", 50), ("cosine", 2000), ("linear", 30), ("quad", 30),
+                                    ("warmup10", 30), ("warmup50", 30), ("const", 10), ("jsd", 10)])
+def test_schedule_tables_bit_exact(golden, name, T):
+    g = golden("schedules.npz")
+    with np.errstate(divide="ignore"):
+        tab = O.schedule_tables(O.beta_schedule(name, T, 1e-6, 1e-2))
+    for k, v in tab.items():
+        ref = g[f"{name}{T}.{k}"]
+        assert v.dtype == ref.dtype and v.shape == ref.shape
+        assert np.array_equal(v, ref, equal_nan=True), (name, T, k)
+
+
+def test_schedule_spot_values():
+    # SURVEY.md 8c spot values measured on the reference at T=50
+    tab = O.schedule_tables(O.beta_schedule("cosine", 50, 1e-6, 1e-2))
+    assert abs(tab["betas"][0] - 0.0017475) < 1e-7 and abs(tab["betas"][49] - 0.999) < 1e-7
+    assert abs(tab["sqrt_alphas_cumprod_prev"][1] - 0.99912586) < 1e-7
+    assert abs(tab["posterior_log_variance_clipped"][0] + 46.0517) < 1e-3
+
+
+@pytest.mark.parametrize("tag", list(UNET_CASES))
+def test_unet_forward_matches_reference(golden, tag):
+    cfg, seed, n, hw, lvls = UNET_CASES[tag]
+    g = golden("unet_forward.npz")
+    sd = synth.unet_state_dict(cfg, seed)
+    x = rand((n, 6, hw, hw), 1000 + seed)
+    lv = torch.tensor(lvls, dtype=torch.float32).view(n, 1)
+    taps = {}
+    with torch.no_grad():
+        y = O.unet_forward(sd, cfg.as_oracle_cfg(), x, lv, taps)
+    assert rel(y.numpy(), g[f"{tag}.eps"]) < 2e-6
+    for k, v in taps.items():
+        if f"{tag}.tap.{k}" in g:
+            assert rel(v.numpy(), g[f"{tag}.tap.{k}"]) < 2e-6, k
+        else:
+            fp = g[f"{tag}.fp.{k}"]
+            mine = np.array([v.mean().item(), v.std().item(), v.abs().max().item()])
+            assert np.allclose(mine, fp, rtol=1e-4, atol=1e-6), k
+
+
+def test_sample_loop_matches_reference(golden):
+    g = golden("sample_loop.npz")
+    T, n, hw = int(g["T"]), 2, 16
+    sd = synth.unet_state_dict(SMALL, 21)
+    tab = O.schedule_tables(O.beta_schedule("cosine", T, 1e-6, 1e-2))
+    cond = rand((n, 3, hw, hw), 31)
+    x_T, tape = synth.noise_tape(n, T, 3, hw, hw, seed=32)
+    eps_l, x_l = [], []
+    with torch.no_grad():
+        ret = O.sample_loop(sd, SMALL.as_oracle_cfg(), tab, cond, x_T, lambda i: tape[:, T - 1 - i], continous=True,
+                            record=lambda i, e, x: (eps_l.append(e), x_l.append(x)))
+        last = O.sample_loop(sd, SMALL.as_oracle_cfg(), tab, cond, x_T, lambda i: tape[:, T - 1 - i], continous=False)
+    assert rel(torch.stack(eps_l).numpy(), g["eps"]) < 5e-6
+    assert rel(torch.stack(x_l).numpy(), g["x"]) < 5e-6
+    assert ret.shape == g["ret_all"].shape and rel(ret.numpy(), g["ret_all"]) < 5e-6
+    assert last.shape == g["ret_last"].shape == (3, hw, hw) and rel(last.numpy(), g["ret_last"]) < 5e-6
+
+
+@pytest.mark.parametrize("tag", list(GAE_CASES))
+def test_gae_matches_reference(golden, tag):
+    geom, seed, hw = GAE_CASES[tag]
+    g = golden("gae.npz")
+    G, start, end = O.gae_groups(geom.n_colors, geom.n_subs, geom.n_ovls)
+    assert start == list(g[f"{tag}.start"]) and end == list(g[f"{tag}.end"]) and G == geom.G
+    assert (start, end) == geom.groups()
+    sd = synth.gae_state_dict(geom, seed)
+    x = synth.sr_cube(2, geom.n_colors, hw, seed=seed + 100)
+    with torch.no_grad():
+        zs = O.gae_encode(sd, geom.as_oracle_geom(), x)
+        y = O.gae_decode(sd, geom.as_oracle_geom(), x, zs)
+    assert rel(torch.stack(zs).numpy(), g[f"{tag}.z"]) < 2e-6
+    assert rel(y.numpy(), g[f"{tag}.dec"]) < 2e-6
+
+
+def test_end_to_end_cube_and_metrics(golden):
+    from hsi_dmgasr_b200.spec import GAEGeometry
+    g = golden("e2e.npz")
+    geom, T, hw = GAEGeometry(31, 8, 2), int(g["T"]), 16
+    gsd = synth.gae_state_dict(geom, 51)
+    usd = synth.unet_state_dict(SMALL, 52)
+    tab = O.schedule_tables(O.beta_schedule("cosine", T, 1e-6, 1e-2))
+    sr = synth.sr_cube(1, 31, hw, seed=53)
+    hr = synth.sr_cube(1, 31, hw, seed=54)
+    x_T, tape = synth.noise_tape(geom.G, T, 3, hw, hw, seed=55)
+    with torch.no_grad():
+        cube = O.sr_cube(usd, SMALL.as_oracle_cfg(), tab, gsd, geom.as_oracle_geom(), sr,
+                         [x_T[i:i + 1] for i in range(geom.G)], lambda gi, i: tape[gi:gi + 1, T - 1 - i])
+    assert rel(cube.numpy(), g["cube"]) < 1e-5
+    pred = cube[0].permute(1, 2, 0).numpy()
+    true = hr[0].permute(1, 2, 0).numpy()
+    assert abs(O.sam_deg(true, pred) - float(g["sam"])) < 1e-3          # reference compare_sam (python loop)
+    assert abs(O.mpsnr(true, pred) - float(g["mpsnr"])) < 1e-4
