@@ -1,0 +1,89 @@
+// Library-level C ABI entry points and the test hooks of include/hsidm_debug.h.
+#include "../../include/hsidm_debug.h"
+#include "net.cuh"
+
+using namespace hsidm;
+
+extern "C" {
+
+int hsidm_version(void) { return HSIDM_VERSION; }
+const char* hsidm_last_error(void) { return g_last_error.c_str(); }
+int64_t hsidm_launch_count(void) { return g_launches; }
+
+int hsidm_debug_conv2d(int backend, int precision, const void* src0, int c0, const void* src1, int c1, int src_layout,
+                       int N, int H, int W, int up, int stride, const float* weight, const float* bias, int Cout,
+                       int ksize, const float* nbias, int64_t nbias_stride, int act, float scale, const void* resid,
+                       void* out, int out_layout) {
+  if (!src0 || !weight || !out) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_debug_conv2d: null argument");
+  ParamStore ps;
+  ConvW w = make_conv(ps, "w", c0 + c1, Cout, ksize, bias != nullptr);
+  HSIDM_TRY(ps.alloc_all());
+  int64_t wshape[4] = {Cout, c0 + c1, ksize, ksize};
+  HSIDM_TRY(ps.set("w.weight", weight, wshape, 4));
+  int64_t bshape[1] = {Cout};
+  if (bias) HSIDM_TRY(ps.set("w.bias", bias, bshape, 1));
+  if (precision == HSIDM_BF16) HSIDM_TRY(conv_tc_init());
+  int s = pack_conv(ps, w, precision == HSIDM_BF16);
+  if (s != HSIDM_OK) {
+    free_conv(w);
+    return s;
+  }
+  ConvOp op;
+  op.src[0].p = src0, op.src[0].C = c0, op.src[0].layout = src_layout;
+  if (c1) op.src[1].p = src1, op.src[1].C = c1, op.src[1].layout = src_layout;
+  op.N = N, op.Hin = H, op.Win = W, op.up = up, op.stride = stride, op.ksize = ksize;
+  const int He = up ? 2 * H : H, We = up ? 2 * W : W;
+  op.Hout = stride == 2 ? (He + 1) / 2 : He, op.Wout = stride == 2 ? (We + 1) / 2 : We;
+  op.Cout = Cout;
+  op.nbias = nbias, op.nbias_stride = nbias_stride, op.act = act, op.scale = scale, op.resid = resid;
+  op.out = out, op.out_layout = out_layout;
+  if (backend == 2) {
+    Exec ex;
+    ex.prec = precision;
+    ex.arena.begin(true), ex.dry = true;
+    run_conv(ex, op, w, ps);
+    s = ex.arena.reserve(ex.arena.peak() + 1024);
+    if (s == HSIDM_OK) {
+      ex.arena.begin(false), ex.dry = false, ex.status = HSIDM_OK;
+      run_conv(ex, op, w, ps);
+      s = ex.status;
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess && s == HSIDM_OK) {
+      set_last_error("kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+      s = HSIDM_CUDA_ERROR;
+    }
+    free_conv(w);
+    return s;
+  }
+  op.w_f32 = w.w_f32, op.w_bf16 = w.w_bf16, op.bias = ps.dev(w.pb);
+  s = backend == 1 ? conv_tc(op, nullptr) : conv_simt(op, precision, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess && s == HSIDM_OK) {
+    set_last_error("kernel failed: %s", cudaGetErrorString(e));
+    s = HSIDM_CUDA_ERROR;
+  }
+  free_conv(w);
+  return s;
+}
+
+int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const void* x1, int c1, int N, int HW, int groups,
+                          const float* gamma, const float* beta, float eps, int swish, void* out) {
+  double* gsum = nullptr;
+  HSIDM_CUDA(cudaMalloc(&gsum, sizeof(double) * 2 * N * groups));
+  int s = gn_stats(x0, c0, x1, c1, N, HW, groups, gsum, precision, nullptr);
+  if (s == HSIDM_OK) s = gn_apply(x0, c0, x1, c1, N, HW, groups, gsum, gamma, beta, eps, swish, out, precision, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(gsum);
+  if (e != cudaSuccess && s == HSIDM_OK) {
+    set_last_error("kernel failed: %s", cudaGetErrorString(e));
+    s = HSIDM_CUDA_ERROR;
+  }
+  return s;
+}
+
+int hsidm_debug_tc_error_flag(int* value) {
+  if (!value) HSIDM_FAIL(HSIDM_BAD_ARG, "null argument");
+  return conv_tc_error_flag(value);
+}
+
+}  // extern "C"

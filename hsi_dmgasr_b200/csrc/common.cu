@@ -1,0 +1,115 @@
+// Error state, launch counter and the stream-ordered workspace arena.
+#include "common.cuh"
+
+namespace hsidm {
+
+thread_local std::string g_last_error;
+int64_t g_launches = 0;
+
+void set_last_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+static constexpr int64_t kAlign = 1024;
+static char* const kDryBase = reinterpret_cast<char*>(uintptr_t(1) << 40);  // never dereferenced
+
+Arena::~Arena() {
+  if (base_) cudaFree(base_);
+}
+
+int Arena::reserve(int64_t bytes) {
+  if (bytes <= cap_) return HSIDM_OK;
+  if (base_) {
+    HSIDM_CUDA(cudaDeviceSynchronize());
+    HSIDM_CUDA(cudaFree(base_));
+    base_ = nullptr;
+    cap_ = 0;
+  }
+  bytes = round_up(bytes, 1 << 20);
+  cudaError_t e = cudaMalloc(&base_, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    base_ = nullptr;
+    HSIDM_FAIL(HSIDM_OOM_WORKSPACE, "workspace of %lld bytes could not be allocated: %s", (long long)bytes,
+               cudaGetErrorString(e));
+  }
+  cap_ = bytes;
+  return HSIDM_OK;
+}
+
+void Arena::begin(bool dry) {
+  dry_ = dry;
+  failed_ = false;
+  nblocks_ = 0;
+  top_ = 0;
+  if (dry) peak_ = 0;
+}
+
+void* Arena::alloc(int64_t bytes) {
+  bytes = round_up(bytes < 1 ? 1 : bytes, kAlign);
+  char* base = dry_ ? kDryBase : base_;
+  int best = -1;
+  for (int i = 0; i < nblocks_; ++i)
+    if (!blocks_[i].used && blocks_[i].size >= bytes && (best < 0 || blocks_[i].size < blocks_[best].size)) best = i;
+  if (best >= 0) {
+    Block& b = blocks_[best];
+    if (b.size > bytes && nblocks_ < kMaxBlocks) {  // split, keep the list sorted by offset
+      for (int j = nblocks_; j > best + 1; --j) blocks_[j] = blocks_[j - 1];
+      blocks_[best + 1] = Block{b.off + bytes, b.size - bytes, false};
+      ++nblocks_;
+      blocks_[best].size = bytes;
+    }
+    blocks_[best].used = true;
+    return base + blocks_[best].off;
+  }
+  if (nblocks_ >= kMaxBlocks) {
+    failed_ = true;
+    return nullptr;
+  }
+  // grow at the top (absorbing a trailing free block)
+  int64_t off = top_;
+  if (nblocks_ > 0 && !blocks_[nblocks_ - 1].used) {
+    off = blocks_[nblocks_ - 1].off;
+    --nblocks_;
+  }
+  blocks_[nblocks_++] = Block{off, bytes, true};
+  top_ = off + bytes;
+  if (top_ > peak_) peak_ = top_;
+  if (!dry_ && top_ > cap_) {
+    failed_ = true;
+    return nullptr;
+  }
+  return base + off;
+}
+
+void Arena::free(void* p) {
+  if (!p) return;
+  char* base = dry_ ? kDryBase : base_;
+  int64_t off = static_cast<char*>(p) - base;
+  for (int i = 0; i < nblocks_; ++i) {
+    if (blocks_[i].off != off || !blocks_[i].used) continue;
+    blocks_[i].used = false;
+    if (i + 1 < nblocks_ && !blocks_[i + 1].used) {  // merge right
+      blocks_[i].size += blocks_[i + 1].size;
+      for (int j = i + 1; j + 1 < nblocks_; ++j) blocks_[j] = blocks_[j + 1];
+      --nblocks_;
+    }
+    if (i > 0 && !blocks_[i - 1].used) {  // merge left
+      blocks_[i - 1].size += blocks_[i].size;
+      for (int j = i; j + 1 < nblocks_; ++j) blocks_[j] = blocks_[j + 1];
+      --nblocks_;
+    }
+    if (nblocks_ > 0 && !blocks_[nblocks_ - 1].used) {  // give the tail back
+      top_ = blocks_[nblocks_ - 1].off;
+      --nblocks_;
+    }
+    return;
+  }
+}
+
+}  // namespace hsidm

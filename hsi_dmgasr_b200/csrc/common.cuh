@@ -1,0 +1,163 @@
+// Shared host/device helpers for the hsidm kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/hsidm.h"
+
+namespace hsidm {
+
+// ---- error plumbing -------------------------------------------------------------------------------
+struct Error {
+  int code;
+  std::string msg;
+};
+void set_last_error(const char* fmt, ...);
+extern thread_local std::string g_last_error;
+extern int64_t g_launches;  // kernels launched by this library (bench.py reports it)
+
+#define HSIDM_FAIL(code, ...)            \
+  do {                                   \
+    ::hsidm::set_last_error(__VA_ARGS__); \
+    return (code);                       \
+  } while (0)
+
+#define HSIDM_CUDA(expr)                                                                       \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::hsidm::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                              __LINE__);                                                       \
+      return HSIDM_CUDA_ERROR;                                                                 \
+    }                                                                                          \
+  } while (0)
+
+#define HSIDM_TRY(expr)        \
+  do {                         \
+    int _s = (expr);           \
+    if (_s != HSIDM_OK) return _s; \
+  } while (0)
+
+inline int after_launch(const char* what) {
+  ++g_launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_last_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+    return HSIDM_CUDA_ERROR;
+  }
+  return HSIDM_OK;
+}
+
+// ---- activation element types ------------------------------------------------------------------------
+using bf16 = __nv_bfloat16;
+
+template <typename T>
+struct ActTraits;
+template <>
+struct ActTraits<float> {
+  static constexpr int kPrecision = HSIDM_F32;
+};
+template <>
+struct ActTraits<bf16> {
+  static constexpr int kPrecision = HSIDM_BF16;
+};
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ bf16 from_f32<bf16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// 8 consecutive activations <-> 8 floats (16 B for bf16, 32 B for fp32); pointers must be so aligned.
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+__device__ __forceinline__ float swish_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---- activation tensor handle (NHWC, element type decided by the context precision) ----------------------
+struct Act {
+  void* p = nullptr;
+  int N = 0, H = 0, W = 0, C = 0;
+  int64_t numel() const { return (int64_t)N * H * W * C; }
+};
+
+// ---- stream-ordered workspace arena --------------------------------------------------------------------
+// All kernels of one context run on one stream in program order, so a block can be handed out again as soon
+// as the host code that consumed it has *enqueued* its last reader.  Dry mode only measures the peak.
+class Arena {
+ public:
+  ~Arena();
+  int reserve(int64_t bytes);  // (re)allocate backing store; synchronises when it has to grow
+  void begin(bool dry);        // start a pass; every block must have been freed
+  void* alloc(int64_t bytes);
+  void free(void* p);
+  int64_t peak() const { return peak_; }
+  int64_t capacity() const { return cap_; }
+  bool dry() const { return dry_; }
+  bool failed() const { return failed_; }
+
+ private:
+  struct Block {
+    int64_t off, size;
+    bool used;
+  };
+  char* base_ = nullptr;
+  int64_t cap_ = 0, peak_ = 0, top_ = 0;
+  bool dry_ = false, failed_ = false;
+  static constexpr int kMaxBlocks = 512;
+  Block blocks_[kMaxBlocks];
+  int nblocks_ = 0;
+};
+
+}  // namespace hsidm

@@ -1,0 +1,524 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+// GEMM view of a 3x3 (pad 1) or 1x1 stride-1 convolution over NHWC activations:
+//   D[m, co] = sum_{tap, c} X[n, y+ky-1, x+kx-1, c] * Wt[co, tap*Ctot + c]       m = (n, y, x)
+// A tile  : 128 output pixels x 64 channels of ONE tap = one 4-D TMA box {64, bw, bh, bn} (bw*bh*bn = 128) of the
+//           NHWC tensor at coordinates shifted by the tap; out-of-bounds rows/cols are zero-filled by the TMA unit,
+//           which is exactly the conv padding.  No im2col buffer exists anywhere.  Rows land in shared memory as
+//           128-byte lines with the 128B swizzle -> canonical K-major SWIZZLE_128B UMMA operand.
+// B tile  : BN output channels x 64 k of the pre-packed K-major weight matrix, one 2-D TMA box.
+// MMA     : tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 (x4 per 64-wide k-block), issued by one thread.
+// D       : fp32 in TMEM, double buffered (2*BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Epilogue: 4 warps, tcgen05.ld 32x32b -> +bias +noise-embedding bias -> activation -> *scale -> +residual ->
+//           bf16 NHWC (or fp32 NCHW for the last layer) straight to global memory.
+// Two NHWC sources may be given; their channels are consumed as consecutive K ranges (virtual torch.cat, unet.py:259).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Persistent: grid = min(#tiles, #SMs); tiles are walked n-tile-fastest so the CTAs in flight share A tiles in L2.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "kernels.cuh"
+
+namespace hsidm {
+namespace {
+
+constexpr int kBM = 128;       // UMMA M
+constexpr int kBK = 64;        // bf16 elements per k-block = one 128-byte swizzle line
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+struct TcP {
+  int M, N_img, H, W, Cout;
+  int bw, bh, bn;          // box extents: x, y, image
+  int tiles_x, tiles_y;    // tiles per image along x / y (bn == 1)
+  int m_tiles, n_tiles;
+  int taps;                // 1 or 9
+  int chunks0, chunks1;    // 64-channel chunks taken from source 0 / source 1
+  const float* bias;
+  const float* nbias;
+  long long nbs;
+  const int* nb_t;
+  long long nb_ts;
+  int act;
+  float scale;
+  const bf16* resid;
+  void* out;
+  int out_layout, clamp01;
+  int* err;                // device flag set when a barrier wait times out (never in a healthy run)
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a descriptor or protocol bug must not hang the GPU box.  Returns false on timeout.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  for (uint32_t i = 0; i < kSpinLimit; ++i)
+    if (mbar_try_wait(bar, parity)) return true;
+  if (err) atomicExch(err, code);
+  return false;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row groups are 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB, const TcP p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tail = smem + C::kStages * C::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int kblocks = p.taps * (p.chunks0 + p.chunks1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.chunks1) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        int n0, y0, x0;
+        if (p.bn > 1) {
+          n0 = mt * p.bn, y0 = 0, x0 = 0;
+        } else {
+          const int tpi = p.tiles_x * p.tiles_y;
+          n0 = mt / tpi;
+          const int r = mt - n0 * tpi;
+          y0 = (r / p.tiles_x) * p.bh;
+          x0 = (r % p.tiles_x) * p.bw;
+        }
+        int kb = 0;
+        for (int tap = 0; tap < p.taps && ok; ++tap) {
+          const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          for (int ch = 0; ch < p.chunks0 + p.chunks1; ++ch, ++kb) {
+            ok = mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
+            if (!ok) break;
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+            mbar_expect_tx(fb, C::kStageBytes);
+            if (ch < p.chunks0)
+              tma_load_4d(sa, &tmA0, fb, ch * kBK, x0 + dx, y0 + dy, n0);
+            else
+              tma_load_4d(sa, &tmA1, fb, (ch - p.chunks0) * kBK, x0 + dx, y0 + dy, n0);
+            tma_load_2d(sa + C::kABytes, &tmB, fb, kb * kBK, nt * BN);
+            if (++stage == C::kStages) stage = 0, phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        ok = mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 2);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          ok = mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)  // +32 bytes (encoded +2) per K=16 slice inside the swizzle line
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == C::kStages) stage = 0, phase ^= 1;
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));
+        if (++acc == 2) acc = 0, acc_phase ^= 1;
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;     // accumulator row = pixel within the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int HW = p.H * p.W;
+    const float* nbias = p.nbias ? p.nbias + (p.nb_t ? (long long)(*p.nb_t) * p.nb_ts : 0) : nullptr;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      int n, y, x;
+      if (p.bn > 1) {
+        n = mt * p.bn + row / (p.bw * p.bh);
+        const int r = row % (p.bw * p.bh);
+        y = r / p.bw, x = r % p.bw;
+      } else {
+        const int tpi = p.tiles_x * p.tiles_y;
+        n = mt / tpi;
+        const int r = mt - n * tpi;
+        y = (r / p.tiles_x) * p.bh + row / p.bw;
+        x = (r % p.tiles_x) * p.bw + row % p.bw;
+      }
+      const bool valid = n < p.N_img;
+      const long long m = ((long long)n * p.H + y) * p.W + x;
+      ok = mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 4);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        const int co0 = nt * BN + c0;
+        if (valid && co0 < p.Cout) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.out_layout == L_NHWC) {
+            // Cout is a multiple of 16 on this path
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
+                v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+              }
+            }
+            if (nbias) {
+              const float* nb = nbias + (long long)n * p.nbs + co0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(nb + j));
+                v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+              }
+            }
+            if (p.act == ACT_LRELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
+            }
+            if (p.scale != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] *= p.scale;
+            }
+            if (p.resid) {
+              const bf16* rp = p.resid + m * p.Cout + co0;
+              float a[8], b[8];
+              load8(rp, a);
+              load8(rp + 8, b);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += a[j], v[8 + j] += b[j];
+            }
+            bf16* op = static_cast<bf16*>(p.out) + m * p.Cout + co0;
+            float lo[8], hi[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) lo[j] = v[j], hi[j] = v[8 + j];
+            store8(op, lo);
+            store8(op + 8, hi);
+          } else {
+            // fp32 NCHW (last UNet layer / GAE outputs): a handful of channels, scalar tail-safe path
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = co0 + j;
+              if (co < p.Cout) {
+                float o = v[j];
+                if (p.bias) o += __ldg(p.bias + co);
+                if (nbias) o += __ldg(nbias + (long long)n * p.nbs + co);
+                if (p.act == ACT_LRELU) o = o > 0.f ? o : 0.01f * o;
+                o *= p.scale;
+                if (p.clamp01) o = fminf(fmaxf(o, 0.f), 1.f);
+                static_cast<float*>(p.out)[((long long)n * p.Cout + co) * HW + (long long)y * p.W + x] = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) acc = 0, acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 0;
+int* g_err_flag = nullptr;
+std::once_flag g_once;
+int g_init_status = HSIDM_OK;
+
+int do_init() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  HSIDM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess)
+    HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  int dev = 0;
+  HSIDM_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  HSIDM_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<16>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmemBytes));
+  HSIDM_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
+  HSIDM_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
+  return HSIDM_OK;
+}
+
+int encode_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: %d", N, H, W, C, (int)r);
+  return HSIDM_OK;
+}
+
+int encode_weight_map(CUtensorMap* map, const void* base, int K, int rows, int bn_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)bn_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled(weights %dx%d) failed: %d", rows, K, (int)r);
+  return HSIDM_OK;
+}
+
+bool tile_geometry(int H, int W, int* bw, int* bh, int* bn) {
+  if (W >= kBM) {
+    if (W % kBM) return false;
+    *bw = kBM, *bh = 1, *bn = 1;
+    return true;
+  }
+  if (W <= 0 || (kBM % W)) return false;
+  *bw = W;
+  int rows = kBM / W;
+  if (H >= rows) {
+    if (H % rows) return false;
+    *bh = rows, *bn = 1;
+    return true;
+  }
+  if (rows % H) return false;
+  *bh = H, *bn = rows / H;
+  return true;
+}
+
+int pick_bn(int Cout) {
+  if (Cout <= 16) return 16;
+  if (Cout % 256 == 0) return 256;
+  if (Cout % 128 == 0) return 128;
+  if (Cout % 64 == 0) return 64;
+  return 0;
+}
+
+}  // namespace
+
+int conv_tc_init() {
+  std::call_once(g_once, [] { g_init_status = do_init(); });
+  return g_init_status;
+}
+
+int conv_tc_bn_rows(int Cout) { return pick_bn(Cout); }
+
+bool conv_tc_supported(const ConvOp& op, int prec) {
+  if (prec != HSIDM_BF16 || !op.w_bf16) return false;
+  if (op.stride != 1 || op.up || (op.ksize != 1 && op.ksize != 3)) return false;
+  if (op.src[0].layout != L_NHWC || op.src[0].C % kBK) return false;
+  if (op.src[1].C && (op.src[1].layout != L_NHWC || op.src[1].C % kBK)) return false;
+  if (op.Hout != op.Hin || op.Wout != op.Win) return false;
+  if (pick_bn(op.Cout) == 0) return false;
+  if (op.out_layout == L_NHWC && op.Cout % 16) return false;
+  if (op.out_layout != L_NHWC && op.resid) return false;
+  int bw, bh, bn;
+  return tile_geometry(op.Hin, op.Win, &bw, &bh, &bn);
+}
+
+int conv_tc(const ConvOp& op, cudaStream_t stream) {
+  HSIDM_TRY(conv_tc_init());
+  if (!conv_tc_supported(op, HSIDM_BF16))
+    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: op (Cin %d+%d, Cout %d, k%d s%d, %dx%d) does not fit the tensor-core kernel",
+               op.src[0].C, op.src[1].C, op.Cout, op.ksize, op.stride, op.Hin, op.Win);
+  TcP p;
+  tile_geometry(op.Hin, op.Win, &p.bw, &p.bh, &p.bn);
+  const int BN = pick_bn(op.Cout);
+  p.N_img = op.N, p.H = op.Hin, p.W = op.Win, p.Cout = op.Cout;
+  p.M = op.N * op.Hin * op.Win;
+  p.tiles_x = op.Win / p.bw;
+  p.tiles_y = op.Hin / p.bh;
+  p.m_tiles = p.bn > 1 ? (int)ceil_div(op.N, p.bn) : op.N * p.tiles_x * p.tiles_y;
+  p.n_tiles = (int)ceil_div(op.Cout, BN);
+  p.taps = op.ksize * op.ksize;
+  p.chunks0 = op.src[0].C / kBK;
+  p.chunks1 = op.src[1].C / kBK;
+  p.bias = op.bias, p.nbias = op.nbias, p.nbs = op.nbias_stride, p.nb_t = op.nbias_t, p.nb_ts = op.nbias_t_stride, p.act = op.act, p.scale = op.scale;
+  p.resid = static_cast<const bf16*>(op.resid), p.out = op.out, p.out_layout = op.out_layout, p.clamp01 = op.clamp01;
+  p.err = g_err_flag;
+
+  CUtensorMap tmA0, tmA1, tmB;
+  HSIDM_TRY(encode_act_map(&tmA0, op.src[0].p, op.N, op.Hin, op.Win, op.src[0].C, p.bw, p.bh, p.bn));
+  if (p.chunks1)
+    HSIDM_TRY(encode_act_map(&tmA1, op.src[1].p, op.N, op.Hin, op.Win, op.src[1].C, p.bw, p.bh, p.bn));
+  else
+    tmA1 = tmA0;
+  const int K = op.K();
+  HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, BN));
+
+  const int grid = std::min(p.m_tiles * p.n_tiles, g_num_sms);
+  switch (BN) {
+    case 16: conv_tc_kernel<16><<<grid, kThreads, Cfg<16>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;
+    case 64: conv_tc_kernel<64><<<grid, kThreads, Cfg<64>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;
+    case 128: conv_tc_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;
+    default: conv_tc_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;
+  }
+  return after_launch("conv_tc_kernel");
+}
+
+// Reads and clears the barrier-timeout flag (0 = healthy). Synchronises the device; test/debug use only.
+int conv_tc_error_flag(int* value) {
+  *value = 0;
+  if (!g_err_flag) return HSIDM_OK;
+  HSIDM_CUDA(cudaDeviceSynchronize());
+  HSIDM_CUDA(cudaMemcpy(value, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  HSIDM_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
+  return HSIDM_OK;
+}
+
+}  // namespace hsidm

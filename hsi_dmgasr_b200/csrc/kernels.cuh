@@ -1,0 +1,125 @@
+// Host-side launch interface of every hsidm kernel.  All launchers enqueue on `stream` and return an
+// hsidm_status; none synchronises.  `prec` selects the activation element type (HSIDM_F32 / HSIDM_BF16).
+#pragma once
+#include "common.cuh"
+
+namespace hsidm {
+
+enum ActFn { ACT_NONE = 0, ACT_LRELU = 1 };
+enum TensorLayout { L_NHWC = 0, L_NCHW_F32 = 1 };
+
+// One input of a convolution.  NHWC sources hold the context's activation type; NCHW sources are the
+// caller's fp32 tensors in the reference layout (first UNet conv, GAE head convs).
+struct ConvSrc {
+  const void* p = nullptr;
+  int C = 0;
+  int layout = L_NHWC;
+  const int64_t* img_off = nullptr;  // NCHW only: per-image element offset (device); null -> n*C*H*W
+};
+
+// out = [clamp01]( act(conv(cat(src0,src1)) + bias + nbias[n]) * scale + resid )
+struct ConvOp {
+  ConvSrc src[2];
+  int N = 0, Hin = 0, Win = 0;  // source spatial size
+  int up = 0;                   // 1: source is nearest-2x upsampled on the fly (unet.py:58-65)
+  int ksize = 3, stride = 1;    // padding = ksize/2
+  int Hout = 0, Wout = 0, Cout = 0;
+  const float* w_f32 = nullptr;  // [K][Cout], k = tap*(C0+C1) + c
+  const bf16* w_bf16 = nullptr;  // [Cout][K]   (tensor-core path)
+  const float* bias = nullptr;
+  const float* nbias = nullptr;  // noise-embedding bias, element (n, co) at nbias[t*nbias_t_stride + n*nbias_stride + co]
+  int64_t nbias_stride = 0;
+  const int* nbias_t = nullptr;  // optional device-side timestep index t (CUDA-graph replay); null -> t = 0
+  int64_t nbias_t_stride = 0;
+  int act = ACT_NONE;
+  float scale = 1.0f;
+  const void* resid = nullptr;  // NHWC activation [N,Hout,Wout,Cout]
+  void* out = nullptr;
+  int out_layout = L_NHWC;
+  int clamp01 = 0;
+  int K() const { return ksize * ksize * (src[0].C + src[1].C); }
+};
+
+// conv_simt.cu : CUDA-core implicit GEMM, fp32 accumulate; handles every ConvOp.
+int conv_simt(const ConvOp& op, int prec, cudaStream_t stream);
+// conv_tc.cu : tcgen05/TMEM/TMA implicit GEMM (bf16 operands).  conv_tc_supported() says whether an op
+// fits the tensor-core kernel's constraints; conv_tc() fails loudly otherwise.
+bool conv_tc_supported(const ConvOp& op, int prec);
+int conv_tc(const ConvOp& op, cudaStream_t stream);
+int conv_tc_init();               // resolves cuTensorMapEncodeTiled, sets kernel attributes
+int conv_tc_bn_rows(int Cout);    // N-tile height; packed bf16 weights are padded to a multiple of it (0 = unsupported)
+int conv_tc_error_flag(int* v);   // barrier-timeout flag of the tensor-core kernel (synchronises; tests only)
+
+// Batched GEMM on CUDA cores: C[b] = alpha * A[b] (MxK, row-major lda) * op(B[b]); B is [N][K] (transB=1)
+// or [K][N] (transB=0). A/B hold the activation type, C is fp32 (c_f32=1) or the activation type.
+struct GemmOp {
+  const void* A = nullptr;
+  const void* B = nullptr;
+  void* C = nullptr;
+  int M = 0, N = 0, K = 0;
+  int64_t lda = 0, ldb = 0, ldc = 0, sA = 0, sB = 0, sC = 0;
+  int batch = 1, transB = 1, a_f32 = 0, c_f32 = 0;
+  float alpha = 1.0f;
+};
+int gemm_simt(const GemmOp& op, int prec, cudaStream_t stream);
+int softmax_rows(float* x, int64_t rows, int cols, cudaStream_t stream);  // in place, fp32
+
+// GroupNorm over the (virtual) concatenation of two NHWC tensors with the same N,H,W.
+// gsum: [N][groups][2] doubles (sum, sum of squares); zeroed by gn_stats itself.
+int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, double* gsum, int prec,
+             cudaStream_t stream);
+int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const double* gsum,
+             const float* gamma, const float* beta, float eps, int swish, void* out, int prec, cudaStream_t stream);
+
+int upsample2x(const void* x, void* out, int N, int H, int W, int C, int prec, cudaStream_t stream);
+// Stride-2 3x3 im2col for the tensor-core path: out [N,H/2,W/2,9*C] (bf16).
+int im2col_s2(const void* x, void* out, int N, int H, int W, int C, cudaStream_t stream);
+
+// Noise-level embedding (unet.py:18-31, 182-187) followed by every FeatureWiseAffine linear (unet.py:34-50).
+struct NoiseLayer {
+  const float* w;  // [C][dim]
+  const float* b;  // [C]
+  int C, off;
+};
+int noise_embed(const float* level, int level_stride, int n, int dim, const float* w1, const float* b1,
+                const float* w3, const float* b3, const NoiseLayer* layers_dev, int n_layers, int total,
+                float* nbias /*[n][total]*/, cudaStream_t stream);
+
+// Fused DDPM posterior step (diffusion.py:142-175). coef: device [T][5] = {recip, recipm1, c1, c2, sigma}.
+// t_dev (optional) overrides t with *t_dev (graph replay). noise == null -> zeros; philox != 0 -> in-kernel RNG.
+struct PosteriorArgs {
+  const float* x_t;
+  const float* eps;
+  const float* noise;
+  float* x_prev;
+  int64_t n;           // elements
+  int64_t per_image;   // elements per image (C*H*W), used to index the tape
+  int64_t tape_image_stride, tape_step_stride;
+  const float* coef;
+  int T;
+  int t;               // loop index (host known) or -1 -> read *t_dev
+  const int* t_dev;
+  uint64_t seed;
+  const unsigned long long* seed_dev;  // optional: overrides seed (graph replay)
+  int use_philox;
+  float* snapshot_base;   // optional: [n_snap][n] written when i % inter == 0
+  int inter;
+};
+int posterior_step(const PosteriorArgs& a, cudaStream_t stream);
+int step_counter_dec(int* t_dev, cudaStream_t stream);  // *t_dev -= 1
+// state[0] = t (int), state[2..3] = seed (uint64): set from kernel arguments so no host buffer has to outlive the call
+int sampler_state_set(int* state, int t, uint64_t seed, cudaStream_t stream);
+
+// GAE pieces (common.py:231-271, AE.py:288-295).
+int channel_mean(const void* x, int N, int HW, int C, float* mean /*[N][C]*/, int prec, cudaStream_t stream);
+int ca_gate(const float* mean, int N, int C, int Cr, const float* w0, const float* b0, const float* w1,
+            const float* b1, float* gate /*[N][C]*/, cudaStream_t stream);
+// out = x * gate[n][c] * scale + resid
+int scale_residual(const void* x, const float* gate, float scale, const void* resid, void* out, int N, int HW, int C,
+                   int prec, cudaStream_t stream);
+// y[b, band] = sum_g dec[b*G+g, band - start[g]] / count[band]; dec NHWC [B*G,H,W,n_subs]; writes NHWC act
+// [B,H,W,n_colors] (trunk input) and keeps fp32 precision by also writing y_f32 NHWC when non-null.
+int overlap_average(const void* dec, int B, int G, int HW, int n_subs, int n_colors, const int* start_dev,
+                    const float* inv_count_dev, void* y, int prec, cudaStream_t stream);
+
+}  // namespace hsidm

@@ -1,0 +1,165 @@
+#include "net.cuh"
+
+#include <cstring>
+
+namespace hsidm {
+
+// ---- ParamStore ---------------------------------------------------------------------------------------------
+ParamStore::~ParamStore() {
+  if (slab_) cudaFree(slab_);
+}
+
+int ParamStore::add(const std::string& key, std::vector<int64_t> shape) {
+  Param p;
+  p.key = key;
+  p.shape = std::move(shape);
+  params_.push_back(std::move(p));
+  return (int)params_.size() - 1;
+}
+
+int ParamStore::find(const std::string& key) const {
+  for (int i = 0; i < (int)params_.size(); ++i)
+    if (params_[i].key == key) return i;
+  return -1;
+}
+
+int ParamStore::alloc_all() {
+  int64_t total = 0;
+  for (auto& p : params_) total += round_up(p.numel(), 64);
+  slab_bytes_ = total * (int64_t)sizeof(float);
+  HSIDM_CUDA(cudaMalloc(&slab_, slab_bytes_));
+  HSIDM_CUDA(cudaMemset(slab_, 0, slab_bytes_));
+  int64_t off = 0;
+  for (auto& p : params_) {
+    p.dev = slab_ + off;
+    off += round_up(p.numel(), 64);
+  }
+  return HSIDM_OK;
+}
+
+int ParamStore::set(const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (!key || !data) HSIDM_FAIL(HSIDM_BAD_ARG, "set_param: null key or data");
+  int idx = find(key);
+  if (idx < 0) HSIDM_FAIL(HSIDM_BAD_ARG, "set_param: unknown parameter '%s'", key);
+  Param& p = params_[idx];
+  bool same = ndim == (int)p.shape.size();
+  for (int i = 0; same && i < ndim; ++i) same = shape[i] == p.shape[i];
+  if (!same) {
+    std::string want, got;
+    for (auto d : p.shape) want += std::to_string(d) + ",";
+    for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+    HSIDM_FAIL(HSIDM_BAD_SHAPE, "set_param: '%s' expects shape [%s] but got [%s]", key, want.c_str(), got.c_str());
+  }
+  HSIDM_CUDA(cudaMemcpy(p.dev, data, sizeof(float) * p.numel(), cudaMemcpyDefault));
+  p.set = true;
+  return HSIDM_OK;
+}
+
+int ParamStore::check_all_set() const {
+  for (auto& p : params_)
+    if (!p.set) HSIDM_FAIL(HSIDM_BAD_STATE, "commit: parameter '%s' was never set", p.key.c_str());
+  return HSIDM_OK;
+}
+
+// ---- conv weights -------------------------------------------------------------------------------------------
+ConvW make_conv(ParamStore& ps, const std::string& prefix, int Cin, int Cout, int ks, bool bias) {
+  ConvW c;
+  c.Cin = Cin, c.Cout = Cout, c.ks = ks;
+  c.pw = ps.add(prefix + ".weight", {Cout, Cin, ks, ks});
+  if (bias) c.pb = ps.add(prefix + ".bias", {Cout});
+  return c;
+}
+
+namespace {
+// w[co][ci][tap] -> f32[(tap*Cin+ci)*Cout + co] ; bf16[co*K + tap*Cin + ci]
+__global__ void pack_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, float* __restrict__ o32,
+                            bf16* __restrict__ o16) {
+  const int64_t total = (int64_t)Cout * Cin * taps;
+  const int K = Cin * taps;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    const int co = (int)(i / ((int64_t)taps * Cin));
+    const float v = w[i];
+    o32[((int64_t)tap * Cin + ci) * Cout + co] = v;
+    if (o16) o16[(int64_t)co * K + tap * Cin + ci] = __float2bfloat16_rn(v);
+  }
+}
+}  // namespace
+
+void free_conv(ConvW& c) {
+  if (c.w_f32) cudaFree(c.w_f32);
+  if (c.w_bf16) cudaFree(c.w_bf16);
+  c.w_f32 = nullptr, c.w_bf16 = nullptr, c.packed_bytes = 0;
+}
+
+int pack_conv(const ParamStore& ps, ConvW& c, bool bf16_too) {
+  free_conv(c);
+  const int taps = c.ks * c.ks;
+  const int64_t K = (int64_t)taps * c.Cin;
+  HSIDM_CUDA(cudaMalloc(&c.w_f32, sizeof(float) * K * c.Cout));
+  c.packed_bytes = sizeof(float) * K * c.Cout;
+  const int bn = conv_tc_bn_rows(c.Cout);
+  if (bf16_too && bn > 0 && c.Cin % 64 == 0) {
+    const int64_t rows = round_up(c.Cout, bn);
+    HSIDM_CUDA(cudaMalloc(&c.w_bf16, sizeof(bf16) * rows * K));
+    HSIDM_CUDA(cudaMemset(c.w_bf16, 0, sizeof(bf16) * rows * K));
+    c.packed_bytes += sizeof(bf16) * rows * K;
+  }
+  const int64_t total = K * c.Cout;
+  const int grid = (int)std::min<int64_t>(ceil_div(total, 256), 4096);
+  pack_kernel<<<grid, 256>>>(ps.dev(c.pw), c.Cout, c.Cin, taps, c.w_f32, c.w_bf16);
+  return after_launch("pack_kernel");
+}
+
+// ---- dispatcher -----------------------------------------------------------------------------------------------
+void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps) {
+  op.w_f32 = w.w_f32;
+  op.w_bf16 = w.w_bf16;
+  op.bias = ps.dev(w.pb);
+  op.ksize = w.ks;
+  op.Cout = w.Cout;
+  cudaStream_t st = ex.stream;
+  const int prec = ex.prec;
+  if (prec == HSIDM_BF16 && w.w_bf16) {
+    if (conv_tc_supported(op, prec)) {
+      ex.run([&] { return conv_tc(op, st); });
+      return;
+    }
+    const bool nhwc1 = op.src[0].layout == L_NHWC && op.src[1].C == 0 && op.src[0].C % 64 == 0;
+    if (nhwc1 && op.stride == 2 && op.ksize == 3 && !op.up && op.Hin % 2 == 0 && op.Win % 2 == 0) {
+      // Downsample (unet.py:68-74): gather the 9 taps once, then a 1x1 tensor-core GEMM with K = 9*C.
+      const int C = op.src[0].C;
+      Act col = ex.alloc_act(op.N, op.Hout, op.Wout, 9 * C);
+      const void* src = op.src[0].p;
+      ex.run([&] { return im2col_s2(src, col.p, op.N, op.Hin, op.Win, C, st); });
+      ConvOp g = op;
+      g.src[0].p = col.p, g.src[0].C = 9 * C;
+      g.Hin = op.Hout, g.Win = op.Wout, g.stride = 1, g.ksize = 1;
+      if (conv_tc_supported(g, prec)) {
+        ex.run([&] { return conv_tc(g, st); });
+        ex.release(col);
+        return;
+      }
+      ex.release(col);
+    } else if (nhwc1 && op.up && op.stride == 1) {
+      // Upsample (unet.py:58-65): materialise the nearest-2x tensor, then the ordinary 3x3 tensor-core conv.
+      const int C = op.src[0].C;
+      Act big = ex.alloc_act(op.N, 2 * op.Hin, 2 * op.Win, C);
+      const void* src = op.src[0].p;
+      ex.run([&] { return upsample2x(src, big.p, op.N, op.Hin, op.Win, C, prec, st); });
+      ConvOp g = op;
+      g.src[0].p = big.p;
+      g.Hin = 2 * op.Hin, g.Win = 2 * op.Win, g.up = 0;
+      if (conv_tc_supported(g, prec)) {
+        ex.run([&] { return conv_tc(g, st); });
+        ex.release(big);
+        return;
+      }
+      ex.release(big);
+    }
+  }
+  ex.run([&] { return conv_simt(op, prec, st); });
+}
+
+}  // namespace hsidm

@@ -1,0 +1,104 @@
+// Shared host-side machinery of the two network executors (UNet in unet.cu, GAE in gae.cu):
+// a named fp32 parameter store fed by *_set_param, convolution weight packing, and the conv dispatcher that
+// routes each ConvOp to the tensor-core kernel (BF16 mode, shapes permitting) or the CUDA-core kernel.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace hsidm {
+
+struct Param {
+  std::string key;
+  std::vector<int64_t> shape;
+  float* dev = nullptr;
+  bool set = false;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+class ParamStore {
+ public:
+  ~ParamStore();
+  int add(const std::string& key, std::vector<int64_t> shape);  // returns index
+  int find(const std::string& key) const;
+  int set(const char* key, const float* data, const int64_t* shape, int ndim);
+  int check_all_set() const;
+  int alloc_all();  // one device slab for every parameter
+  const float* dev(int idx) const { return idx < 0 ? nullptr : params_[idx].dev; }
+  int size() const { return (int)params_.size(); }
+  const Param& at(int i) const { return params_[i]; }
+  int64_t bytes() const { return slab_bytes_; }
+
+ private:
+  std::vector<Param> params_;
+  float* slab_ = nullptr;
+  int64_t slab_bytes_ = 0;
+};
+
+// One convolution's parameters and packed copies.
+struct ConvW {
+  int pw = -1, pb = -1;  // indices into the ParamStore (weight [Cout,Cin,k,k], bias [Cout])
+  int Cin = 0, Cout = 0, ks = 3;
+  float* w_f32 = nullptr;  // [k*k*Cin][Cout]
+  bf16* w_bf16 = nullptr;  // [rows >= Cout][k*k*Cin], zero padded rows
+  int64_t packed_bytes = 0;
+};
+
+// Registers "<prefix>.weight" / "<prefix>.bias" and returns the ConvW.
+ConvW make_conv(ParamStore& ps, const std::string& prefix, int Cin, int Cout, int ks, bool bias = true);
+// (Re)packs w_f32 always and w_bf16 when `bf16_too`. Idempotent; frees previous packs.
+int pack_conv(const ParamStore& ps, ConvW& c, bool bf16_too);
+void free_conv(ConvW& c);
+
+// Execution context shared by both executors.
+struct Exec {
+  int prec = HSIDM_F32;
+  Arena arena;
+  bool dry = false;
+  cudaStream_t stream = nullptr;
+  int status = HSIDM_OK;  // first failure (sticky within one pass)
+
+  size_t esize() const { return prec == HSIDM_BF16 ? 2 : 4; }
+  Act alloc_act(int N, int H, int W, int C) {
+    Act a;
+    a.N = N, a.H = H, a.W = W, a.C = C;
+    a.p = arena.alloc(a.numel() * (int64_t)esize());
+    if (!a.p && status == HSIDM_OK) {
+      set_last_error("workspace arena exhausted (%lld bytes requested, capacity %lld)",
+                     (long long)(a.numel() * (int64_t)esize()), (long long)arena.capacity());
+      status = HSIDM_OOM_WORKSPACE;
+    }
+    return a;
+  }
+  void* alloc_raw(int64_t bytes) {
+    void* p = arena.alloc(bytes);
+    if (!p && status == HSIDM_OK) {
+      set_last_error("workspace arena exhausted (%lld bytes requested)", (long long)bytes);
+      status = HSIDM_OOM_WORKSPACE;
+    }
+    return p;
+  }
+  void release(Act& a) {
+    arena.free(a.p);
+    a.p = nullptr;
+  }
+  void release_raw(void* p) { arena.free(p); }
+  // run a launcher unless this is a dry (measuring) pass or an earlier step already failed
+  template <typename F>
+  void run(F&& f) {
+    if (dry || status != HSIDM_OK) return;
+    int s = f();
+    if (s != HSIDM_OK) status = s;
+  }
+};
+
+// Fills the weight/bias fields of `op` from `w` and dispatches it. In BF16 mode stride-2 and upsampled convs
+// whose channels fit the tensor-core kernel are lowered to (im2col | upsample) + tensor-core GEMM.
+void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps);
+
+}  // namespace hsidm

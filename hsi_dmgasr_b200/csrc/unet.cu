@@ -1,0 +1,677 @@
+// SR3 UNet executor + diffusion sampler behind the hsidm_ctx C ABI.
+//
+// The layer list is rebuilt from the constructor arguments exactly as UNet.__init__ does
+// (model/sr3_modules/unet.py:190-236) and executed as straight-line host code that enqueues kernels on one
+// stream; intermediate activations are NHWC in the context's element type and live in a stream-ordered arena.
+// hsidm_sample captures one (UNet forward + posterior step) into a CUDA graph and replays it T times; the
+// timestep lives in device memory so the graph is identical for every step.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "net.cuh"
+
+namespace hsidm {
+
+struct ResW {
+  int cin = 0, cout = 0, skip = 0;
+  bool attn = false, has_res = false;
+  int gn1_w = -1, gn1_b = -1, gn2_w = -1, gn2_b = -1;
+  int nf_w = -1, nf_b = -1, noise_off = 0;
+  ConvW c1, c2, rc;
+  int an_w = -1, an_b = -1;
+  ConvW qkv, aout;
+};
+
+struct LayerW {
+  enum Kind { CONV, RES, DOWN, UP } kind = CONV;
+  ConvW conv;  // CONV / DOWN / UP
+  ResW rb;     // RES
+};
+
+}  // namespace hsidm
+
+using namespace hsidm;
+
+struct hsidm_ctx {
+  hsidm_unet_cfg cfg;
+  int device = 0;
+  ParamStore ps;
+  std::vector<LayerW> downs, mid, ups;
+  int fin_gn_w = -1, fin_gn_b = -1;
+  ConvW fin_conv;
+  int mlp1_w = -1, mlp1_b = -1, mlp3_w = -1, mlp3_b = -1;
+  std::vector<NoiseLayer> noise_layers_host;  // filled at commit (device pointers)
+  NoiseLayer* noise_layers_dev = nullptr;
+  int noise_total = 0;
+  bool committed = false;
+  Exec ex;
+  int64_t packed_bytes = 0;
+
+  // schedule
+  int T = 0;
+  std::vector<float> coef_host;  // [T][5]
+  float* coef_dev = nullptr;     // [T][5]
+  float* levels_dev = nullptr;   // [T]
+  float* nbias_table = nullptr;  // [T][noise_total]
+  bool table_dirty = true;
+  int* t_dev = nullptr;
+
+  // persistent buffers
+  float* nbias_buf = nullptr;  // [cap_n][noise_total] for hsidm_unet_forward
+  int nbias_cap = 0;
+  float* samp_buf = nullptr;   // cond | x | eps for hsidm_sample
+  int64_t samp_cap = 0;
+
+  // workspace bookkeeping: peak per (N,H,W) measured by a dry pass
+  int ws_N = 0, ws_H = 0, ws_W = 0;
+
+  // cached one-step CUDA graph of hsidm_sample and the arguments baked into it
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  struct GraphKey {
+    int N = 0, H = 0, W = 0;
+    const float* tape = nullptr;
+    int64_t s_img = 0, s_step = 0;
+    float* snaps = nullptr;
+    bool operator==(const GraphKey& o) const {
+      return N == o.N && H == o.H && W == o.W && tape == o.tape && s_img == o.s_img && s_step == o.s_step && snaps == o.snaps;
+    }
+  } graph_key;
+  int64_t graph_nodes = 0;  // kernels per replay (for hsidm_launch_count)
+};
+
+namespace {
+
+constexpr float kGnEps = 1e-5f;
+
+int build_layers(hsidm_ctx* c) {
+  const hsidm_unet_cfg& g = c->cfg;
+  ParamStore& ps = c->ps;
+  const int ic = g.inner_channel;
+  c->mlp1_w = ps.add("noise_level_mlp.1.weight", {4 * ic, ic});
+  c->mlp1_b = ps.add("noise_level_mlp.1.bias", {4 * ic});
+  c->mlp3_w = ps.add("noise_level_mlp.3.weight", {ic, 4 * ic});
+  c->mlp3_b = ps.add("noise_level_mlp.3.bias", {ic});
+
+  auto in_attn = [&](int res) {
+    for (int i = 0; i < g.n_attn_res; ++i)
+      if (g.attn_res[i] == res) return true;
+    return false;
+  };
+  auto make_res = [&](const std::string& name, int cin, int cout, bool attn, int skip) {
+    LayerW L;
+    L.kind = LayerW::RES;
+    ResW& r = L.rb;
+    r.cin = cin, r.cout = cout, r.attn = attn, r.skip = skip, r.has_res = cin != cout;
+    const std::string p = name + ".res_block";
+    r.nf_w = ps.add(p + ".noise_func.noise_func.0.weight", {cout, ic});
+    r.nf_b = ps.add(p + ".noise_func.noise_func.0.bias", {cout});
+    r.noise_off = c->noise_total;
+    c->noise_total += cout;
+    r.gn1_w = ps.add(p + ".block1.block.0.weight", {cin});
+    r.gn1_b = ps.add(p + ".block1.block.0.bias", {cin});
+    r.c1 = make_conv(ps, p + ".block1.block.3", cin, cout, 3);
+    r.gn2_w = ps.add(p + ".block2.block.0.weight", {cout});
+    r.gn2_b = ps.add(p + ".block2.block.0.bias", {cout});
+    r.c2 = make_conv(ps, p + ".block2.block.3", cout, cout, 3);
+    if (r.has_res) r.rc = make_conv(ps, p + ".res_conv", cin, cout, 1);
+    if (attn) {
+      const std::string a = name + ".attn";
+      r.an_w = ps.add(a + ".norm.weight", {cout});
+      r.an_b = ps.add(a + ".norm.bias", {cout});
+      r.qkv = make_conv(ps, a + ".qkv", cout, 3 * cout, 1, /*bias=*/false);
+      r.aout = make_conv(ps, a + ".out", cout, cout, 1);
+    }
+    return L;
+  };
+
+  int pre = ic, now = g.image_size;
+  std::vector<int> feat{pre};
+  {
+    LayerW L;
+    L.kind = LayerW::CONV;
+    L.conv = make_conv(ps, "downs.0", g.in_channel, ic, 3);
+    c->downs.push_back(L);
+  }
+  for (int lev = 0; lev < g.n_mults; ++lev) {
+    const int cm = ic * g.channel_mults[lev];
+    for (int b = 0; b < g.res_blocks; ++b) {
+      c->downs.push_back(make_res("downs." + std::to_string(c->downs.size()), pre, cm, in_attn(now), 0));
+      pre = cm;
+      feat.push_back(pre);
+    }
+    if (lev + 1 < g.n_mults) {
+      LayerW L;
+      L.kind = LayerW::DOWN;
+      L.conv = make_conv(ps, "downs." + std::to_string(c->downs.size()) + ".conv", pre, pre, 3);
+      c->downs.push_back(L);
+      feat.push_back(pre);
+      now /= 2;
+    }
+  }
+  c->mid.push_back(make_res("mid.0", pre, pre, true, 0));
+  c->mid.push_back(make_res("mid.1", pre, pre, false, 0));
+  for (int lev = g.n_mults - 1; lev >= 0; --lev) {
+    const int cm = ic * g.channel_mults[lev];
+    for (int b = 0; b < g.res_blocks + 1; ++b) {
+      const int sk = feat.back();
+      feat.pop_back();
+      c->ups.push_back(make_res("ups." + std::to_string(c->ups.size()), pre + sk, cm, in_attn(now), sk));
+      pre = cm;
+    }
+    if (lev > 0) {
+      LayerW L;
+      L.kind = LayerW::UP;
+      L.conv = make_conv(ps, "ups." + std::to_string(c->ups.size()) + ".conv", pre, pre, 3);
+      c->ups.push_back(L);
+      now *= 2;
+    }
+  }
+  c->fin_gn_w = ps.add("final_conv.block.0.weight", {pre});
+  c->fin_gn_b = ps.add("final_conv.block.0.bias", {pre});
+  c->fin_conv = make_conv(ps, "final_conv.block.3", pre, g.out_channel, 3);
+  return HSIDM_OK;
+}
+
+template <typename F>
+void for_each_conv(hsidm_ctx* c, F&& f) {
+  auto visit = [&](std::vector<LayerW>& v) {
+    for (auto& L : v) {
+      if (L.kind != LayerW::RES) {
+        f(L.conv);
+        continue;
+      }
+      f(L.rb.c1);
+      f(L.rb.c2);
+      if (L.rb.has_res) f(L.rb.rc);
+      if (L.rb.attn) f(L.rb.qkv), f(L.rb.aout);
+    }
+  };
+  visit(c->downs);
+  visit(c->mid);
+  visit(c->ups);
+  f(c->fin_conv);
+}
+
+// ---- forward ------------------------------------------------------------------------------------------------
+struct NoiseRef {
+  const float* base;   // [.., noise_total]
+  int64_t n_stride;    // per image
+  const int* t_dev;    // optional device timestep
+  int64_t t_stride;
+};
+
+// GroupNorm(+Swish) over cat(a, b) -> new tensor with a.C + b.C channels.
+Act gn_act(hsidm_ctx* c, const Act& a, const Act* b, int gw, int gb, bool swish) {
+  Exec& ex = c->ex;
+  const int C1 = b ? b->C : 0;
+  const int groups = c->cfg.norm_groups;
+  double* gsum = static_cast<double*>(ex.alloc_raw(sizeof(double) * 2 * a.N * groups));
+  Act out = ex.alloc_act(a.N, a.H, a.W, a.C + C1);
+  const void* p1 = b ? b->p : nullptr;
+  ex.run([&] { return gn_stats(a.p, a.C, p1, C1, a.N, a.H * a.W, groups, gsum, ex.prec, ex.stream); });
+  ex.run([&] {
+    return gn_apply(a.p, a.C, p1, C1, a.N, a.H * a.W, groups, gsum, c->ps.dev(gw), c->ps.dev(gb), kGnEps, swish ? 1 : 0,
+                    out.p, ex.prec, ex.stream);
+  });
+  ex.release_raw(gsum);
+  return out;
+}
+
+ConvOp conv_op_nhwc(const Act& in, const Act* in2, const Act& out) {
+  ConvOp op;
+  op.src[0].p = in.p, op.src[0].C = in.C;
+  if (in2) op.src[1].p = in2->p, op.src[1].C = in2->C;
+  op.N = in.N, op.Hin = in.H, op.Win = in.W;
+  op.Hout = out.H, op.Wout = out.W;
+  op.out = out.p;
+  return op;
+}
+
+// SelfAttention.forward (unet.py:124-143), n_head = 1.
+Act attention(hsidm_ctx* c, const ResW& r, Act x) {
+  Exec& ex = c->ex;
+  const int C = x.C, S = x.H * x.W;
+  Act nrm = gn_act(c, x, nullptr, r.an_w, r.an_b, false);
+  Act qkv = ex.alloc_act(x.N, x.H, x.W, 3 * C);
+  run_conv(ex, conv_op_nhwc(nrm, nullptr, qkv), r.qkv, c->ps);
+  ex.release(nrm);
+  float* scores = static_cast<float*>(ex.alloc_raw(sizeof(float) * (int64_t)x.N * S * S));
+  Act av = ex.alloc_act(x.N, x.H, x.W, C);
+  const size_t es = ex.esize();
+  GemmOp qk;
+  qk.A = qkv.p, qk.B = static_cast<const char*>(qkv.p) + es * C, qk.C = scores;
+  qk.M = S, qk.N = S, qk.K = C, qk.lda = 3 * C, qk.ldb = 3 * C, qk.ldc = S;
+  qk.sA = (int64_t)S * 3 * C, qk.sB = qk.sA, qk.sC = (int64_t)S * S;
+  qk.batch = x.N, qk.transB = 1, qk.c_f32 = 1, qk.alpha = 1.0f / std::sqrt((float)C);
+  ex.run([&] { return gemm_simt(qk, ex.prec, ex.stream); });
+  ex.run([&] { return softmax_rows(scores, (int64_t)x.N * S, S, ex.stream); });
+  GemmOp pv;
+  pv.A = scores, pv.B = static_cast<const char*>(qkv.p) + es * 2 * C, pv.C = av.p;
+  pv.M = S, pv.N = C, pv.K = S, pv.lda = S, pv.ldb = 3 * C, pv.ldc = C;
+  pv.sA = (int64_t)S * S, pv.sB = (int64_t)S * 3 * C, pv.sC = (int64_t)S * C;
+  pv.batch = x.N, pv.transB = 0, pv.a_f32 = 1, pv.c_f32 = 0;
+  ex.run([&] { return gemm_simt(pv, ex.prec, ex.stream); });
+  ex.release_raw(scores);
+  ex.release(qkv);
+  Act out = ex.alloc_act(x.N, x.H, x.W, C);
+  ConvOp op = conv_op_nhwc(av, nullptr, out);
+  op.resid = x.p;
+  run_conv(ex, op, r.aout, c->ps);
+  ex.release(av);
+  return out;
+}
+
+// ResnetBlocWithAttn.forward (unet.py:105-111, 155-159) on cat(x, skip).  Does not release its inputs.
+Act res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const NoiseRef& nz) {
+  Exec& ex = c->ex;
+  Act a1 = gn_act(c, x, skip, r.gn1_w, r.gn1_b, true);
+  Act h = ex.alloc_act(x.N, x.H, x.W, r.cout);
+  {
+    ConvOp op = conv_op_nhwc(a1, nullptr, h);
+    op.nbias = nz.base + r.noise_off, op.nbias_stride = nz.n_stride;
+    op.nbias_t = nz.t_dev, op.nbias_t_stride = nz.t_stride;
+    run_conv(ex, op, r.c1, c->ps);
+  }
+  ex.release(a1);
+  Act a2 = gn_act(c, h, nullptr, r.gn2_w, r.gn2_b, true);
+  ex.release(h);
+  Act out = ex.alloc_act(x.N, x.H, x.W, r.cout);
+  Act shortcut;
+  const void* resid = x.p;
+  if (r.has_res) {
+    shortcut = ex.alloc_act(x.N, x.H, x.W, r.cout);
+    run_conv(ex, conv_op_nhwc(x, skip, shortcut), r.rc, c->ps);
+    resid = shortcut.p;
+  }
+  {
+    ConvOp op = conv_op_nhwc(a2, nullptr, out);
+    op.resid = resid;
+    run_conv(ex, op, r.c2, c->ps);
+  }
+  if (r.has_res) ex.release(shortcut);
+  ex.release(a2);
+  if (r.attn) {
+    Act o2 = attention(c, r, out);
+    ex.release(out);
+    out = o2;
+  }
+  return out;
+}
+
+// UNet.forward (unet.py:239-263).  x0/x1: fp32 NCHW halves of the input; eps: fp32 NCHW.
+void unet_forward_pass(hsidm_ctx* c, const float* x0, int c0, const float* x1, int c1, const NoiseRef& nz, float* eps,
+                       int N, int H, int W) {
+  Exec& ex = c->ex;
+  std::vector<Act> feats;
+  Act x = ex.alloc_act(N, H, W, c->cfg.inner_channel);
+  {
+    ConvOp op;
+    op.src[0].p = x0, op.src[0].C = c0, op.src[0].layout = L_NCHW_F32;
+    if (c1) op.src[1].p = x1, op.src[1].C = c1, op.src[1].layout = L_NCHW_F32;
+    op.N = N, op.Hin = H, op.Win = W, op.Hout = H, op.Wout = W, op.out = x.p;
+    run_conv(ex, op, c->downs[0].conv, c->ps);
+  }
+  feats.push_back(x);
+  for (size_t i = 1; i < c->downs.size(); ++i) {
+    const LayerW& L = c->downs[i];
+    Act y;
+    if (L.kind == LayerW::RES) {
+      y = res_block(c, L.rb, x, nullptr, nz);
+    } else {
+      y = ex.alloc_act(N, (x.H + 1) / 2, (x.W + 1) / 2, L.conv.Cout);
+      ConvOp op = conv_op_nhwc(x, nullptr, y);
+      op.stride = 2;
+      run_conv(ex, op, L.conv, c->ps);
+    }
+    feats.push_back(y);  // every downs output is a skip tensor (unet.py:243-249): keep it alive
+    x = y;
+  }
+  bool x_owned = false;  // x aliases feats.back() here
+  for (const LayerW& L : c->mid) {
+    Act y = res_block(c, L.rb, x, nullptr, nz);
+    if (x_owned) ex.release(x);
+    x = y, x_owned = true;
+  }
+  for (const LayerW& L : c->ups) {
+    Act y;
+    if (L.kind == LayerW::RES) {
+      Act skip = feats.back();
+      feats.pop_back();
+      y = res_block(c, L.rb, x, &skip, nz);
+      ex.release(skip);
+    } else {
+      y = ex.alloc_act(N, x.H * 2, x.W * 2, L.conv.Cout);
+      ConvOp op = conv_op_nhwc(x, nullptr, y);
+      op.up = 1;
+      run_conv(ex, op, L.conv, c->ps);
+    }
+    if (x_owned) ex.release(x);
+    x = y, x_owned = true;
+  }
+  Act a = gn_act(c, x, nullptr, c->fin_gn_w, c->fin_gn_b, true);
+  ex.release(x);
+  {
+    ConvOp op;
+    op.src[0].p = a.p, op.src[0].C = a.C;
+    op.N = N, op.Hin = a.H, op.Win = a.W, op.Hout = a.H, op.Wout = a.W;
+    op.out = eps, op.out_layout = L_NCHW_F32;
+    run_conv(ex, op, c->fin_conv, c->ps);
+  }
+  ex.release(a);
+}
+
+int check_shape(hsidm_ctx* c, int c0, int c1, int N, int H, int W) {
+  if (!c->committed) HSIDM_FAIL(HSIDM_BAD_STATE, "hsidm_unet_commit has not been called");
+  if (N <= 0 || H <= 0 || W <= 0) HSIDM_FAIL(HSIDM_BAD_SHAPE, "non-positive shape N=%d H=%d W=%d", N, H, W);
+  if (c0 + c1 != c->cfg.in_channel)
+    HSIDM_FAIL(HSIDM_BAD_SHAPE, "input channels %d+%d != in_channel %d", c0, c1, c->cfg.in_channel);
+  const int div = 1 << (c->cfg.n_mults - 1);
+  if (H % div || W % div)
+    HSIDM_FAIL(HSIDM_BAD_SHAPE, "H=%d, W=%d must be multiples of %d (one per down/up level, unet.py:68-74, 58-65)", H, W, div);
+  return HSIDM_OK;
+}
+
+void drop_graph(hsidm_ctx* c) {
+  if (c->graph_exec) {
+    cudaDeviceSynchronize();
+    cudaGraphExecDestroy(c->graph_exec);
+  }
+  if (c->graph) cudaGraphDestroy(c->graph);
+  c->graph_exec = nullptr, c->graph = nullptr;
+}
+
+// Measure the arena peak for this shape with a dry pass and make sure the backing store is large enough.
+int ensure_workspace(hsidm_ctx* c, int c0, int c1, int N, int H, int W) {
+  if (c->ws_N == N && c->ws_H == H && c->ws_W == W) return HSIDM_OK;
+  drop_graph(c);  // the arena may move
+  Exec& ex = c->ex;
+  ex.dry = true, ex.status = HSIDM_OK;
+  ex.arena.begin(true);
+  NoiseRef nz{nullptr, 0, nullptr, 0};
+  unet_forward_pass(c, nullptr, c0, nullptr, c1, nz, nullptr, N, H, W);
+  ex.dry = false;
+  if (ex.status != HSIDM_OK) return ex.status;
+  HSIDM_TRY(ex.arena.reserve(ex.arena.peak()));
+  c->ws_N = N, c->ws_H = H, c->ws_W = W;
+  return HSIDM_OK;
+}
+
+int run_forward(hsidm_ctx* c, const float* x0, int c0, const float* x1, int c1, const NoiseRef& nz, float* eps, int N,
+                int H, int W, cudaStream_t stream) {
+  Exec& ex = c->ex;
+  ex.stream = stream, ex.dry = false, ex.status = HSIDM_OK;
+  ex.arena.begin(false);
+  unet_forward_pass(c, x0, c0, x1, c1, nz, eps, N, H, W);
+  return ex.status;
+}
+
+int ensure_table(hsidm_ctx* c, cudaStream_t stream) {
+  if (!c->table_dirty) return HSIDM_OK;
+  if (c->T <= 0) HSIDM_FAIL(HSIDM_BAD_STATE, "hsidm_set_schedule has not been called");
+  if (c->nbias_table) cudaFree(c->nbias_table);
+  HSIDM_CUDA(cudaMalloc(&c->nbias_table, sizeof(float) * (int64_t)c->T * c->noise_total));
+  HSIDM_TRY(noise_embed(c->levels_dev, 1, c->T, c->cfg.inner_channel, c->ps.dev(c->mlp1_w), c->ps.dev(c->mlp1_b),
+                        c->ps.dev(c->mlp3_w), c->ps.dev(c->mlp3_b), c->noise_layers_dev,
+                        (int)c->noise_layers_host.size(), c->noise_total, c->nbias_table, stream));
+  c->table_dirty = false;
+  return HSIDM_OK;
+}
+
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+int hsidm_ctx_create(const hsidm_unet_cfg* cfg, int device, hsidm_ctx** out) {
+  if (!cfg || !out) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_ctx_create: null argument");
+  *out = nullptr;
+  if (cfg->n_mults < 1 || cfg->n_mults > HSIDM_MAX_LEVELS || cfg->n_attn_res < 0 || cfg->n_attn_res > HSIDM_MAX_LEVELS)
+    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "channel_multiplier / attn_res length out of range");
+  if (cfg->precision != HSIDM_F32 && cfg->precision != HSIDM_BF16) HSIDM_FAIL(HSIDM_BAD_DTYPE, "unknown precision %d", cfg->precision);
+  if (cfg->inner_channel <= 0 || cfg->inner_channel % 8 || cfg->norm_groups <= 0 || cfg->inner_channel % cfg->norm_groups)
+    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "inner_channel=%d must be a positive multiple of 8 and of norm_groups=%d",
+               cfg->inner_channel, cfg->norm_groups);
+  if (cfg->in_channel <= 0 || cfg->out_channel <= 0 || cfg->res_blocks < 1)
+    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "in_channel/out_channel/res_blocks must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    HSIDM_FAIL(HSIDM_CUDA_ERROR, "no CUDA device available (this library has no CPU path)");
+  }
+  HSIDM_CUDA(cudaSetDevice(device));
+  hsidm_ctx* c = new hsidm_ctx();
+  c->cfg = *cfg;
+  c->device = device;
+  c->ex.prec = cfg->precision;
+  build_layers(c);
+  int s = c->ps.alloc_all();
+  if (s == HSIDM_OK && cudaMalloc(&c->t_dev, 4 * sizeof(int)) != cudaSuccess) s = HSIDM_CUDA_ERROR;
+  if (s == HSIDM_OK && cfg->precision == HSIDM_BF16) s = conv_tc_init();
+  if (s != HSIDM_OK) {
+    delete c;
+    return s;
+  }
+  *out = c;
+  return HSIDM_OK;
+}
+
+int hsidm_ctx_destroy(hsidm_ctx* c) {
+  if (!c) return HSIDM_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  drop_graph(c);
+  for_each_conv(c, [](ConvW& w) { free_conv(w); });
+  if (c->noise_layers_dev) cudaFree(c->noise_layers_dev);
+  if (c->coef_dev) cudaFree(c->coef_dev);
+  if (c->levels_dev) cudaFree(c->levels_dev);
+  if (c->nbias_table) cudaFree(c->nbias_table);
+  if (c->t_dev) cudaFree(c->t_dev);
+  if (c->nbias_buf) cudaFree(c->nbias_buf);
+  if (c->samp_buf) cudaFree(c->samp_buf);
+  delete c;
+  return HSIDM_OK;
+}
+
+int hsidm_unet_param_count(const hsidm_ctx* c) { return c ? c->ps.size() : 0; }
+const char* hsidm_unet_param_name(const hsidm_ctx* c, int i) {
+  return (c && i >= 0 && i < c->ps.size()) ? c->ps.at(i).key.c_str() : nullptr;
+}
+
+int hsidm_unet_set_param(hsidm_ctx* c, const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (!c) HSIDM_FAIL(HSIDM_BAD_ARG, "null context");
+  HSIDM_CUDA(cudaSetDevice(c->device));
+  c->committed = false;
+  drop_graph(c);
+  return c->ps.set(key, data, shape, ndim);
+}
+
+int hsidm_unet_commit(hsidm_ctx* c) {
+  if (!c) HSIDM_FAIL(HSIDM_BAD_ARG, "null context");
+  HSIDM_CUDA(cudaSetDevice(c->device));
+  HSIDM_TRY(c->ps.check_all_set());
+  int status = HSIDM_OK;
+  c->packed_bytes = 0;
+  for_each_conv(c, [&](ConvW& w) {
+    if (status != HSIDM_OK) return;
+    status = pack_conv(c->ps, w, c->cfg.precision == HSIDM_BF16);
+    c->packed_bytes += w.packed_bytes;
+  });
+  HSIDM_TRY(status);
+  c->noise_layers_host.clear();
+  auto visit = [&](std::vector<LayerW>& v) {
+    for (auto& L : v)
+      if (L.kind == LayerW::RES)
+        c->noise_layers_host.push_back(NoiseLayer{c->ps.dev(L.rb.nf_w), c->ps.dev(L.rb.nf_b), L.rb.cout, L.rb.noise_off});
+  };
+  visit(c->downs), visit(c->mid), visit(c->ups);
+  if (c->noise_layers_dev) cudaFree(c->noise_layers_dev);
+  HSIDM_CUDA(cudaMalloc(&c->noise_layers_dev, sizeof(NoiseLayer) * c->noise_layers_host.size()));
+  HSIDM_CUDA(cudaMemcpy(c->noise_layers_dev, c->noise_layers_host.data(), sizeof(NoiseLayer) * c->noise_layers_host.size(),
+                        cudaMemcpyHostToDevice));
+  HSIDM_CUDA(cudaDeviceSynchronize());
+  c->committed = true;
+  c->table_dirty = true;
+  return HSIDM_OK;
+}
+
+int hsidm_set_schedule(hsidm_ctx* c, const double* betas, int T) {
+  if (!c || !betas || T <= 0) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_set_schedule: bad argument");
+  HSIDM_CUDA(cudaSetDevice(c->device));
+  drop_graph(c);
+  // float64 tables then fp32 casts, as set_new_noise_schedule does (diffusion.py:103-140)
+  std::vector<float> coef((size_t)T * 5), levels(T);
+  double ac = 1.0;
+  for (int t = 0; t < T; ++t) {
+    const double b = betas[t], alpha = 1.0 - b, ac_prev = ac;
+    ac *= alpha;
+    const double post_var = b * (1.0 - ac_prev) / (1.0 - ac);
+    const float logvar = (float)std::log(std::max(post_var, 1e-20));
+    coef[t * 5 + 0] = (float)std::sqrt(1.0 / ac);
+    coef[t * 5 + 1] = (float)std::sqrt(1.0 / ac - 1.0);
+    coef[t * 5 + 2] = (float)(b * std::sqrt(ac_prev) / (1.0 - ac));
+    coef[t * 5 + 3] = (float)((1.0 - ac_prev) * std::sqrt(alpha) / (1.0 - ac));
+    coef[t * 5 + 4] = std::exp(0.5f * logvar);  // (0.5 * log_variance).exp() in fp32, diffusion.py:175
+    levels[t] = (float)std::sqrt(ac);           // sqrt_alphas_cumprod_prev[t+1], diffusion.py:154
+  }
+  if (c->coef_dev) cudaFree(c->coef_dev);
+  if (c->levels_dev) cudaFree(c->levels_dev);
+  c->coef_dev = nullptr, c->levels_dev = nullptr;
+  HSIDM_CUDA(cudaMalloc(&c->coef_dev, sizeof(float) * coef.size()));
+  HSIDM_CUDA(cudaMalloc(&c->levels_dev, sizeof(float) * T));
+  HSIDM_CUDA(cudaMemcpy(c->coef_dev, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice));
+  HSIDM_CUDA(cudaMemcpy(c->levels_dev, levels.data(), sizeof(float) * T, cudaMemcpyHostToDevice));
+  c->coef_host = coef;
+  c->T = T;
+  c->table_dirty = true;
+  return HSIDM_OK;
+}
+
+int hsidm_num_timesteps(const hsidm_ctx* c) { return c ? c->T : 0; }
+int hsidm_snapshot_count(const hsidm_ctx* c) {
+  if (!c || c->T <= 0) return 0;
+  const int inter = 1 | (c->T / 10);
+  return (c->T - 1) / inter + 1;
+}
+int64_t hsidm_ctx_bytes(const hsidm_ctx* c) {
+  if (!c) return 0;
+  return c->ex.arena.capacity() + c->packed_bytes + c->ps.bytes() + (int64_t)c->T * c->noise_total * 4 + c->samp_cap * 4;
+}
+
+int hsidm_unet_forward(hsidm_ctx* c, const float* x0, int c0, const float* x1, int c1, const float* noise_level,
+                       int level_stride, float* eps_out, int N, int H, int W, hsidm_stream stream_) {
+  if (!c || !x0 || !noise_level || !eps_out) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_unet_forward: null argument");
+  if (c1 > 0 && !x1) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_unet_forward: c1 > 0 but x1 is null");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  HSIDM_CUDA(cudaSetDevice(c->device));
+  HSIDM_TRY(check_shape(c, c0, c1, N, H, W));
+  HSIDM_TRY(ensure_workspace(c, c0, c1, N, H, W));
+  if (c->nbias_cap < N) {
+    if (c->nbias_buf) {
+      HSIDM_CUDA(cudaDeviceSynchronize());
+      cudaFree(c->nbias_buf);
+      c->nbias_buf = nullptr;
+    }
+    HSIDM_CUDA(cudaMalloc(&c->nbias_buf, sizeof(float) * (int64_t)N * c->noise_total));
+    c->nbias_cap = N;
+  }
+  const int n_emb = level_stride == 0 ? 1 : N;
+  HSIDM_TRY(noise_embed(noise_level, level_stride, n_emb, c->cfg.inner_channel, c->ps.dev(c->mlp1_w), c->ps.dev(c->mlp1_b),
+                        c->ps.dev(c->mlp3_w), c->ps.dev(c->mlp3_b), c->noise_layers_dev, (int)c->noise_layers_host.size(),
+                        c->noise_total, c->nbias_buf, stream));
+  NoiseRef nz{c->nbias_buf, level_stride == 0 ? 0 : (int64_t)c->noise_total, nullptr, 0};
+  return run_forward(c, x0, c0, x1, c1, nz, eps_out, N, H, W, stream);
+}
+
+int hsidm_posterior_step(hsidm_ctx* c, int t, const float* x_t, const float* eps, const float* noise, float* x_prev,
+                         int64_t n, hsidm_stream stream_) {
+  if (!c || !x_t || !eps || !x_prev) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_posterior_step: null argument");
+  if (c->T <= 0) HSIDM_FAIL(HSIDM_BAD_STATE, "hsidm_set_schedule has not been called");
+  if (t < 0 || t >= c->T) HSIDM_FAIL(HSIDM_BAD_ARG, "timestep %d outside [0,%d)", t, c->T);
+  HSIDM_CUDA(cudaSetDevice(c->device));
+  PosteriorArgs a{};
+  a.x_t = x_t, a.eps = eps, a.noise = noise, a.x_prev = x_prev, a.n = n;
+  a.per_image = n, a.tape_image_stride = 0, a.tape_step_stride = 0;  // noise is given for this very step
+  a.coef = c->coef_dev, a.T = c->T, a.t = t, a.t_dev = nullptr, a.seed = 0, a.use_philox = 0;
+  a.snapshot_base = nullptr, a.inter = 1;
+  // a.noise indexes with j = T-1-t: fold that into the pointer by using zero strides
+  return posterior_step(a, static_cast<cudaStream_t>(stream_));
+}
+
+int hsidm_sample(hsidm_ctx* c, const float* cond, const float* x_T, const float* noise_tape, int64_t tape_image_stride,
+                 int64_t tape_step_stride, uint64_t seed, float* out, float* snapshots, int N, int H, int W,
+                 hsidm_stream stream_) {
+  if (!c || !cond || !x_T || !out) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_sample: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  HSIDM_CUDA(cudaSetDevice(c->device));
+  if (c->cfg.in_channel % 2 || c->cfg.out_channel * 2 != c->cfg.in_channel)
+    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conditional sampling needs in_channel == 2*out_channel (diffusion.py:158)");
+  const int ch = c->cfg.out_channel;
+  HSIDM_TRY(check_shape(c, ch, ch, N, H, W));
+  HSIDM_TRY(ensure_workspace(c, ch, ch, N, H, W));
+  HSIDM_TRY(ensure_table(c, stream));
+  const int64_t per_image = (int64_t)ch * H * W, n = per_image * N;
+  if (c->samp_cap < 3 * n) {
+    drop_graph(c);
+    if (c->samp_buf) {
+      HSIDM_CUDA(cudaDeviceSynchronize());
+      cudaFree(c->samp_buf);
+      c->samp_buf = nullptr;
+    }
+    HSIDM_CUDA(cudaMalloc(&c->samp_buf, sizeof(float) * 3 * n));
+    c->samp_cap = 3 * n;
+  }
+  float* cond_b = c->samp_buf;
+  float* x_b = c->samp_buf + n;
+  float* eps_b = c->samp_buf + 2 * n;
+  hsidm_ctx::GraphKey key;
+  key.N = N, key.H = H, key.W = W, key.tape = noise_tape, key.s_img = tape_image_stride, key.s_step = tape_step_stride;
+  key.snaps = snapshots;
+  if (c->graph_exec && !(c->graph_key == key)) drop_graph(c);
+  if (!c->graph_exec) {
+    // ---- capture one denoising step: UNet forward + fused posterior + timestep decrement ----
+    const int64_t launches_before = g_launches;
+    HSIDM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    NoiseRef nz{c->nbias_table, 0, c->t_dev, (int64_t)c->noise_total};
+    int s = run_forward(c, cond_b, ch, x_b, ch, nz, eps_b, N, H, W, stream);
+    if (s == HSIDM_OK) {
+      PosteriorArgs a{};
+      a.x_t = x_b, a.eps = eps_b, a.noise = noise_tape, a.x_prev = x_b, a.n = n, a.per_image = per_image;
+      a.tape_image_stride = tape_image_stride, a.tape_step_stride = tape_step_stride;
+      a.coef = c->coef_dev, a.T = c->T, a.t = -1, a.t_dev = c->t_dev, a.seed = 0;
+      a.seed_dev = reinterpret_cast<const unsigned long long*>(c->t_dev + 2), a.use_philox = noise_tape ? 0 : 1;
+      a.snapshot_base = snapshots, a.inter = 1 | (c->T / 10);
+      s = posterior_step(a, stream);
+    }
+    if (s == HSIDM_OK) s = step_counter_dec(c->t_dev, stream);
+    cudaError_t ce = cudaStreamEndCapture(stream, &c->graph);
+    if (s != HSIDM_OK) {
+      drop_graph(c);
+      return s;
+    }
+    if (ce != cudaSuccess) {
+      drop_graph(c);
+      HSIDM_FAIL(HSIDM_CUDA_ERROR, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+    }
+    ce = cudaGraphInstantiate(&c->graph_exec, c->graph, 0);
+    if (ce != cudaSuccess) {
+      drop_graph(c);
+      HSIDM_FAIL(HSIDM_CUDA_ERROR, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    }
+    c->graph_key = key;
+    c->graph_nodes = g_launches - launches_before;  // captured, not executed: count them per replay instead
+    g_launches = launches_before;
+  }
+  HSIDM_CUDA(cudaMemcpyAsync(cond_b, cond, sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
+  HSIDM_CUDA(cudaMemcpyAsync(x_b, x_T, sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
+  HSIDM_TRY(sampler_state_set(c->t_dev, c->T - 1, seed, stream));
+  for (int i = 0; i < c->T; ++i) {
+    HSIDM_CUDA(cudaGraphLaunch(c->graph_exec, stream));
+    g_launches += c->graph_nodes;
+  }
+  HSIDM_CUDA(cudaMemcpyAsync(out, x_b, sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
+  return HSIDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+"""Drop-in for ``model/sr3_modules/diffusion.py::GaussianDiffusion`` (sampling side).
+
+``super_resolution`` -> ``p_sample_loop`` runs the whole T-step conditional loop inside the native library
+(``hsidm_sample``: one CUDA graph of UNet forward + fused posterior step, replayed T times), batched over all
+latent images it is given.  ``p_sample`` / ``p_mean_variance`` keep the reference's step-wise semantics through
+``hsidm_unet_forward`` + ``hsidm_posterior_step`` and are what the per-step parity tests drive.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .schedule import BUFFER_NAMES, diffusion_buffers, make_beta_schedule
+
+
+class GaussianDiffusion(nn.Module):
+    def __init__(self, denoise_fn, image_size, channels=31, loss_type="l1", conditional=True, schedule_opt=None):
+        super().__init__()
+        self.channels = channels
+        self.image_size = image_size
+        self.denoise_fn = denoise_fn
+        self.loss_type = loss_type
+        self.conditional = conditional
+        self.num_timesteps = 0
+        self._betas64: Optional[np.ndarray] = None
+        # like the reference (diffusion.py:82-84) the schedule is NOT installed here; DDPM.__init__ does it.
+
+    # ---- schedule -------------------------------------------------------------------------------------------
+    def set_loss(self, device):
+        if self.loss_type == "l1":
+            self.loss_func = nn.L1Loss(reduction="sum").to(device)
+        elif self.loss_type == "l2":
+            self.loss_func = nn.MSELoss(reduction="sum").to(device)
+        else:
+            raise NotImplementedError()
+
+    def set_new_noise_schedule(self, schedule_opt, device):
+        """diffusion.py:93-140: float64 tables -> 12 fp32 buffers + float64 ``sqrt_alphas_cumprod_prev``."""
+        betas = make_beta_schedule(schedule=schedule_opt["schedule"], n_timestep=schedule_opt["n_timestep"],
+                                   linear_start=schedule_opt["linear_start"], linear_end=schedule_opt["linear_end"])
+        tabs = diffusion_buffers(betas)
+        self.sqrt_alphas_cumprod_prev = tabs["sqrt_alphas_cumprod_prev"]
+        self.num_timesteps = int(betas.shape[0])
+        self._betas64 = np.ascontiguousarray(betas, dtype=np.float64)
+        for name in BUFFER_NAMES:
+            self.register_buffer(name, torch.tensor(tabs[name], dtype=torch.float32, device=device))
+
+    def _native(self, device):
+        h = self.denoise_fn.native(device)
+        if self._betas64 is None:
+            raise _lib.HsidmError(-7, "set_new_noise_schedule has not been called")
+        sig = (self._betas64.ctypes.data, self.num_timesteps, float(self._betas64.sum()))
+        if h.schedule_sig != sig:
+            lib = _lib.load()
+            _lib.check(lib.hsidm_set_schedule(h.ptr, self._betas64.ctypes.data_as(C.POINTER(C.c_double)),
+                                              self.num_timesteps))
+            h.schedule_sig = sig
+        return h
+
+    # ---- reference helper formulas (diffusion.py:142-150), kept for API parity -------------------------------------
+    def predict_start_from_noise(self, x_t, t, noise):
+        return self.sqrt_recip_alphas_cumprod[t] * x_t - self.sqrt_recipm1_alphas_cumprod[t] * noise
+
+    def q_posterior(self, x_start, x_t, t):
+        mean = self.posterior_mean_coef1[t] * x_start + self.posterior_mean_coef2[t] * x_t
+        return mean, self.posterior_log_variance_clipped[t]
+
+    # ---- step-wise path -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def predict_noise(self, x, t, condition_x=None):
+        """eps = denoise_fn(cat([condition_x, x]), noise_level_t) (diffusion.py:154-161) without materialising the cat."""
+        x = _lib.require_cuda_f32(x, "x")
+        h = self._native(x.device)
+        n, c, hh, ww = x.shape
+        level = torch.full((1,), float(self.sqrt_alphas_cumprod_prev[t + 1]), dtype=torch.float32, device=x.device)
+        eps = torch.empty((n, self.denoise_fn.cfg.out_channel, hh, ww), device=x.device, dtype=torch.float32)
+        lib = _lib.load()
+        st = _lib.stream_ptr(x.device)
+        if condition_x is not None:
+            cond = _lib.require_cuda_f32(condition_x, "condition_x")
+            _lib.check(lib.hsidm_unet_forward(h.ptr, cond.data_ptr(), cond.shape[1], x.data_ptr(), c, level.data_ptr(), 0,
+                                              eps.data_ptr(), n, hh, ww, st))
+        else:
+            _lib.check(lib.hsidm_unet_forward(h.ptr, x.data_ptr(), c, None, 0, level.data_ptr(), 0, eps.data_ptr(), n, hh,
+                                              ww, st))
+        return eps
+
+    @torch.no_grad()
+    def p_sample(self, x, t, clip_denoised=True, condition_x=None, noise=None):
+        """One reverse step (diffusion.py:170-175). ``noise`` defaults to ``torch.randn_like(x)`` for t > 0."""
+        if not clip_denoised:
+            raise NotImplementedError("clip_denoised=False is never used by the reference drivers")
+        eps = self.predict_noise(x, t, condition_x)
+        h = self._native(x.device)
+        if t > 0 and noise is None:
+            noise = torch.randn_like(x)
+        if t == 0:
+            noise = None
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        _lib.check(_lib.load().hsidm_posterior_step(h.ptr, int(t), x.data_ptr(), eps.data_ptr(), _lib.ptr(noise),
+                                                    out.data_ptr(), x.numel(), _lib.stream_ptr(x.device)))
+        return out
+
+    # ---- whole loop -----------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def p_sample_loop(self, x_in, continous=False, *, x_T=None, noise_tape=None, return_all=False, seed=None):
+        """diffusion.py:177-201.
+
+        Conditional: ``x_in`` is the condition [N,c,H,W]; all N images are sampled as one batch.
+        ``x_T`` [N,c,H,W] / ``noise_tape`` [N,T-1,c,H,W] inject the random draws (parity tests); otherwise x_T comes
+        from ``torch.randn`` and the per-step noise from the library's counter-based generator seeded from torch's
+        default generator.  Return shapes follow the reference: ``continous`` -> cat([x_in, snapshots...], 0);
+        else the LAST batch element of the final image as a 3-D tensor (diffusion.py:198-201), unless
+        ``return_all`` asks for the whole batch [N,c,H,W].
+        """
+        device = self.betas.device
+        if not self.conditional:
+            shape = x_in
+            img = torch.randn(shape, device=device) if x_T is None else x_T
+            ret = img
+            inter = 1 | (self.num_timesteps // 10)
+            for i in reversed(range(self.num_timesteps)):
+                img = self.p_sample(img, i)
+                if i % inter == 0:
+                    ret = torch.cat([ret, img], dim=0)
+            return ret if continous else (img if return_all else ret[-1])
+        cond = _lib.require_cuda_f32(x_in, "x_in")
+        n, c, hh, ww = cond.shape
+        h = self._native(cond.device)
+        lib = _lib.load()
+        x_T = torch.randn(cond.shape, device=cond.device) if x_T is None else _lib.require_cuda_f32(x_T, "x_T")
+        if tuple(x_T.shape) != tuple(cond.shape):
+            raise _lib.HsidmError(-1, f"x_T shape {tuple(x_T.shape)} != condition shape {tuple(cond.shape)}")
+        tape_ptr, s_img, s_step = None, 0, 0
+        if noise_tape is not None:
+            noise_tape = _lib.require_cuda_f32(noise_tape, "noise_tape")
+            want = (n, max(self.num_timesteps - 1, 0), c, hh, ww)
+            if tuple(noise_tape.shape) != want:
+                raise _lib.HsidmError(-1, f"noise_tape shape {tuple(noise_tape.shape)} != {want}")
+            tape_ptr, s_img, s_step = noise_tape.data_ptr(), noise_tape.stride(0), noise_tape.stride(1)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        out = torch.empty_like(cond)
+        snaps = None
+        if continous:
+            n_snap = lib.hsidm_snapshot_count(h.ptr)
+            snaps = torch.empty((n_snap,) + tuple(cond.shape), device=cond.device, dtype=torch.float32)
+        _lib.check(lib.hsidm_sample(h.ptr, cond.data_ptr(), x_T.data_ptr(), tape_ptr, s_img, s_step, seed, out.data_ptr(),
+                                    _lib.ptr(snaps), n, hh, ww, _lib.stream_ptr(cond.device)))
+        if continous:
+            return torch.cat([cond, snaps.reshape(-1, c, hh, ww)], dim=0)
+        return out if return_all else out[-1]
+
+    @torch.no_grad()
+    def sample(self, batch_size=1, continous=False):
+        return self.p_sample_loop((batch_size, self.channels, self.image_size, self.image_size), continous)
+
+    @torch.no_grad()
+    def super_resolution(self, x_in, continous=False, **kw):
+        return self.p_sample_loop(x_in, continous, **kw)
+
+    # ---- training side: SURVEY.md 8f row N2, not built yet ---------------------------------------------------------------
+    def q_sample(self, x_start, continuous_sqrt_alpha_cumprod, noise=None):
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return continuous_sqrt_alpha_cumprod * x_start + (1 - continuous_sqrt_alpha_cumprod ** 2).sqrt() * noise
+
+    def p_losses(self, x_in, noise=None):
+        raise NotImplementedError("p_losses (training forward+backward) is a 'next' row of the scope table (SURVEY.md 8f N2); "
+                                  "this package implements the inference hot path only")
+
+    def forward(self, x, *args, **kwargs):
+        return self.p_losses(x, *args, **kwargs)

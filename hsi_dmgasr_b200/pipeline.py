@@ -1,0 +1,95 @@
+"""Batched restatement of the reference's validation loop (sr_gae.py:436-475) and its multi-GPU sharding.
+
+Reference: per cube -> ``encode`` -> for each of the G groups, sequentially at batch 1: ``feed_data`` / ``test`` /
+``get_current_visuals`` (a D2H + H2D round trip per group) -> ``decode`` -> clamp to [0,1].
+Here: all B*G latent images of a batch of cubes are denoised together (the UNet weights are shared by every group),
+nothing leaves the device between encode and decode, and cubes are sharded across GPUs with no per-step collective
+(SURVEY.md 8e): one process per GPU, a contiguous slice of the work list each, one gather at the very end.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from .diffusion import GaussianDiffusion
+from .gae import GAE
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced slice [lo, hi) of a work list for `rank` of `world` (first n%world ranks get one more)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class SRPipeline:
+    """encode -> T-step conditional sampling of every group latent -> decode, for a batch of cubes on one GPU."""
+
+    def __init__(self, diffusion: GaussianDiffusion, gae: GAE, max_latents: Optional[int] = None):
+        self.diffusion = diffusion
+        self.gae = gae
+        self.max_latents = max_latents      # cap on latent images per sampling call (None = all B*G at once)
+
+    @torch.no_grad()
+    def super_resolve(self, sr: torch.Tensor, *, x_T: Optional[torch.Tensor] = None,
+                      noise_tape: Optional[torch.Tensor] = None, seed: Optional[int] = None,
+                      clamp: bool = True, return_latents: bool = False):
+        """sr: bicubic-upsampled cubes [B,C,H,W] on the GPU -> SR cubes [B,C,H,W] (clamped to [0,1] like sr_gae.py:474-475).
+
+        x_T [B*G,3,H,W] / noise_tape [B*G,T-1,3,H,W] inject the random draws in (cube, group)-major order."""
+        z = self.gae.encode_batched(sr)
+        n = z.shape[0]
+        step = self.max_latents or n
+        outs = []
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            outs.append(self.diffusion.super_resolution(
+                z[lo:hi], False, return_all=True, x_T=None if x_T is None else x_T[lo:hi],
+                noise_tape=None if noise_tape is None else noise_tape[lo:hi],
+                seed=None if seed is None else seed + lo))
+        lat = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+        y = self.gae.decode_batched(lat, clamp01=clamp)
+        return (y, lat) if return_latents else y
+
+    @torch.no_grad()
+    def super_resolve_host(self, sr_host: torch.Tensor, device: torch.device, **kw) -> torch.Tensor:
+        """End-to-end call with HOST buffers: pinned H2D of the cubes, the pipeline, D2H of the result."""
+        if sr_host.is_cuda:
+            raise ValueError("super_resolve_host expects a host tensor")
+        src = sr_host if sr_host.is_pinned() else sr_host.pin_memory()
+        dev = src.to(device, non_blocking=True)
+        y = self.super_resolve(dev, **kw)
+        out = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+        out.copy_(y, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        return out
+
+
+def run_sharded(pipeline: SRPipeline, cubes_host: torch.Tensor, device: torch.device, rank: int, world: int,
+                batch: int, gather: bool = False, **kw) -> Optional[torch.Tensor]:
+    """Each rank super-resolves its contiguous slice of `cubes_host` in batches of `batch` cubes.
+
+    No data-path collective. With gather=True the per-rank results are collected on rank 0 through
+    torch.distributed (NCCL on GPUs, gloo on CPU tests) once at the end; other ranks return None."""
+    lo, hi = shard_bounds(cubes_host.shape[0], rank, world)
+    parts: List[torch.Tensor] = []
+    for b0 in range(lo, hi, batch):
+        parts.append(pipeline.super_resolve_host(cubes_host[b0:min(hi, b0 + batch)], device, **kw))
+    mine = torch.cat(parts, dim=0) if parts else cubes_host.new_zeros((0,) + tuple(cubes_host.shape[1:]))
+    if not gather or world == 1:
+        return mine
+    import torch.distributed as dist
+    gathered = gather_variable(mine, rank, world, dist)
+    return gathered
+
+
+def gather_variable(mine: torch.Tensor, rank: int, world: int, dist) -> Optional[torch.Tensor]:
+    """Gather per-rank row blocks of differing length on rank 0 (host tensors; backend-agnostic)."""
+    objs = [None] * world if rank == 0 else None
+    dist.gather_object(mine.cpu(), objs, dst=0)
+    if rank != 0:
+        return None
+    return torch.cat(objs, dim=0)

@@ -36,7 +36,7 @@ class UNetConfig:
             res_blocks=u["res_blocks"], dropout=u["dropout"] or 0.0,
             image_size=model_opt["diffusion"]["image_size"])
 
-    def as_oracle_cfg(self) -> dict:
+    def as_dict(self) -> dict:
         return dict(inner_channel=self.inner_channel, channel_multiplier=list(self.channel_mults),
                     attn_res=list(self.attn_res), res_blocks=self.res_blocks, image_size=self.image_size,
                     norm_groups=self.norm_groups, in_channel=self.in_channel, out_channel=self.out_channel)
@@ -165,7 +165,7 @@ class GAEGeometry:
                 cnt[c] += 1
         return cnt
 
-    def as_oracle_geom(self) -> dict:
+    def as_dict(self) -> dict:
         return dict(n_colors=self.n_colors, n_subs=self.n_subs, n_ovls=self.n_ovls)
 
 

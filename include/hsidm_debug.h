@@ -1,0 +1,33 @@
+/*
+ * hsidm_debug.h - test hooks into single kernels of libhsidm_b200 (used by tests/, never by the product path).
+ * All pointers are device pointers; activations are NHWC in the element type selected by `precision`
+ * (fp32 or bf16) unless the layout argument says NCHW fp32. Each call synchronises the device before returning.
+ */
+#ifndef HSIDM_DEBUG_H_
+#define HSIDM_DEBUG_H_
+#include "hsidm.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One convolution as the executors issue it (nn.Conv2d of unet.py:62,71,87,102,121,122 / AE.py / common.py).
+ * backend: 0 = CUDA-core kernel, 1 = tcgen05 tensor-core kernel (fails if the shape does not fit),
+ *          2 = the executors' dispatcher (tensor core when possible, lowering stride-2 / upsample).
+ * weight: fp32 [Cout, c0+c1, k, k] (reference layout); bias/nbias/resid may be NULL.
+ * src_layout / out_layout: 0 = NHWC activation type, 1 = NCHW fp32. */
+HSIDM_API int hsidm_debug_conv2d(int backend, int precision, const void* src0, int c0, const void* src1, int c1, int src_layout,
+                       int N, int H, int W, int up, int stride, const float* weight, const float* bias, int Cout,
+                       int ksize, const float* nbias, int64_t nbias_stride, int act, float scale, const void* resid,
+                       void* out, int out_layout);
+
+/* GroupNorm(+Swish) over the concatenation of two NHWC tensors (unet.py:84). */
+HSIDM_API int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const void* x1, int c1, int N, int HW, int groups,
+                          const float* gamma, const float* beta, float eps, int swish, void* out);
+
+/* Reads and clears the tensor-core kernel's barrier-timeout flag (0 = healthy). */
+HSIDM_API int hsidm_debug_tc_error_flag(int* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

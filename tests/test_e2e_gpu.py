@@ -1,0 +1,62 @@
+"""End-to-end cube parity: encode -> batched T-step sampling of all groups -> decode -> clamp, against the
+reference's sequential val loop (tests/golden/e2e.npz, produced by oracle/make_golden.py section 5).
+Gates from BASELINE.json: |dMPSNR| <= 0.05 dB, |dSAM| <= 0.01 degrees."""
+import numpy as np
+import pytest
+import torch
+
+from hsi_dmgasr_b200 import GAE, GaussianDiffusion, SRPipeline, UNet, synth
+from hsi_dmgasr_b200.metrics import mpsnr, sam_degrees
+from hsi_dmgasr_b200.spec import GAEGeometry
+from tests.cfgs import SMALL
+from tests.gpu_util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def build(precision, T):
+    geom = GAEGeometry(31, 8, 2)
+    gae = GAE(n_subs=8, n_ovls=2, n_colors=31, n_feats=64)
+    gae.load_state_dict(synth.gae_state_dict(geom, 51))
+    net = UNet(in_channel=6, out_channel=3, inner_channel=SMALL.inner_channel, norm_groups=SMALL.norm_groups,
+               channel_mults=SMALL.channel_mults, attn_res=SMALL.attn_res, res_blocks=SMALL.res_blocks,
+               dropout=SMALL.dropout, image_size=SMALL.image_size, precision=precision)
+    net.load_state_dict(synth.unet_state_dict(SMALL, 52))
+    gd = GaussianDiffusion(net, image_size=16, channels=3, conditional=True).cuda().eval()
+    gd.set_new_noise_schedule(dict(schedule="cosine", n_timestep=T, linear_start=1e-6, linear_end=1e-2), torch.device("cuda"))
+    return SRPipeline(gd, gae.cuda().eval()), geom
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cube_and_metric_gates(golden, precision):
+    g = golden("e2e.npz")
+    T, hw = int(g["T"]), 16
+    pipe, geom = build(precision, T)
+    sr = synth.sr_cube(1, 31, hw, seed=53).cuda()
+    hr = synth.sr_cube(1, 31, hw, seed=54)
+    x_T, tape = synth.noise_tape(geom.G, T, 3, hw, hw, seed=55)
+    cube, lat = pipe.super_resolve(sr, x_T=x_T.cuda(), noise_tape=tape.cuda(), return_latents=True)
+    want = torch.from_numpy(g["cube"])
+    print(precision, "cube rel-L2", rel_l2(cube, want), "latents", rel_l2(lat, torch.from_numpy(g["latents"])))
+    true = hr[0].permute(1, 2, 0).numpy()
+    pred = cube[0].permute(1, 2, 0).cpu().numpy()
+    d_psnr = abs(mpsnr(true, pred) - float(g["mpsnr"]))
+    d_sam = abs(sam_degrees(true, pred) - float(g["sam"]))
+    print(precision, "dMPSNR", d_psnr, "dSAM", d_sam)
+    assert d_psnr <= 0.05 and d_sam <= 0.01
+    if precision == "fp32":
+        assert rel_l2(cube, want) < 1e-4
+
+
+def test_host_buffer_call_and_batch_independence():
+    pipe, geom = build("fp32", 5)
+    sr = synth.sr_cube(3, 31, 16, seed=60)
+    x_T, tape = synth.noise_tape(3 * geom.G, 5, 3, 16, 16, seed=61)
+    out = pipe.super_resolve_host(sr, torch.device("cuda"), x_T=x_T.cuda(), noise_tape=tape.cuda())
+    assert out.shape == sr.shape and not out.is_cuda and float(out.min()) >= 0 and float(out.max()) <= 1
+    one = pipe.super_resolve(sr[1:2].cuda(), x_T=x_T[geom.G:2 * geom.G].cuda(), noise_tape=tape[geom.G:2 * geom.G].cuda())
+    assert rel_l2(one, out[1:2]) < 1e-5
+    # chunked sampling (max_latents) is the same computation
+    pipe.max_latents = 4
+    chunked = pipe.super_resolve(sr.cuda(), x_T=x_T.cuda(), noise_tape=tape.cuda())
+    assert rel_l2(chunked, out) < 1e-5

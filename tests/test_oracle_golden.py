@@ -47,7 +47,7 @@ def test_unet_forward_matches_reference(golden, tag):
     lv = torch.tensor(lvls, dtype=torch.float32).view(n, 1)
     taps = {}
     with torch.no_grad():
-        y = O.unet_forward(sd, cfg.as_oracle_cfg(), x, lv, taps)
+        y = O.unet_forward(sd, cfg.as_dict(), x, lv, taps)
     assert rel(y.numpy(), g[f"{tag}.eps"]) < 2e-6
     for k, v in taps.items():
         if f"{tag}.tap.{k}" in g:
@@ -67,9 +67,9 @@ def test_sample_loop_matches_reference(golden):
     x_T, tape = synth.noise_tape(n, T, 3, hw, hw, seed=32)
     eps_l, x_l = [], []
     with torch.no_grad():
-        ret = O.sample_loop(sd, SMALL.as_oracle_cfg(), tab, cond, x_T, lambda i: tape[:, T - 1 - i], continous=True,
+        ret = O.sample_loop(sd, SMALL.as_dict(), tab, cond, x_T, lambda i: tape[:, T - 1 - i], continous=True,
                             record=lambda i, e, x: (eps_l.append(e), x_l.append(x)))
-        last = O.sample_loop(sd, SMALL.as_oracle_cfg(), tab, cond, x_T, lambda i: tape[:, T - 1 - i], continous=False)
+        last = O.sample_loop(sd, SMALL.as_dict(), tab, cond, x_T, lambda i: tape[:, T - 1 - i], continous=False)
     assert rel(torch.stack(eps_l).numpy(), g["eps"]) < 5e-6
     assert rel(torch.stack(x_l).numpy(), g["x"]) < 5e-6
     assert ret.shape == g["ret_all"].shape and rel(ret.numpy(), g["ret_all"]) < 5e-6
@@ -86,8 +86,8 @@ def test_gae_matches_reference(golden, tag):
     sd = synth.gae_state_dict(geom, seed)
     x = synth.sr_cube(2, geom.n_colors, hw, seed=seed + 100)
     with torch.no_grad():
-        zs = O.gae_encode(sd, geom.as_oracle_geom(), x)
-        y = O.gae_decode(sd, geom.as_oracle_geom(), x, zs)
+        zs = O.gae_encode(sd, geom.as_dict(), x)
+        y = O.gae_decode(sd, geom.as_dict(), x, zs)
     assert rel(torch.stack(zs).numpy(), g[f"{tag}.z"]) < 2e-6
     assert rel(y.numpy(), g[f"{tag}.dec"]) < 2e-6
 
@@ -103,7 +103,7 @@ def test_end_to_end_cube_and_metrics(golden):
     hr = synth.sr_cube(1, 31, hw, seed=54)
     x_T, tape = synth.noise_tape(geom.G, T, 3, hw, hw, seed=55)
     with torch.no_grad():
-        cube = O.sr_cube(usd, SMALL.as_oracle_cfg(), tab, gsd, geom.as_oracle_geom(), sr,
+        cube = O.sr_cube(usd, SMALL.as_dict(), tab, gsd, geom.as_dict(), sr,
                          [x_T[i:i + 1] for i in range(geom.G)], lambda gi, i: tape[gi:gi + 1, T - 1 - i])
     assert rel(cube.numpy(), g["cube"]) < 1e-5
     pred = cube[0].permute(1, 2, 0).numpy()

@@ -1,0 +1,69 @@
+"""UNet eps parity on the B200 against vectors produced by the unmodified reference (tests/golden/unet_forward.npz)
+and against the CPU oracle on the same seeded inputs.  Gates from BASELINE.json: 1e-4 relative in fp32 mode,
+2e-2 in bf16 mode."""
+import numpy as np
+import pytest
+import torch
+
+from hsi_dmgasr_b200 import UNet, synth
+from tests.cfgs import UNET_CASES
+from tests.gpu_util import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def build(cfg, seed, precision):
+    net = UNet(in_channel=cfg.in_channel, out_channel=cfg.out_channel, inner_channel=cfg.inner_channel,
+               norm_groups=cfg.norm_groups, channel_mults=cfg.channel_mults, attn_res=cfg.attn_res,
+               res_blocks=cfg.res_blocks, dropout=cfg.dropout, image_size=cfg.image_size, precision=precision)
+    net.load_state_dict(synth.unet_state_dict(cfg, seed), strict=True)
+    return net.cuda().eval()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", list(UNET_CASES))
+def test_unet_eps_matches_reference(golden, tag, precision):
+    cfg, seed, n, hw, lvls = UNET_CASES[tag]
+    g = golden("unet_forward.npz")
+    net = build(cfg, seed, precision)
+    x = torch.from_numpy(np.random.default_rng(1000 + seed).standard_normal((n, 6, hw, hw), dtype=np.float32)).cuda()
+    lv = torch.tensor(lvls, dtype=torch.float32).view(n, 1).cuda()
+    with torch.no_grad():
+        eps = net(x, lv)
+    want = torch.from_numpy(g[f"{tag}.eps"])
+    err = rel_l2(eps, want)
+    print(f"{tag} {precision}: rel-L2 {err:.3e}")
+    assert eps.shape == want.shape and torch.isfinite(eps).all()
+    assert err < TOL[precision]
+
+
+def test_unet_state_dict_is_drop_in():
+    cfg, seed, *_ = UNET_CASES["full32"]
+    net = build(cfg, seed, "fp32")
+    sd = synth.unet_state_dict(cfg, seed)
+    assert list(net.state_dict().keys()) == list(sd.keys())
+
+
+def test_unet_rejects_bad_shapes_loudly():
+    from hsi_dmgasr_b200._lib import HsidmError
+    cfg, seed, *_ = UNET_CASES["small"]
+    net = build(cfg, seed, "fp32")
+    with pytest.raises(HsidmError):
+        net(torch.zeros(1, 6, 15, 16, device="cuda"), torch.ones(1, 1, device="cuda"))      # not a multiple of 2
+    with pytest.raises(HsidmError):
+        net(torch.zeros(1, 5, 16, 16, device="cuda"), torch.ones(1, 1, device="cuda"))      # wrong channel count
+    with pytest.raises(HsidmError):
+        net(torch.zeros(1, 6, 16, 16), torch.ones(1, 1))                                    # CPU tensors: no fallback
+
+
+def test_weights_follow_parameter_updates():
+    cfg, seed, n, hw, lvls = UNET_CASES["small"]
+    net = build(cfg, seed, "fp32")
+    x = torch.randn(1, 6, hw, hw, device="cuda")
+    lv = torch.full((1, 1), 0.5, device="cuda")
+    a = net(x, lv)
+    with torch.no_grad():
+        net.final_conv["block"]["3"].bias.add_(1.0)
+    b = net(x, lv)
+    assert torch.allclose(b - a, torch.ones_like(a), atol=1e-5)
