@@ -45,6 +45,8 @@ SIGNATURES = {
     "hsidm_version": (C.c_int, []),
     "hsidm_last_error": (C.c_char_p, []),
     "hsidm_launch_count": (C.c_int64, []),
+    "hsidm_prof_enable": (C.c_int, [C.c_int]),
+    "hsidm_prof_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "hsidm_ctx_create": (C.c_int, [C.POINTER(UNetCfg), C.c_int, C.POINTER(_P)]),
     "hsidm_ctx_destroy": (C.c_int, [_P]),
     "hsidm_unet_param_count": (C.c_int, [_P]),

@@ -10,6 +10,16 @@ int hsidm_version(void) { return HSIDM_VERSION; }
 const char* hsidm_last_error(void) { return g_last_error.c_str(); }
 int64_t hsidm_launch_count(void) { return g_launches; }
 
+int hsidm_prof_enable(int on) {
+  prof_reset();
+  g_prof_on = on != 0;
+  return HSIDM_OK;
+}
+int hsidm_prof_read(int kind, double* ms, double* work, int64_t* launches) {
+  if (!ms || !work || !launches || kind < 0 || kind >= PROF_KINDS) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_prof_read: bad argument");
+  return prof_read(kind, ms, work, launches);
+}
+
 int hsidm_debug_conv2d(int backend, int precision, const void* src0, int c0, const void* src1, int c1, int src_layout,
                        int N, int H, int W, int up, int stride, const float* weight, const float* bias, int Cout,
                        int ksize, const float* nbias, int64_t nbias_stride, int act, float scale, const void* resid,
@@ -68,12 +78,16 @@ int hsidm_debug_conv2d(int backend, int precision, const void* src0, int c0, con
 
 int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const void* x1, int c1, int N, int HW, int groups,
                           const float* gamma, const float* beta, float eps, int swish, void* out) {
-  double* gsum = nullptr;
-  HSIDM_CUDA(cudaMalloc(&gsum, sizeof(double) * 2 * N * groups));
-  int s = gn_stats(x0, c0, x1, c1, N, HW, groups, gsum, precision, nullptr);
-  if (s == HSIDM_OK) s = gn_apply(x0, c0, x1, c1, N, HW, groups, gsum, gamma, beta, eps, swish, out, precision, nullptr);
+  void* scratch = nullptr;
+  unsigned* tickets = nullptr;
+  HSIDM_CUDA(cudaMalloc(&scratch, gn_scratch_bytes(c0, c1, N, HW, groups) + 16));
+  HSIDM_CUDA(cudaMalloc(&tickets, sizeof(unsigned) * N));
+  HSIDM_CUDA(cudaMemset(tickets, 0, sizeof(unsigned) * N));
+  int s = gn_stats(x0, c0, x1, c1, N, HW, groups, eps, scratch, tickets, precision, nullptr);
+  if (s == HSIDM_OK) s = gn_apply(x0, c0, x1, c1, N, HW, groups, scratch, gamma, beta, swish, out, precision, nullptr);
   cudaError_t e = cudaDeviceSynchronize();
-  cudaFree(gsum);
+  cudaFree(scratch);
+  cudaFree(tickets);
   if (e != cudaSuccess && s == HSIDM_OK) {
     set_last_error("kernel failed: %s", cudaGetErrorString(e));
     s = HSIDM_CUDA_ERROR;

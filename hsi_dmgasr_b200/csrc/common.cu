@@ -1,6 +1,8 @@
 // Error state, launch counter and the stream-ordered workspace arena.
 #include "common.cuh"
 
+#include <vector>
+
 namespace hsidm {
 
 thread_local std::string g_last_error;
@@ -13,6 +15,52 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(buf, sizeof(buf), fmt, ap);
   va_end(ap);
   g_last_error = buf;
+}
+
+// ---- profiling ------------------------------------------------------------------------------------------------
+bool g_prof_on = false;
+namespace {
+struct ProfRec {
+  cudaEvent_t a, b;
+  int kind;
+  double work;
+};
+std::vector<ProfRec> g_prof_recs;
+}  // namespace
+
+int prof_start(int kind, double work, cudaStream_t stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return -1;
+  }
+  ProfRec r;
+  r.kind = kind, r.work = work;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+  cudaEventRecord(r.a, stream);
+  g_prof_recs.push_back(r);
+  return (int)g_prof_recs.size() - 1;
+}
+
+void prof_stop(int token, cudaStream_t stream) { cudaEventRecord(g_prof_recs[token].b, stream); }
+
+void prof_reset() {
+  for (auto& r : g_prof_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof_recs.clear();
+}
+
+int prof_read(int kind, double* ms, double* work, int64_t* launches) {
+  *ms = 0, *work = 0, *launches = 0;
+  HSIDM_CUDA(cudaDeviceSynchronize());
+  for (auto& r : g_prof_recs) {
+    if (r.kind != kind) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) *ms += t, *work += r.work, *launches += 1;
+  }
+  return HSIDM_OK;
 }
 
 static constexpr int64_t kAlign = 1024;

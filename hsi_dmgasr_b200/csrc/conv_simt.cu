@@ -230,6 +230,7 @@ int conv_simt(const ConvOp& op, int prec, cudaStream_t stream) {
   int64_t M = (int64_t)op.N * op.Hout * op.Wout;
   if (M <= 0 || M > INT32_MAX) HSIDM_FAIL(HSIDM_BAD_SHAPE, "conv_simt: M=%lld out of range", (long long)M);
   p.M = (int)M;
+  ProfScope prof(PROF_CONV_SIMT, 2.0 * (double)M * op.Cout * p.Ktot, stream);
   return prec == HSIDM_BF16 ? launch<bf16>(p, stream) : launch<float>(p, stream);
 }
 

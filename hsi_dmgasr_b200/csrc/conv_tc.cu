@@ -502,6 +502,7 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
   HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, BN));
 
   const int grid = std::min(p.m_tiles * p.n_tiles, g_num_sms);
+  ProfScope prof(PROF_CONV_TC, 2.0 * p.M * (double)op.Cout * K, stream);
   switch (BN) {
     case 16: conv_tc_kernel<16><<<grid, kThreads, Cfg<16>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;
     case 64: conv_tc_kernel<64><<<grid, kThreads, Cfg<64>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;

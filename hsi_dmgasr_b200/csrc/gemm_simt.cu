@@ -93,6 +93,7 @@ int gemm_simt(const GemmOp& op, int prec, cudaStream_t stream) {
   GemmP p{op.A, op.B, op.C, op.M, op.N, op.K, op.lda, op.ldb, op.ldc, op.sA, op.sB, op.sC, op.transB, op.a_f32, op.c_f32,
           op.alpha};
   dim3 grid((unsigned)ceil_div(op.M, 64), (unsigned)ceil_div(op.N, 64), op.batch);
+  ProfScope prof(PROF_GEMM, 2.0 * op.M * (double)op.N * op.K * op.batch, stream);
   if (prec == HSIDM_BF16)
     gemm_simt_kernel<bf16><<<grid, 256, 0, stream>>>(p);
   else

@@ -64,12 +64,21 @@ struct GemmOp {
 int gemm_simt(const GemmOp& op, int prec, cudaStream_t stream);
 int softmax_rows(float* x, int64_t rows, int cols, cudaStream_t stream);  // in place, fp32
 
-// GroupNorm over the (virtual) concatenation of two NHWC tensors with the same N,H,W.
-// gsum: [N][groups][2] doubles (sum, sum of squares); zeroed by gn_stats itself.
-int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, double* gsum, int prec,
-             cudaStream_t stream);
-int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const double* gsum,
-             const float* gamma, const float* beta, float eps, int swish, void* out, int prec, cudaStream_t stream);
+// GroupNorm over the (virtual) concatenation of two NHWC tensors with the same N,H,W (deterministic reduction).
+// scratch: gn_scratch_bytes() bytes = per-block partials followed by the published (mean, rstd) pairs.
+// tickets: N zero-initialised counters, left zero again by gn_stats (one array per stream is enough).
+struct GnGeo {
+  int CV, lanes, threads, pix_per_block, slabs;
+};
+int gn_geometry(int C0, int C1, int N, int HW, GnGeo* g);
+int64_t gn_scratch_bytes(int C0, int C1, int N, int HW, int groups);
+inline float* gn_stats_ptr(void* scratch, int N, int slabs, int groups) {
+  return reinterpret_cast<float*>(static_cast<double*>(scratch) + (int64_t)2 * N * slabs * groups);
+}
+int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, float eps, void* scratch,
+             unsigned* tickets, int prec, cudaStream_t stream);
+int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const void* scratch,
+             const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream);
 
 int upsample2x(const void* x, void* out, int N, int H, int W, int C, int prec, cudaStream_t stream);
 // Stride-2 3x3 im2col for the tensor-core path: out [N,H/2,W/2,9*C] (bf16).

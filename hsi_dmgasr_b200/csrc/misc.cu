@@ -190,17 +190,33 @@ __global__ void softmax_kernel(float* __restrict__ x, int64_t rows, int cols) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// GAE: CALayer global average pool. grid (slabs, N), thread -> channel (C <= 256), atomics across slabs.
+// GAE: CALayer global average pool. One block per image (deterministic: fixed-order fold, no float atomics);
+// thread -> (lane, channel), C <= 256.
 template <typename AT>
-__global__ void channel_mean_kernel(const AT* __restrict__ x, int HW, int C, int pix_per_block, float inv_hw,
-                                    float* __restrict__ mean) {
-  const int n = blockIdx.y;
-  const int c = threadIdx.x % C, lane = threadIdx.x / C, lanes = blockDim.x / C;
-  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
-  float s = 0.f;
-  if (lane < lanes)
-    for (int p = p0 + lane; p < p1; p += lanes) s += to_f32(x[((int64_t)n * HW + p) * C + c]);
-  if (lane < lanes) atomicAdd(&mean[(int64_t)n * C + c], s * inv_hw);
+__global__ void channel_mean_kernel(const AT* __restrict__ x, int HW, int C, float inv_hw, float* __restrict__ mean) {
+  __shared__ float part[256];
+  const int n = blockIdx.x;
+  const int lanes = blockDim.x / C;
+  const int c = threadIdx.x % C, lane = threadIdx.x / C;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (lane < lanes) {
+    const AT* base = x + (int64_t)n * HW * C + c;
+    int p = lane;
+    for (; p + 3 * lanes < HW; p += 4 * lanes) {
+      s0 += to_f32(base[(int64_t)p * C]);
+      s1 += to_f32(base[(int64_t)(p + lanes) * C]);
+      s2 += to_f32(base[(int64_t)(p + 2 * lanes) * C]);
+      s3 += to_f32(base[(int64_t)(p + 3 * lanes) * C]);
+    }
+    for (; p < HW; p += lanes) s0 += to_f32(base[(int64_t)p * C]);
+  }
+  part[threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += part[l * C + threadIdx.x];
+    mean[(int64_t)n * C + threadIdx.x] = acc * inv_hw;
+  }
 }
 
 __global__ void ca_gate_kernel(const float* __restrict__ mean, int C, int Cr, const float* __restrict__ w0,
@@ -264,6 +280,7 @@ int posterior_step(const PosteriorArgs& a, cudaStream_t stream) {
   if (a.n % 4 || a.per_image % 4) HSIDM_FAIL(HSIDM_BAD_SHAPE, "posterior_step: element counts must be multiples of 4");
   if (((uintptr_t)a.x_t | (uintptr_t)a.eps | (uintptr_t)a.x_prev | (uintptr_t)a.noise) & 15)
     HSIDM_FAIL(HSIDM_BAD_ARG, "posterior_step: pointers must be 16-byte aligned");
+  ProfScope prof(PROF_POSTERIOR, (double)a.n * 4 * (a.noise ? 4 : 3), stream);
   posterior_kernel<<<grid_for(a.n / 4, 256), 256, 0, stream>>>(a);
   return after_launch("posterior_kernel");
 }
@@ -311,16 +328,10 @@ int softmax_rows(float* x, int64_t rows, int cols, cudaStream_t stream) {
 
 int channel_mean(const void* x, int N, int HW, int C, float* mean, int prec, cudaStream_t stream) {
   if (C > 256) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "channel_mean: C=%d > 256", C);
-  HSIDM_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * N * C, stream));
-  const int lanes = 256 / C;
-  int slabs = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(148 * 4, N), ceil_div(HW, lanes * 8)));
-  const int ppb = (int)ceil_div(HW, slabs);
-  slabs = (int)ceil_div(HW, ppb);
-  dim3 grid(slabs, N);
   if (prec == HSIDM_BF16)
-    channel_mean_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)x, HW, C, ppb, 1.0f / HW, mean);
+    channel_mean_kernel<bf16><<<N, 256, 0, stream>>>((const bf16*)x, HW, C, 1.0f / HW, mean);
   else
-    channel_mean_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, HW, C, ppb, 1.0f / HW, mean);
+    channel_mean_kernel<float><<<N, 256, 0, stream>>>((const float*)x, HW, C, 1.0f / HW, mean);
   return after_launch("channel_mean_kernel");
 }
 

@@ -61,6 +61,24 @@ int ParamStore::check_all_set() const {
   return HSIDM_OK;
 }
 
+Exec::~Exec() {
+  if (tickets) cudaFree(tickets);
+}
+
+int Exec::ensure_tickets(int n) {
+  if (n <= tickets_cap) return HSIDM_OK;
+  if (tickets) {
+    HSIDM_CUDA(cudaDeviceSynchronize());
+    cudaFree(tickets);
+    tickets = nullptr;
+  }
+  const int cap = (int)round_up(n, 256);
+  HSIDM_CUDA(cudaMalloc(&tickets, sizeof(unsigned) * cap));
+  HSIDM_CUDA(cudaMemset(tickets, 0, sizeof(unsigned) * cap));
+  tickets_cap = cap;
+  return HSIDM_OK;
+}
+
 // ---- conv weights -------------------------------------------------------------------------------------------
 ConvW make_conv(ParamStore& ps, const std::string& prefix, int Cin, int Cout, int ks, bool bias) {
   ConvW c;

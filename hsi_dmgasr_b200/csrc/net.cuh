@@ -62,6 +62,10 @@ struct Exec {
   bool dry = false;
   cudaStream_t stream = nullptr;
   int status = HSIDM_OK;  // first failure (sticky within one pass)
+  unsigned* tickets = nullptr;  // GroupNorm ticket counters (zero between kernels)
+  int tickets_cap = 0;
+  int ensure_tickets(int n);  // grows the counter array (synchronises when it has to)
+  ~Exec();
 
   size_t esize() const { return prec == HSIDM_BF16 ? 2 : 4; }
   Act alloc_act(int N, int H, int W, int C) {

@@ -1,16 +1,21 @@
 // GroupNorm (+Swish) over NHWC activations, including the virtual concatenation of two tensors whose groups
 // may straddle the concat boundary (unet.py:84, :120, :259; C = 192/384/768 in the `ups` blocks).
 //
-// Both kernels are HBM-bound: 128-bit accesses (8 channels per thread), warp-shuffle-free per-channel register
-// accumulation, one shared-memory fold per block, fp64 atomics for the few cross-block partials.
-//   gn_stats : read x once                 -> (sum, sumsq) per (image, group)
+// Both kernels are HBM-bound: 128-bit accesses (8 channels per thread), 4 independent loads in flight per thread,
+// per-channel register accumulation, one shared-memory fold per block.  The reduction is DETERMINISTIC: every
+// block writes its per-group partial (sum, sumsq) to a fixed slot, and the last block of an image to finish
+// (ticket counter) adds the slots in index order and publishes (mean, rstd).  No floating-point atomics.
+//   gn_stats : read x once                 -> stats[n][g] = (mean, rstd)
 //   gn_apply : read x once, write y once   -> y = swish?(x * A[n,c] + B[n,c])
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace hsidm {
 namespace {
 
 constexpr int kMaxThreads = 256;
+constexpr int kUnroll = 4;
 
 template <typename AT>
 __device__ __forceinline__ const AT* src_ptr(const AT* x0, int C0, const AT* x1, int C1, int64_t pix, int c) {
@@ -19,98 +24,140 @@ __device__ __forceinline__ const AT* src_ptr(const AT* x0, int C0, const AT* x1,
 
 // grid = (slabs, N); block = lanes*CV threads, CV = C/8 channel-vectors, each thread owns one channel-vector.
 template <typename AT>
-__global__ void gn_stats_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, int C1, int HW,
-                                int groups, int CV, int lanes, int pix_per_block, double* __restrict__ gsum) {
-  extern __shared__ float sm[];  // [2][C]
+__global__ void __launch_bounds__(kMaxThreads)
+gn_stats_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, int C1, int HW, int groups, int CV,
+                int lanes, int pix_per_block, float eps, double* __restrict__ partial /*[N][slabs][groups][2]*/,
+                unsigned* __restrict__ tickets /*[N], zero on entry and on exit*/, float* __restrict__ stats) {
+  extern __shared__ float sm[];  // [lanes][2][C]  then reused as [2][C]
+  __shared__ bool is_last;
   const int C = C0 + C1;
-  const int n = blockIdx.y;
+  const int n = blockIdx.y, slab = blockIdx.x, slabs = gridDim.x;
   const int tid = threadIdx.x;
   const int cv = tid % CV, lane = tid / CV;
   const int c = cv * 8;
-  const int p0 = blockIdx.x * pix_per_block;
+  const int p0 = slab * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
-  for (int i = tid; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = 0.f, q[j] = 0.f;
-  for (int pix = p0 + lane; pix < p1; pix += lanes) {
+  const int64_t img = (int64_t)n * HW;
+  int pix = p0 + lane;
+  for (; pix + (kUnroll - 1) * lanes < p1; pix += kUnroll * lanes) {
+    float v[kUnroll][8];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) load8(src_ptr<AT>(x0, C0, x1, C1, img + pix + u * lanes, c), v[u]);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[u][j], q[j] = fmaf(v[u][j], v[u][j], q[j]);
+  }
+  for (; pix < p1; pix += lanes) {
     float v[8];
-    load8(src_ptr<AT>(x0, C0, x1, C1, (int64_t)n * HW + pix, c), v);
+    load8(src_ptr<AT>(x0, C0, x1, C1, img + pix, c), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] += v[j], q[j] = fmaf(v[j], v[j], q[j]);
   }
+  float* mine = sm + (size_t)lane * 2 * C;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[c + j], s[j]);
-    atomicAdd(&sm[C + c + j], q[j]);
+  for (int j = 0; j < 8; ++j) mine[c + j] = s[j], mine[C + c + j] = q[j];
+  __syncthreads();
+  // fold the lanes in index order: thread -> (which, channel)
+  for (int i = tid; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += sm[(size_t)l * 2 * C + i];
+    sm[i] = acc;  // lane 0's slot doubles as the result (each i is read by this thread only before the write)
   }
   __syncthreads();
   const int cpg = C / groups;
+  double* my_partial = partial + ((int64_t)n * slabs + slab) * groups * 2;
   for (int g = tid; g < groups; g += blockDim.x) {
     double a = 0.0, b = 0.0;
     for (int j = 0; j < cpg; ++j) a += (double)sm[g * cpg + j], b += (double)sm[C + g * cpg + j];
-    atomicAdd(&gsum[((int64_t)n * groups + g) * 2 + 0], a);
-    atomicAdd(&gsum[((int64_t)n * groups + g) * 2 + 1], b);
+    my_partial[g * 2] = a;
+    my_partial[g * 2 + 1] = b;
   }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd(&tickets[n], 1u) == (unsigned)(slabs - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const double cnt = (double)cpg * HW;
+  for (int g = tid; g < groups; g += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    const double* p = partial + (int64_t)n * slabs * groups * 2 + g * 2;
+    for (int sl = 0; sl < slabs; ++sl) a += p[(int64_t)sl * groups * 2], b += p[(int64_t)sl * groups * 2 + 1];
+    const double mean = a / cnt;
+    double var = b / cnt - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    stats[((int64_t)n * groups + g) * 2] = (float)mean;
+    stats[((int64_t)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  if (tid == 0) tickets[n] = 0;  // ready for the next GroupNorm on this stream
 }
 
 template <typename AT>
-__global__ void gn_apply_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, int C1, int HW,
-                                int groups, int CV, int lanes, int pix_per_block, const double* __restrict__ gsum,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int swish,
-                                AT* __restrict__ out) {
-  extern __shared__ float sm[];  // A[C], B[C]
+__global__ void __launch_bounds__(kMaxThreads)
+gn_apply_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, int C1, int HW, int groups, int CV,
+                int lanes, int pix_per_block, const float* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int swish, AT* __restrict__ out) {
   const int C = C0 + C1;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
   const int cpg = C / groups;
-  const double cnt = (double)cpg * HW;
-  for (int c = tid; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const double mean = gsum[((int64_t)n * groups + g) * 2] / cnt;
-    double var = gsum[((int64_t)n * groups + g) * 2 + 1] / cnt - mean * mean;
-    var = var < 0.0 ? 0.0 : var;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float a = rstd * gamma[c];
-    sm[c] = a;
-    sm[C + c] = beta[c] - (float)mean * a;
-  }
-  __syncthreads();
   const int cv = tid % CV, lane = tid / CV;
   const int c = cv * 8;
   float A[8], B[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) A[j] = sm[c + j], B[j] = sm[C + c + j];
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    const float mean = stats[((int64_t)n * groups + g) * 2], rstd = stats[((int64_t)n * groups + g) * 2 + 1];
+    A[j] = rstd * __ldg(gamma + c + j);
+    B[j] = __ldg(beta + c + j) - mean * A[j];
+  }
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
-  for (int pix = p0 + lane; pix < p1; pix += lanes) {
+  const int64_t img = (int64_t)n * HW;
+  int pix = p0 + lane;
+  for (; pix + (kUnroll - 1) * lanes < p1; pix += kUnroll * lanes) {
+    float v[kUnroll][8];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) load8(src_ptr<AT>(x0, C0, x1, C1, img + pix + u * lanes, c), v[u]);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = fmaf(v[u][j], A[j], B[j]);
+        v[u][j] = swish ? swish_f(y) : y;
+      }
+      store8(out + (img + pix + u * lanes) * C + c, v[u]);
+    }
+  }
+  for (; pix < p1; pix += lanes) {
     float v[8];
-    const int64_t gp = (int64_t)n * HW + pix;
-    load8(src_ptr<AT>(x0, C0, x1, C1, gp, c), v);
+    load8(src_ptr<AT>(x0, C0, x1, C1, img + pix, c), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float y = fmaf(v[j], A[j], B[j]);
+      const float y = fmaf(v[j], A[j], B[j]);
       v[j] = swish ? swish_f(y) : y;
     }
-    store8(out + gp * C + c, v);
+    store8(out + (img + pix) * C + c, v);
   }
 }
 
-struct Geo {
-  int CV, lanes, threads, pix_per_block, slabs;
-};
+}  // namespace
 
-int geometry(int C0, int C1, int N, int HW, Geo* g) {
+int gn_geometry(int C0, int C1, int N, int HW, GnGeo* g) {
   const int C = C0 + C1;
-  if (C0 % 8 || C1 % 8 || C <= 0) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "GroupNorm needs channel counts that are multiples of 8 (got %d+%d)", C0, C1);
+  if (C0 % 8 || C1 % 8 || C <= 0)
+    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "GroupNorm needs channel counts that are multiples of 8 (got %d+%d)", C0, C1);
   g->CV = C / 8;
   if (g->CV > kMaxThreads) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "GroupNorm over %d channels exceeds the supported 2048", C);
   g->lanes = kMaxThreads / g->CV;
   g->threads = g->lanes * g->CV;
-  // enough blocks to fill 148 SMs a few times over, but at least 4 pixels per lane per block
+  // enough blocks to fill the 148 SMs several times over, but at least 2*kUnroll pixels per lane per block
   int slabs = (int)ceil_div(148 * 8, N);
-  int min_pix = g->lanes * 4;
+  const int min_pix = g->lanes * 2 * kUnroll;
   slabs = (int)std::min<int64_t>(slabs, ceil_div(HW, min_pix));
   if (slabs < 1) slabs = 1;
   g->pix_per_block = (int)ceil_div(HW, slabs);
@@ -118,41 +165,47 @@ int geometry(int C0, int C1, int N, int HW, Geo* g) {
   return HSIDM_OK;
 }
 
-}  // namespace
+int64_t gn_scratch_bytes(int C0, int C1, int N, int HW, int groups) {
+  GnGeo g;
+  if (gn_geometry(C0, C1, N, HW, &g) != HSIDM_OK) return 0;
+  return (int64_t)sizeof(double) * 2 * N * g.slabs * groups + (int64_t)sizeof(float) * 2 * N * groups;
+}
 
-int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, double* gsum, int prec,
-             cudaStream_t stream) {
-  Geo g;
-  HSIDM_TRY(geometry(C0, C1, N, HW, &g));
+int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, float eps, void* scratch,
+             unsigned* tickets, int prec, cudaStream_t stream) {
+  GnGeo g;
+  HSIDM_TRY(gn_geometry(C0, C1, N, HW, &g));
   const int C = C0 + C1;
   if (C % groups) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "GroupNorm: %d channels not divisible by %d groups", C, groups);
-  HSIDM_CUDA(cudaMemsetAsync(gsum, 0, sizeof(double) * 2 * N * groups, stream));
+  double* partial = static_cast<double*>(scratch);
+  float* stats = gn_stats_ptr(scratch, N, g.slabs, groups);
   dim3 grid(g.slabs, N);
-  size_t smem = sizeof(float) * 2 * C;
+  const size_t smem = sizeof(float) * 2 * C * g.lanes;
+  ProfScope prof(PROF_GN_STATS, (double)N * HW * C * (prec == HSIDM_BF16 ? 2 : 4), stream);
   if (prec == HSIDM_BF16)
     gn_stats_kernel<bf16><<<grid, g.threads, smem, stream>>>((const bf16*)x0, C0, (const bf16*)x1, C1, HW, groups, g.CV,
-                                                              g.lanes, g.pix_per_block, gsum);
+                                                              g.lanes, g.pix_per_block, eps, partial, tickets, stats);
   else
     gn_stats_kernel<float><<<grid, g.threads, smem, stream>>>((const float*)x0, C0, (const float*)x1, C1, HW, groups,
-                                                               g.CV, g.lanes, g.pix_per_block, gsum);
+                                                               g.CV, g.lanes, g.pix_per_block, eps, partial, tickets,
+                                                               stats);
   return after_launch("gn_stats_kernel");
 }
 
-int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const double* gsum,
-             const float* gamma, const float* beta, float eps, int swish, void* out, int prec, cudaStream_t stream) {
-  Geo g;
-  HSIDM_TRY(geometry(C0, C1, N, HW, &g));
-  const int C = C0 + C1;
+int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const void* scratch,
+             const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream) {
+  GnGeo g;
+  HSIDM_TRY(gn_geometry(C0, C1, N, HW, &g));
+  const float* stats = gn_stats_ptr(const_cast<void*>(scratch), N, g.slabs, groups);
   dim3 grid(g.slabs, N);
-  size_t smem = sizeof(float) * 2 * C;
+  ProfScope prof(PROF_GN_APPLY, 2.0 * N * HW * (C0 + C1) * (prec == HSIDM_BF16 ? 2 : 4), stream);
   if (prec == HSIDM_BF16)
-    gn_apply_kernel<bf16><<<grid, g.threads, smem, stream>>>((const bf16*)x0, C0, (const bf16*)x1, C1, HW, groups, g.CV,
-                                                              g.lanes, g.pix_per_block, gsum, gamma, beta, eps, swish,
-                                                              (bf16*)out);
+    gn_apply_kernel<bf16><<<grid, g.threads, 0, stream>>>((const bf16*)x0, C0, (const bf16*)x1, C1, HW, groups, g.CV,
+                                                           g.lanes, g.pix_per_block, stats, gamma, beta, swish, (bf16*)out);
   else
-    gn_apply_kernel<float><<<grid, g.threads, smem, stream>>>((const float*)x0, C0, (const float*)x1, C1, HW, groups,
-                                                               g.CV, g.lanes, g.pix_per_block, gsum, gamma, beta, eps,
-                                                               swish, (float*)out);
+    gn_apply_kernel<float><<<grid, g.threads, 0, stream>>>((const float*)x0, C0, (const float*)x1, C1, HW, groups, g.CV,
+                                                            g.lanes, g.pix_per_block, stats, gamma, beta, swish,
+                                                            (float*)out);
   return after_launch("gn_apply_kernel");
 }
 

@@ -79,6 +79,10 @@ struct hsidm_ctx {
     }
   } graph_key;
   int64_t graph_nodes = 0;  // kernels per replay (for hsidm_launch_count)
+  // hsidm_sample runs on its own non-blocking stream (the caller's may be the legacy default stream, which cannot
+  // be captured) and is stitched into the caller's stream with two events
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 namespace {
@@ -207,15 +211,17 @@ Act gn_act(hsidm_ctx* c, const Act& a, const Act* b, int gw, int gb, bool swish)
   Exec& ex = c->ex;
   const int C1 = b ? b->C : 0;
   const int groups = c->cfg.norm_groups;
-  double* gsum = static_cast<double*>(ex.alloc_raw(sizeof(double) * 2 * a.N * groups));
+  void* scratch = ex.alloc_raw(gn_scratch_bytes(a.C, C1, a.N, a.H * a.W, groups));
   Act out = ex.alloc_act(a.N, a.H, a.W, a.C + C1);
   const void* p1 = b ? b->p : nullptr;
-  ex.run([&] { return gn_stats(a.p, a.C, p1, C1, a.N, a.H * a.W, groups, gsum, ex.prec, ex.stream); });
   ex.run([&] {
-    return gn_apply(a.p, a.C, p1, C1, a.N, a.H * a.W, groups, gsum, c->ps.dev(gw), c->ps.dev(gb), kGnEps, swish ? 1 : 0,
-                    out.p, ex.prec, ex.stream);
+    return gn_stats(a.p, a.C, p1, C1, a.N, a.H * a.W, groups, kGnEps, scratch, ex.tickets, ex.prec, ex.stream);
   });
-  ex.release_raw(gsum);
+  ex.run([&] {
+    return gn_apply(a.p, a.C, p1, C1, a.N, a.H * a.W, groups, scratch, c->ps.dev(gw), c->ps.dev(gb), swish ? 1 : 0, out.p,
+                    ex.prec, ex.stream);
+  });
+  ex.release_raw(scratch);
   return out;
 }
 
@@ -387,6 +393,7 @@ int ensure_workspace(hsidm_ctx* c, int c0, int c1, int N, int H, int W) {
   if (c->ws_N == N && c->ws_H == H && c->ws_W == W) return HSIDM_OK;
   drop_graph(c);  // the arena may move
   Exec& ex = c->ex;
+  HSIDM_TRY(ex.ensure_tickets(N));
   ex.dry = true, ex.status = HSIDM_OK;
   ex.arena.begin(true);
   NoiseRef nz{nullptr, 0, nullptr, 0};
@@ -449,6 +456,12 @@ int hsidm_ctx_create(const hsidm_unet_cfg* cfg, int device, hsidm_ctx** out) {
   int s = c->ps.alloc_all();
   if (s == HSIDM_OK && cudaMalloc(&c->t_dev, 4 * sizeof(int)) != cudaSuccess) s = HSIDM_CUDA_ERROR;
   if (s == HSIDM_OK && cfg->precision == HSIDM_BF16) s = conv_tc_init();
+  if (s == HSIDM_OK && (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess)) {
+    set_last_error("could not create the sampler stream/events");
+    s = HSIDM_CUDA_ERROR;
+  }
   if (s != HSIDM_OK) {
     delete c;
     return s;
@@ -470,6 +483,9 @@ int hsidm_ctx_destroy(hsidm_ctx* c) {
   if (c->t_dev) cudaFree(c->t_dev);
   if (c->nbias_buf) cudaFree(c->nbias_buf);
   if (c->samp_buf) cudaFree(c->samp_buf);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_in) cudaEventDestroy(c->ev_in);
+  if (c->ev_out) cudaEventDestroy(c->ev_out);
   delete c;
   return HSIDM_OK;
 }
@@ -603,7 +619,8 @@ int hsidm_sample(hsidm_ctx* c, const float* cond, const float* x_T, const float*
                  int64_t tape_step_stride, uint64_t seed, float* out, float* snapshots, int N, int H, int W,
                  hsidm_stream stream_) {
   if (!c || !cond || !x_T || !out) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_sample: null argument");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  cudaStream_t caller = static_cast<cudaStream_t>(stream_);
+  cudaStream_t stream = c->side;
   HSIDM_CUDA(cudaSetDevice(c->device));
   if (c->cfg.in_channel % 2 || c->cfg.out_channel * 2 != c->cfg.in_channel)
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conditional sampling needs in_channel == 2*out_channel (diffusion.py:158)");
@@ -625,6 +642,9 @@ int hsidm_sample(hsidm_ctx* c, const float* cond, const float* x_T, const float*
   float* cond_b = c->samp_buf;
   float* x_b = c->samp_buf + n;
   float* eps_b = c->samp_buf + 2 * n;
+  // everything below is ordered after the caller's prior work ...
+  HSIDM_CUDA(cudaEventRecord(c->ev_in, caller));
+  HSIDM_CUDA(cudaStreamWaitEvent(stream, c->ev_in, 0));
   hsidm_ctx::GraphKey key;
   key.N = N, key.H = H, key.W = W, key.tape = noise_tape, key.s_img = tape_image_stride, key.s_step = tape_step_stride;
   key.snaps = snapshots;
@@ -671,6 +691,9 @@ int hsidm_sample(hsidm_ctx* c, const float* cond, const float* x_T, const float*
     g_launches += c->graph_nodes;
   }
   HSIDM_CUDA(cudaMemcpyAsync(out, x_b, sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
+  // ... and the caller's later work is ordered after the sampler
+  HSIDM_CUDA(cudaEventRecord(c->ev_out, stream));
+  HSIDM_CUDA(cudaStreamWaitEvent(caller, c->ev_out, 0));
   return HSIDM_OK;
 }
 

@@ -101,6 +101,10 @@ class GaussianDiffusion(nn.Module):
             noise = torch.randn_like(x)
         if t == 0:
             noise = None
+        if noise is not None:
+            noise = _lib.require_cuda_f32(noise, "noise")
+            if noise.shape != x.shape:
+                raise _lib.HsidmError(-1, f"noise shape {tuple(noise.shape)} != x shape {tuple(x.shape)}")
         x = x.contiguous()
         out = torch.empty_like(x)
         _lib.check(_lib.load().hsidm_posterior_step(h.ptr, int(t), x.data_ptr(), eps.data_ptr(), _lib.ptr(noise),

@@ -90,6 +90,12 @@ HSIDM_API int hsidm_version(void);
 HSIDM_API const char* hsidm_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (all contexts); used by bench.py. */
 HSIDM_API int64_t hsidm_launch_count(void);
+/* Opt-in per-kernel-class timing used by bench.py's roofline leg: while enabled, every launch outside graph capture
+ * is bracketed by CUDA events on its own stream. kind: 0 tensor-core conv, 1 CUDA-core conv, 2 GroupNorm stats,
+ * 3 GroupNorm apply, 4 attention GEMM, 5 posterior step. read() synchronises and returns the summed event time (ms),
+ * algorithmic work (FLOPs for 0/1/4, bytes for 2/3/5) and launch count since enable(1). */
+HSIDM_API int hsidm_prof_enable(int on);
+HSIDM_API int hsidm_prof_read(int kind, double* ms, double* work, int64_t* launches);
 
 /* ---- UNet + diffusion -------------------------------------------------------------------------- */
 

@@ -92,18 +92,21 @@ def test_gae_matches_reference(golden, tag):
     assert rel(y.numpy(), g[f"{tag}.dec"]) < 2e-6
 
 
-def test_end_to_end_cube_and_metrics(golden):
+@pytest.mark.parametrize("tag", ["e2e", "e2e_full"])
+def test_end_to_end_cube_and_metrics(golden, tag):
     from hsi_dmgasr_b200.spec import GAEGeometry
-    g = golden("e2e.npz")
-    geom, T, hw = GAEGeometry(31, 8, 2), int(g["T"]), 16
+    from tests.cfgs import FULL
+    g = golden(tag + ".npz")
+    cfg = SMALL if tag == "e2e" else FULL
+    geom, T, hw = GAEGeometry(31, 8, 2), int(g["T"]), int(g["hw"])
     gsd = synth.gae_state_dict(geom, 51)
-    usd = synth.unet_state_dict(SMALL, 52)
+    usd = synth.unet_state_dict(cfg, 52)
     tab = O.schedule_tables(O.beta_schedule("cosine", T, 1e-6, 1e-2))
     sr = synth.sr_cube(1, 31, hw, seed=53)
     hr = synth.sr_cube(1, 31, hw, seed=54)
     x_T, tape = synth.noise_tape(geom.G, T, 3, hw, hw, seed=55)
     with torch.no_grad():
-        cube = O.sr_cube(usd, SMALL.as_dict(), tab, gsd, geom.as_dict(), sr,
+        cube = O.sr_cube(usd, cfg.as_dict(), tab, gsd, geom.as_dict(), sr,
                          [x_T[i:i + 1] for i in range(geom.G)], lambda gi, i: tape[gi:gi + 1, T - 1 - i])
     assert rel(cube.numpy(), g["cube"]) < 1e-5
     pred = cube[0].permute(1, 2, 0).numpy()
