@@ -46,6 +46,7 @@ SIGNATURES = {
     "hsidm_last_error": (C.c_char_p, []),
     "hsidm_launch_count": (C.c_int64, []),
     "hsidm_prof_enable": (C.c_int, [C.c_int]),
+    "hsidm_prof_dump": (C.c_int, [C.c_char_p]),
     "hsidm_prof_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "hsidm_ctx_create": (C.c_int, [C.POINTER(UNetCfg), C.c_int, C.POINTER(_P)]),
     "hsidm_ctx_destroy": (C.c_int, [_P]),
@@ -74,6 +75,7 @@ SIGNATURES = {
                                      _P, _P, C.c_int]),
     "hsidm_debug_groupnorm": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
                                         C.c_float, C.c_int, _P]),
+    "hsidm_debug_conv_mode": (C.c_int, [C.c_int, C.c_int]),
     "hsidm_debug_tc_error_flag": (C.c_int, [C.POINTER(C.c_int)]),
 }
 

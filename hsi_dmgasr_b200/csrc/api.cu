@@ -15,6 +15,10 @@ int hsidm_prof_enable(int on) {
   g_prof_on = on != 0;
   return HSIDM_OK;
 }
+int hsidm_prof_dump(const char* path) {
+  if (!path) HSIDM_FAIL(HSIDM_BAD_ARG, "null path");
+  return prof_dump(path);
+}
 int hsidm_prof_read(int kind, double* ms, double* work, int64_t* launches) {
   if (!ms || !work || !launches || kind < 0 || kind >= PROF_KINDS) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_prof_read: bad argument");
   return prof_read(kind, ms, work, launches);
@@ -93,6 +97,11 @@ int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const void* x1,
     s = HSIDM_CUDA_ERROR;
   }
   return s;
+}
+
+int hsidm_debug_conv_mode(int no_halo, int base_offset_mode) {
+  conv_tc_set_mode(no_halo, base_offset_mode);
+  return HSIDM_OK;
 }
 
 int hsidm_debug_tc_error_flag(int* value) {

@@ -24,11 +24,12 @@ struct ProfRec {
   cudaEvent_t a, b;
   int kind;
   double work;
+  std::string tag;
 };
 std::vector<ProfRec> g_prof_recs;
 }  // namespace
 
-int prof_start(int kind, double work, cudaStream_t stream) {
+int prof_start(int kind, double work, cudaStream_t stream, const char* tag) {
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
     cudaGetLastError();
@@ -36,6 +37,7 @@ int prof_start(int kind, double work, cudaStream_t stream) {
   }
   ProfRec r;
   r.kind = kind, r.work = work;
+  if (tag) r.tag = tag;
   if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
   cudaEventRecord(r.a, stream);
   g_prof_recs.push_back(r);
@@ -60,6 +62,19 @@ int prof_read(int kind, double* ms, double* work, int64_t* launches) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) *ms += t, *work += r.work, *launches += 1;
   }
+  return HSIDM_OK;
+}
+
+int prof_dump(const char* path) {
+  HSIDM_CUDA(cudaDeviceSynchronize());
+  FILE* f = fopen(path, "w");
+  if (!f) HSIDM_FAIL(HSIDM_BAD_ARG, "cannot open %s", path);
+  fprintf(f, "kind,tag,work,ms\n");
+  for (auto& r : g_prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) fprintf(f, "%d,%s,%.6g,%.6f\n", r.kind, r.tag.c_str(), r.work, t);
+  }
+  fclose(f);
   return HSIDM_OK;
 }
 

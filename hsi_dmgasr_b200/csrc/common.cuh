@@ -47,14 +47,16 @@ extern int64_t g_launches;  // kernels launched by this library (bench.py report
 enum ProfKind { PROF_CONV_TC = 0, PROF_CONV_SIMT = 1, PROF_GN_STATS = 2, PROF_GN_APPLY = 3, PROF_GEMM = 4,
                 PROF_POSTERIOR = 5, PROF_OTHER = 6, PROF_KINDS = 7 };
 extern bool g_prof_on;
-int prof_start(int kind, double work, cudaStream_t stream);  // returns a token (<0: not recording)
+int prof_start(int kind, double work, cudaStream_t stream, const char* tag = nullptr);  // token (<0: not recording)
 void prof_stop(int token, cudaStream_t stream);
 void prof_reset();
 int prof_read(int kind, double* ms, double* work, int64_t* launches);
+int prof_dump(const char* path);  // one CSV line per recorded launch: kind,tag,work,ms
 struct ProfScope {
   int token;
   cudaStream_t stream;
-  ProfScope(int kind, double work, cudaStream_t s) : token(g_prof_on ? prof_start(kind, work, s) : -1), stream(s) {}
+  ProfScope(int kind, double work, cudaStream_t s, const char* tag = nullptr)
+      : token(g_prof_on ? prof_start(kind, work, s, tag) : -1), stream(s) {}
   ~ProfScope() {
     if (token >= 0) prof_stop(token, stream);
   }

@@ -1,0 +1,280 @@
+// tcgen05 3x3 convolution with the input halo resident in shared memory ("halo kernel").
+//
+// The per-tap kernel of conv_tc.cu re-fetches its A tile from L2 for each of the nine taps and streams one B tile
+// per 128 output pixels; at 1.4 PFLOP/s that is ~95 B/clk/SM of L2->SMEM traffic against the ~45 B/clk/SM the L2 can
+// deliver, which is what capped it at 20-47 % of tensor peak (profiles/r1_conv_tc_ncu.md).  This kernel raises the
+// arithmetic intensity per byte fetched:
+//   * a CTA owns MT sub-tiles of 8 x 16 output pixels side by side (8*MT x 16 pixels) and BN output channels;
+//   * per 64-channel chunk ONE TMA box {64 ch, 8*MT+2, 18, 1} brings the tile plus its 1-pixel halo into smem (zero
+//     filled outside the image = conv padding); all 9 taps x MT sub-tiles read it in place: the A operand of tap
+//     (dy,dx), sub-tile s is the same buffer addressed from row (1+dy)*PW + 8*s+1+dx with a 16-group stride of one
+//     halo row (SBO = PW*128 B).  8 pixels of one image row form one 8-row swizzle group, so the canonical K-major
+//     SWIZZLE_128B layout still applies; the hardware swizzle is a function of the shared-memory address bits, so a
+//     start address that is a multiple of 128 B (not 1024 B) addresses the rows TMA wrote.
+//   * one B tile (BN x 64 weights of one tap) feeds MT*4 MMAs instead of 4.
+// L2->SMEM bytes per MMA cycle drop from ~95 to ~35-40 B/clk/SM.
+// Accumulators: MT x BN fp32 columns per tile, double buffered (2*MT*BN <= 512 TMEM columns).
+// Warp roles as in conv_tc.cu: warp 0 TMA producer (A ring of 2 halo buffers + B ring), warp 1 MMA issuer,
+// warps 2..5 epilogue.
+#include <cstdlib>
+
+#include "tc_common.cuh"
+
+namespace hsidm {
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 192;
+constexpr int kRows = 16;          // output rows per tile
+constexpr int kHaloRows = kRows + 2;
+constexpr int kAStages = 2;
+
+struct HaloP {
+  int tiles_x, tiles_y;   // tiles per image
+  int m_tiles, n_tiles;
+  int chunks0, chunks1;   // 64-channel chunks of source 0 / 1
+  int base_offset_mode;   // debug knob: 1 -> put (addr>>7)&7 into the descriptor base_offset field
+  EpiP e;
+  int* err;
+};
+
+template <int MT, int BN>
+struct HCfg {
+  static constexpr int kPW = 8 * MT + 2;                                   // halo row pitch in pixels
+  static constexpr int kABox = kHaloRows * kPW * 128;                      // bytes one TMA box writes
+  static constexpr int kAStage = (kABox + 1023) / 1024 * 1024;             // keep every stage 1024-B aligned
+  static constexpr int kBStage = BN * 128;
+  static constexpr int kBudget = 212 * 1024;
+  static constexpr int kBStagesRaw = (kBudget - kAStages * kAStage) / kBStage;
+  static constexpr int kBStages = kBStagesRaw > 10 ? 10 : kBStagesRaw;
+  static constexpr int kTmemCols = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;
+  static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + 1024 + 512;
+  static_assert(kBStages >= 3, "not enough shared memory for the B ring");
+  static_assert(2 * MT * BN <= 512, "accumulators do not fit TMEM");
+};
+
+template <int MT, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB, const HaloP p) {
+  using C = HCfg<MT, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem + kAStages * C::kAStage;
+  uint8_t* tail = smem_b + C::kBStages * C::kBStage;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* a_empty = a_full + kAStages;
+  uint64_t* b_full = a_empty + kAStages;
+  uint64_t* b_empty = b_full + C::kBStages;
+  uint64_t* tfull_bar = b_empty + C::kBStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int chunks = p.chunks0 + p.chunks1;
+  const int tpi = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    if (p.chunks1) tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kAStages; ++s) mbar_init(smem_u32(&a_full[s]), 1), mbar_init(smem_u32(&a_empty[s]), 1);
+    for (int s = 0; s < C::kBStages; ++s) mbar_init(smem_u32(&b_full[s]), 1), mbar_init(smem_u32(&b_empty[s]), 1);
+    for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&tfull_bar[s]), 1), mbar_init(smem_u32(&tempty_bar[s]), 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        const int n = mt / tpi, r = mt - n * tpi;
+        const int y0 = (r / p.tiles_x) * kRows, x0 = (r % p.tiles_x) * (8 * MT);
+        for (int ch = 0; ch < chunks && ok; ++ch) {
+          ok = mbar_wait(smem_u32(&a_empty[as]), aph ^ 1, p.err, 1);
+          if (!ok) break;
+          const uint32_t fb = smem_u32(&a_full[as]);
+          mbar_expect_tx(fb, C::kABox);
+          if (ch < p.chunks0)
+            tma_load_4d(smem_u32(smem + as * C::kAStage), &tmA0, fb, ch * kBK, x0 - 1, y0 - 1, n);
+          else
+            tma_load_4d(smem_u32(smem + as * C::kAStage), &tmA1, fb, (ch - p.chunks0) * kBK, x0 - 1, y0 - 1, n);
+          if (++as == kAStages) as = 0, aph ^= 1;
+          for (int tap = 0; tap < 9; ++tap) {
+            ok = mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.err, 5);
+            if (!ok) break;
+            const uint32_t bb = smem_u32(&b_full[bs]);
+            mbar_expect_tx(bb, C::kBStage);
+            tma_load_2d(smem_u32(smem_b + bs * C::kBStage), &tmB, bb, (tap * chunks + ch) * kBK, nt * BN);
+            if (++bs == C::kBStages) bs = 0, bph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      constexpr uint64_t desc_hi = (uint64_t)((C::kPW * 128) >> 4) << 32 | (1ull << 46) | (2ull << 61) | (1ull << 16);
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        ok = mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 2);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+        for (int ch = 0; ch < chunks && ok; ++ch) {
+          ok = mbar_wait(smem_u32(&a_full[as]), aph, p.err, 3);
+          if (!ok) break;
+          const uint32_t a_base = smem_u32(smem + as * C::kAStage);
+          for (int tap = 0; tap < 9; ++tap) {
+            ok = mbar_wait(smem_u32(&b_full[bs]), bph, p.err, 6);
+            if (!ok) break;
+            tc_fence_after();
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + bs * C::kBStage));
+            const int dy = tap / 3, dx = tap % 3;   // already offset by the +1 halo
+#pragma unroll
+            for (int s = 0; s < MT; ++s) {
+              const uint32_t a_addr = a_base + (uint32_t)((dy * C::kPW + 8 * s + dx) * 128);
+              uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
+              if (p.base_offset_mode) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k)
+                umma_f16(d_tmem + s * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | tap | k) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&b_empty[bs]));
+            if (++bs == C::kBStages) bs = 0, bph ^= 1;
+          }
+          umma_commit(smem_u32(&a_empty[as]));
+          if (++as == kAStages) as = 0, aph ^= 1;
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));
+        if (++acc == 2) acc = 0, acc_phase ^= 1;
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;   // accumulator row: pixel (row/8, row%8) of a sub-tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const float* nbias = p.e.nbias ? p.e.nbias + (p.e.nb_t ? (long long)(*p.e.nb_t) * p.e.nb_ts : 0) : nullptr;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int n = mt / tpi, r = mt - n * tpi;
+      const int y = (r / p.tiles_x) * kRows + (row >> 3);
+      const int xb = (r % p.tiles_x) * (8 * MT) + (row & 7);
+      ok = mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 4);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * (MT * BN) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int s = 0; s < MT; ++s) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + s * BN + c0, v);
+          tmem_ld_wait();
+          const int co0 = nt * BN + c0;
+          if (co0 < p.e.Cout) epilogue16(p.e, nbias, n, y, xb + 8 * s, co0, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) acc = 0, acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// (MT, BN) for an op, or MT = 0 when the halo kernel does not apply.
+void pick_shape(const ConvOp& op, int* MT, int* BN) {
+  *MT = 0, *BN = 0;
+  if (op.ksize != 3 || op.stride != 1 || op.up) return;
+  if (op.Hin % kRows) return;
+  if (op.Cout % 128 == 0 && op.Win % 16 == 0) {
+    *MT = 2, *BN = 128;
+  } else if (op.Cout % 64 == 0 && op.Win % 32 == 0) {
+    *MT = 4, *BN = 64;
+  } else if (op.Cout <= 16 && op.Win % 32 == 0) {
+    *MT = 4, *BN = 16;
+  }
+}
+
+template <int MT, int BN>
+int launch(const ConvOp& op, cudaStream_t stream) {
+  using C = HCfg<MT, BN>;
+  HaloP p;
+  p.tiles_x = op.Win / (8 * MT);
+  p.tiles_y = op.Hin / kRows;
+  p.m_tiles = op.N * p.tiles_x * p.tiles_y;
+  p.n_tiles = (int)ceil_div(op.Cout, BN);
+  p.chunks0 = op.src[0].C / kBK;
+  p.chunks1 = op.src[1].C / kBK;
+  p.base_offset_mode = host().base_offset_mode;
+  fill_epilogue(&p.e, op);
+  p.err = host().err_flag;
+  CUtensorMap tmA0, tmA1, tmB;
+  HSIDM_TRY(encode_act_map(&tmA0, op.src[0].p, op.N, op.Hin, op.Win, op.src[0].C, C::kPW, kHaloRows, 1));
+  if (p.chunks1)
+    HSIDM_TRY(encode_act_map(&tmA1, op.src[1].p, op.N, op.Hin, op.Win, op.src[1].C, C::kPW, kHaloRows, 1));
+  else
+    tmA1 = tmA0;
+  const int K = op.K();
+  HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, BN));
+  const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
+  char tag[96];
+  snprintf(tag, sizeof(tag), "halo MT%d BN%d cin%d+%d cout%d %dx%d n%d", MT, BN, op.src[0].C, op.src[1].C, op.Cout, op.Hin, op.Win, op.N);
+  ProfScope prof(PROF_CONV_TC, 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * K, stream, tag);
+  conv_halo_kernel<MT, BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p);
+  return after_launch("conv_halo_kernel");
+}
+
+}  // namespace
+
+int conv_halo_init() {
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 128>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 16>::kSmemBytes));
+  return HSIDM_OK;
+}
+
+// Assumes conv_tc_supported(op) already holds (bf16 NHWC sources with 64-multiple channels, Cout fits an N tile).
+bool conv_halo_supported(const ConvOp& op) {
+  int MT, BN;
+  pick_shape(op, &MT, &BN);
+  if (MT == 0) return false;
+  // the packed weight rows are padded to pick_bn(Cout); the halo kernel's BN must divide that padding
+  return tc::pick_bn(op.Cout) % BN == 0;
+}
+
+int conv_halo(const ConvOp& op, cudaStream_t stream) {
+  int MT, BN;
+  pick_shape(op, &MT, &BN);
+  if (MT == 2 && BN == 128) return launch<2, 128>(op, stream);
+  if (MT == 4 && BN == 64) return launch<4, 64>(op, stream);
+  if (MT == 4 && BN == 16) return launch<4, 16>(op, stream);
+  HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_halo: unsupported shape");
+}
+
+}  // namespace hsidm

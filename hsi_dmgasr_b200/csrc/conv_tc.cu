@@ -15,129 +15,29 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 // Persistent: grid = min(#tiles, #SMs); tiles are walked n-tile-fastest so the CTAs in flight share A tiles in L2.
-#include <cuda.h>
-
+#include <cstdlib>
 #include <mutex>
 
-#include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace hsidm {
 namespace {
 
-constexpr int kBM = 128;       // UMMA M
-constexpr int kBK = 64;        // bf16 elements per k-block = one 128-byte swizzle line
+using namespace tc;
+
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 200 * 1024;
-constexpr uint32_t kSpinLimit = 1u << 24;
 
 struct TcP {
-  int M, N_img, H, W, Cout;
+  int M;
   int bw, bh, bn;          // box extents: x, y, image
   int tiles_x, tiles_y;    // tiles per image along x / y (bn == 1)
   int m_tiles, n_tiles;
   int taps;                // 1 or 9
   int chunks0, chunks1;    // 64-channel chunks taken from source 0 / source 1
-  const float* bias;
-  const float* nbias;
-  long long nbs;
-  const int* nb_t;
-  long long nb_ts;
-  int act;
-  float scale;
-  const bf16* resid;
-  void* out;
-  int out_layout, clamp01;
+  EpiP e;
   int* err;                // device flag set when a barrier wait times out (never in a healthy run)
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a descriptor or protocol bug must not hang the GPU box.  Returns false on timeout.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-  for (uint32_t i = 0; i < kSpinLimit; ++i)
-    if (mbar_try_wait(bar, parity)) return true;
-  if (err) atomicExch(err, code);
-  return false;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row groups are 1024 B apart (SBO), LBO unused (=1),
-// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 template <int BN>
 struct Cfg {
@@ -261,8 +161,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int row = quarter * 32 + lane;     // accumulator row = pixel within the tile
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int HW = p.H * p.W;
-    const float* nbias = p.nbias ? p.nbias + (p.nb_t ? (long long)(*p.nb_t) * p.nb_ts : 0) : nullptr;
+    const float* nbias = p.e.nbias ? p.e.nbias + (p.e.nb_t ? (long long)(*p.e.nb_t) * p.e.nb_ts : 0) : nullptr;
     bool ok = true;
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
@@ -278,8 +177,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         y = (r / p.tiles_x) * p.bh + row / p.bw;
         x = (r % p.tiles_x) * p.bw + row % p.bw;
       }
-      const bool valid = n < p.N_img;
-      const long long m = ((long long)n * p.H + y) * p.W + x;
+      const bool valid = n < p.e.N_img;
       ok = mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 4);
       if (!ok) break;
       tc_fence_after();
@@ -290,66 +188,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tmem_ld16(taddr + c0, r);
         tmem_ld_wait();
         const int co0 = nt * BN + c0;
-        if (valid && co0 < p.Cout) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.out_layout == L_NHWC) {
-            // Cout is a multiple of 16 on this path
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
-                v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
-              }
-            }
-            if (nbias) {
-              const float* nb = nbias + (long long)n * p.nbs + co0;
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(nb + j));
-                v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
-              }
-            }
-            if (p.act == ACT_LRELU) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
-            }
-            if (p.scale != 1.0f) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] *= p.scale;
-            }
-            if (p.resid) {
-              const bf16* rp = p.resid + m * p.Cout + co0;
-              float a[8], b[8];
-              load8(rp, a);
-              load8(rp + 8, b);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += a[j], v[8 + j] += b[j];
-            }
-            bf16* op = static_cast<bf16*>(p.out) + m * p.Cout + co0;
-            float lo[8], hi[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) lo[j] = v[j], hi[j] = v[8 + j];
-            store8(op, lo);
-            store8(op + 8, hi);
-          } else {
-            // fp32 NCHW (last UNet layer / GAE outputs): a handful of channels, scalar tail-safe path
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int co = co0 + j;
-              if (co < p.Cout) {
-                float o = v[j];
-                if (p.bias) o += __ldg(p.bias + co);
-                if (nbias) o += __ldg(nbias + (long long)n * p.nbs + co);
-                if (p.act == ACT_LRELU) o = o > 0.f ? o : 0.01f * o;
-                o *= p.scale;
-                if (p.clamp01) o = fminf(fmaxf(o, 0.f), 1.f);
-                static_cast<float*>(p.out)[((long long)n * p.Cout + co) * HW + (long long)y * p.W + x] = o;
-              }
-            }
-          }
-        }
+        if (valid && co0 < p.e.Cout) epilogue16(p.e, nbias, n, y, x, co0, r);
       }
       tc_fence_before();
       __syncwarp();
@@ -367,59 +206,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-int g_num_sms = 0;
-int* g_err_flag = nullptr;
 std::once_flag g_once;
 int g_init_status = HSIDM_OK;
 
 int do_init() {
+  Host& h = host();
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   HSIDM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess)
     HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
-  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  h.encode = reinterpret_cast<EncodeTiledFn>(fn);
   int dev = 0;
   HSIDM_CUDA(cudaGetDevice(&dev));
   cudaDeviceProp prop;
   HSIDM_CUDA(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "tensor-core path needs sm_100 (found sm_%d%d)", prop.major, prop.minor);
-  g_num_sms = prop.multiProcessorCount;
+  h.num_sms = prop.multiProcessorCount;
   HSIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<16>::kSmemBytes));
   HSIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::kSmemBytes));
   HSIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::kSmemBytes));
   HSIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmemBytes));
-  HSIDM_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
-  HSIDM_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
-  return HSIDM_OK;
-}
-
-int encode_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: %d", N, H, W, C, (int)r);
-  return HSIDM_OK;
-}
-
-int encode_weight_map(CUtensorMap* map, const void* base, int K, int rows, int bn_rows) {
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)bn_rows};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled(weights %dx%d) failed: %d", rows, K, (int)r);
-  return HSIDM_OK;
+  HSIDM_CUDA(cudaMalloc(&h.err_flag, sizeof(int)));
+  HSIDM_CUDA(cudaMemset(h.err_flag, 0, sizeof(int)));
+  return conv_halo_init();
 }
 
 bool tile_geometry(int H, int W, int* bw, int* bh, int* bn) {
@@ -441,6 +251,46 @@ bool tile_geometry(int H, int W, int* bw, int* bh, int* bn) {
   return true;
 }
 
+}  // namespace
+
+namespace tc {
+
+Host& host() {
+  static Host h;
+  return h;
+}
+
+int encode_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = host().encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: %d", N, H, W, C, (int)r);
+  return HSIDM_OK;
+}
+
+int encode_weight_map(CUtensorMap* map, const void* base, int K, int rows, int bn_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)bn_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = host().encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled(weights %dx%d) failed: %d", rows, K, (int)r);
+  return HSIDM_OK;
+}
+
+void fill_epilogue(EpiP* e, const ConvOp& op) {
+  e->N_img = op.N, e->H = op.Hout, e->W = op.Wout, e->Cout = op.Cout;
+  e->bias = op.bias, e->nbias = op.nbias, e->nbs = op.nbias_stride, e->nb_t = op.nbias_t, e->nb_ts = op.nbias_t_stride;
+  e->act = op.act, e->scale = op.scale, e->resid = static_cast<const bf16*>(op.resid), e->out = op.out;
+  e->out_layout = op.out_layout, e->clamp01 = op.clamp01;
+}
+
 int pick_bn(int Cout) {
   if (Cout <= 16) return 16;
   if (Cout % 256 == 0) return 256;
@@ -449,11 +299,19 @@ int pick_bn(int Cout) {
   return 0;
 }
 
-}  // namespace
+}  // namespace tc
 
 int conv_tc_init() {
-  std::call_once(g_once, [] { g_init_status = do_init(); });
+  std::call_once(g_once, [] {
+    g_init_status = do_init();
+    if (std::getenv("HSIDM_NO_HALO")) tc::host().no_halo = 1;   // A/B switch for profiling runs
+  });
   return g_init_status;
+}
+
+void conv_tc_set_mode(int no_halo, int base_offset_mode) {
+  tc::host().no_halo = no_halo;
+  tc::host().base_offset_mode = base_offset_mode;
 }
 
 int conv_tc_bn_rows(int Cout) { return pick_bn(Cout); }
@@ -476,10 +334,11 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
   if (!conv_tc_supported(op, HSIDM_BF16))
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: op (Cin %d+%d, Cout %d, k%d s%d, %dx%d) does not fit the tensor-core kernel",
                op.src[0].C, op.src[1].C, op.Cout, op.ksize, op.stride, op.Hin, op.Win);
+  if (!host().no_halo && conv_halo_supported(op)) return conv_halo(op, stream);
   TcP p;
   tile_geometry(op.Hin, op.Win, &p.bw, &p.bh, &p.bn);
   const int BN = pick_bn(op.Cout);
-  p.N_img = op.N, p.H = op.Hin, p.W = op.Win, p.Cout = op.Cout;
+  fill_epilogue(&p.e, op);
   p.M = op.N * op.Hin * op.Win;
   p.tiles_x = op.Win / p.bw;
   p.tiles_y = op.Hin / p.bh;
@@ -488,9 +347,7 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
   p.taps = op.ksize * op.ksize;
   p.chunks0 = op.src[0].C / kBK;
   p.chunks1 = op.src[1].C / kBK;
-  p.bias = op.bias, p.nbias = op.nbias, p.nbs = op.nbias_stride, p.nb_t = op.nbias_t, p.nb_ts = op.nbias_t_stride, p.act = op.act, p.scale = op.scale;
-  p.resid = static_cast<const bf16*>(op.resid), p.out = op.out, p.out_layout = op.out_layout, p.clamp01 = op.clamp01;
-  p.err = g_err_flag;
+  p.err = host().err_flag;
 
   CUtensorMap tmA0, tmA1, tmB;
   HSIDM_TRY(encode_act_map(&tmA0, op.src[0].p, op.N, op.Hin, op.Win, op.src[0].C, p.bw, p.bh, p.bn));
@@ -501,8 +358,11 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
   const int K = op.K();
   HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, BN));
 
-  const int grid = std::min(p.m_tiles * p.n_tiles, g_num_sms);
-  ProfScope prof(PROF_CONV_TC, 2.0 * p.M * (double)op.Cout * K, stream);
+  const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
+  char tag[96];
+  snprintf(tag, sizeof(tag), "pertap BN%d k%d cin%d+%d cout%d %dx%d n%d", BN, op.ksize, op.src[0].C, op.src[1].C, op.Cout, op.Hin,
+           op.Win, op.N);
+  ProfScope prof(PROF_CONV_TC, 2.0 * p.M * (double)op.Cout * K, stream, tag);
   switch (BN) {
     case 16: conv_tc_kernel<16><<<grid, kThreads, Cfg<16>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;
     case 64: conv_tc_kernel<64><<<grid, kThreads, Cfg<64>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;
@@ -515,10 +375,11 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
 // Reads and clears the barrier-timeout flag (0 = healthy). Synchronises the device; test/debug use only.
 int conv_tc_error_flag(int* value) {
   *value = 0;
-  if (!g_err_flag) return HSIDM_OK;
+  int* flag = tc::host().err_flag;
+  if (!flag) return HSIDM_OK;
   HSIDM_CUDA(cudaDeviceSynchronize());
-  HSIDM_CUDA(cudaMemcpy(value, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost));
-  HSIDM_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
+  HSIDM_CUDA(cudaMemcpy(value, flag, sizeof(int), cudaMemcpyDeviceToHost));
+  HSIDM_CUDA(cudaMemset(flag, 0, sizeof(int)));
   return HSIDM_OK;
 }
 

@@ -48,6 +48,7 @@ bool conv_tc_supported(const ConvOp& op, int prec);
 int conv_tc(const ConvOp& op, cudaStream_t stream);
 int conv_tc_init();               // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int conv_tc_bn_rows(int Cout);    // N-tile height; packed bf16 weights are padded to a multiple of it (0 = unsupported)
+void conv_tc_set_mode(int no_halo, int base_offset_mode);  // test knobs
 int conv_tc_error_flag(int* v);   // barrier-timeout flag of the tensor-core kernel (synchronises; tests only)
 
 // Batched GEMM on CUDA cores: C[b] = alpha * A[b] (MxK, row-major lda) * op(B[b]); B is [N][K] (transB=1)

@@ -1,0 +1,210 @@
+// Shared device/host pieces of the tcgen05 convolution kernels (conv_tc.cu: per-tap TMA boxes; conv_halo.cu: halo tile
+// resident in shared memory and reused by all nine taps).
+#pragma once
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace hsidm {
+namespace tc {
+
+constexpr int kBM = 128;       // UMMA M
+constexpr int kBK = 64;        // bf16 elements per k-block = one 128-byte swizzle line
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+// Everything the epilogue needs to turn an fp32 accumulator row into output pixels.
+struct EpiP {
+  int N_img, H, W, Cout;
+  const float* bias;
+  const float* nbias;
+  long long nbs;
+  const int* nb_t;
+  long long nb_ts;
+  int act;
+  float scale;
+  const bf16* resid;
+  void* out;
+  int out_layout, clamp01;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+static __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+static __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+static __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+static __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a descriptor or protocol bug must not hang the GPU box.  Returns false on timeout.
+static __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  for (uint32_t i = 0; i < kSpinLimit; ++i)
+    if (mbar_try_wait(bar, parity)) return true;
+  if (err) atomicExch(err, code);
+  return false;
+}
+static __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+static __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+static __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+static __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+static __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+static __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+static __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+static __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+static __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+static __device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+static __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+static __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row groups are 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
+static __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24.
+static __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+
+// 16 consecutive output channels [co0, co0+16) of pixel (n, y, x): +bias +noise bias -> act -> *scale -> +resid -> store.
+static __device__ __forceinline__ void epilogue16(const EpiP& p, const float* nbias, int n, int y, int x, int co0,
+                                                  const uint32_t (&r)[16]) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.out_layout == L_NHWC) {
+    const long long m = ((long long)n * p.H + y) * p.W + x;
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + j));
+        v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+      }
+    }
+    if (nbias) {
+      const float* nb = nbias + (long long)n * p.nbs + co0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(nb + j));
+        v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+      }
+    }
+    if (p.act == ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
+    }
+    if (p.scale != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= p.scale;
+    }
+    if (p.resid) {
+      const bf16* rp = p.resid + m * p.Cout + co0;
+      float a[8], b[8];
+      load8(rp, a);
+      load8(rp + 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += a[j], v[8 + j] += b[j];
+    }
+    bf16* op = static_cast<bf16*>(p.out) + m * p.Cout + co0;
+    float lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lo[j] = v[j], hi[j] = v[8 + j];
+    store8(op, lo);
+    store8(op + 8, hi);
+  } else {
+    // fp32 NCHW (last UNet layer / GAE outputs): a handful of channels, scalar tail-safe path
+    const long long HW = (long long)p.H * p.W;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int co = co0 + j;
+      if (co < p.Cout) {
+        float o = v[j];
+        if (p.bias) o += __ldg(p.bias + co);
+        if (nbias) o += __ldg(nbias + (long long)n * p.nbs + co);
+        if (p.act == ACT_LRELU) o = o > 0.f ? o : 0.01f * o;
+        o *= p.scale;
+        if (p.clamp01) o = fminf(fmaxf(o, 0.f), 1.f);
+        static_cast<float*>(p.out)[((long long)n * p.Cout + co) * HW + (long long)y * p.W + x] = o;
+      }
+    }
+  }
+}
+
+// ---- host side shared state ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct Host {
+  EncodeTiledFn encode = nullptr;
+  int num_sms = 0;
+  int* err_flag = nullptr;
+  int no_halo = 0;           // test knob: 1 -> always use the per-tap kernel of conv_tc.cu
+  int base_offset_mode = 0;  // test knob for the halo kernel's A descriptors
+};
+Host& host();
+// NHWC bf16 activation [N,H,W,C] as a 4-D tensor map with box {64, bw, bh, bn} and 128B swizzle (OOB reads are zero).
+int encode_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bw, int bh, int bn);
+// K-major bf16 weights [rows][K] with box {64, bn_rows}.
+int encode_weight_map(CUtensorMap* map, const void* base, int K, int rows, int bn_rows);
+void fill_epilogue(EpiP* e, const ConvOp& op);
+int pick_bn(int Cout);
+
+}  // namespace tc
+
+// conv_halo.cu
+bool conv_halo_supported(const ConvOp& op);
+int conv_halo(const ConvOp& op, cudaStream_t stream);
+int conv_halo_init();
+
+}  // namespace hsidm

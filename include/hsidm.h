@@ -96,6 +96,8 @@ HSIDM_API int64_t hsidm_launch_count(void);
  * algorithmic work (FLOPs for 0/1/4, bytes for 2/3/5) and launch count since enable(1). */
 HSIDM_API int hsidm_prof_enable(int on);
 HSIDM_API int hsidm_prof_read(int kind, double* ms, double* work, int64_t* launches);
+/* Writes one CSV line per recorded launch (kind,tag,work,ms); synchronises. */
+HSIDM_API int hsidm_prof_dump(const char* path);
 
 /* ---- UNet + diffusion -------------------------------------------------------------------------- */
 

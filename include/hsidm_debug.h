@@ -24,6 +24,10 @@ HSIDM_API int hsidm_debug_conv2d(int backend, int precision, const void* src0, i
 HSIDM_API int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const void* x1, int c1, int N, int HW, int groups,
                           const float* gamma, const float* beta, float eps, int swish, void* out);
 
+/* Kernel-selection knobs for A/B tests: no_halo = 1 forces the per-tap tcgen05 kernel for every 3x3 conv;
+ * base_offset_mode selects how the halo kernel fills the UMMA descriptor base-offset field (0 = zero). */
+HSIDM_API int hsidm_debug_conv_mode(int no_halo, int base_offset_mode);
+
 /* Reads and clears the tensor-core kernel's barrier-timeout flag (0 = healthy). */
 HSIDM_API int hsidm_debug_tc_error_flag(int* value);
 

@@ -101,8 +101,24 @@ TC_CASES = [
 ]
 
 
+TC_CASES += [
+    (2, 64, 0, 32, 32, 64, 3),        # halo kernel <4,64>, one tile per image
+    (3, 64, 64, 16, 32, 128, 3),      # halo kernel <2,128>, two sources, two tiles per row
+    (1, 192, 0, 48, 64, 64, 3),       # three chunks, H = 3 tiles
+]
+
+
+@pytest.fixture(params=["halo", "pertap"])
+def conv_mode(request):
+    from hsi_dmgasr_b200 import _lib
+    lib = _lib.load()
+    lib.hsidm_debug_conv_mode(1 if request.param == "pertap" else 0, 0)
+    yield request.param
+    lib.hsidm_debug_conv_mode(0, 0)
+
+
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv_tc_matches_torch(case):
+def test_conv_tc_matches_torch(case, conv_mode):
     n, c0, c1, h, w, cout, k = case
     x0 = randn((n, c0, h, w), 11)
     x1 = randn((n, c1, h, w), 12) if c1 else None
@@ -119,7 +135,7 @@ def test_conv_tc_matches_torch(case):
     assert rel_l2(got, simt) < 6e-3
 
 
-def test_conv_tc_epilogue_variants():
+def test_conv_tc_epilogue_variants(conv_mode):
     x = randn((2, 64, 16, 16), 21)
     wt, b = randn((64, 64, 3, 3), 22, scale=0.05), randn((64,), 23)
     got = conv2d(TC, "bf16", x, None, wt, b, ksize=3, act=1, scale=0.1, resid=x)
@@ -129,7 +145,7 @@ def test_conv_tc_epilogue_variants():
     assert tc_flag() == 0 and rel_l2(got, ref_conv(bf(x), None, bf(wt), None)) < 6e-3
 
 
-def test_conv_tc_small_cout_nchw_out():
+def test_conv_tc_small_cout_nchw_out(conv_mode):
     x = randn((2, 64, 32, 32), 31)
     wt, b = randn((3, 64, 3, 3), 32, scale=0.05), randn((3,), 33)
     got = conv2d(TC, "bf16", x, None, wt, b, ksize=3, out_nchw=True)
