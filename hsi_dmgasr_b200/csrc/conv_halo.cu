@@ -45,11 +45,12 @@ struct HCfg {
   static constexpr int kABox = kHaloRows * kPW * 128;                      // bytes one TMA box writes
   static constexpr int kAStage = (kABox + 1023) / 1024 * 1024;             // keep every stage 1024-B aligned
   static constexpr int kBStage = BN * 128;
-  static constexpr int kBudget = 212 * 1024;
+  static constexpr int kStageBytes = 4 * 4096;                             // epilogue staging, 4 KB per epilogue warp
+  static constexpr int kBudget = 212 * 1024 - kStageBytes;
   static constexpr int kBStagesRaw = (kBudget - kAStages * kAStage) / kBStage;
   static constexpr int kBStages = kBStagesRaw > 10 ? 10 : kBStagesRaw;
   static constexpr int kTmemCols = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;
-  static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + 1024 + 512;
+  static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + kStageBytes + 1024 + 512;
   static_assert(kBStages >= 3, "not enough shared memory for the B ring");
   static_assert(2 * MT * BN <= 512, "accumulators do not fit TMEM");
 };
@@ -62,7 +63,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem + kAStages * C::kAStage;
-  uint8_t* tail = smem_b + C::kBStages * C::kBStage;
+  uint8_t* smem_stage = smem_b + C::kBStages * C::kBStage;
+  uint8_t* tail = smem_stage + C::kStageBytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* a_empty = a_full + kAStages;
   uint64_t* b_full = a_empty + kAStages;
@@ -181,15 +183,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (!ok) break;
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * (MT * BN) + ((uint32_t)(quarter * 32) << 16);
+      if constexpr (BN % 64 == 0) {
+        uint4* stage = reinterpret_cast<uint4*>(smem_stage + (warp - 2) * 4096);
+        const int ty0 = (r / p.tiles_x) * kRows, tx0 = (r % p.tiles_x) * (8 * MT);
 #pragma unroll 1
-      for (int s = 0; s < MT; ++s) {
+        for (int s = 0; s < MT; ++s) {
+          auto pix = [&](int R, int& pn, long long& pm) {
+            pn = n;
+            pm = ((long long)n * p.e.H + ty0 + (R >> 3)) * p.e.W + tx0 + 8 * s + (R & 7);
+          };
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + s * BN + c0, v);
-          tmem_ld_wait();
-          const int co0 = nt * BN + c0;
-          if (co0 < p.e.Cout) epilogue16(p.e, nbias, n, y, xb + 8 * s, co0, v);
+          for (int c0 = 0; c0 < BN; c0 += 64)
+            epilogue_rows64(p.e, nbias, taddr + s * BN + c0, quarter, lane, nt * BN + c0, stage, pix);
+        }
+      } else {
+#pragma unroll 1
+        for (int s = 0; s < MT; ++s) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + s * BN + c0, v);
+            tmem_ld_wait();
+            const int co0 = nt * BN + c0;
+            if (co0 < p.e.Cout) epilogue16(p.e, nbias, n, y, xb + 8 * s, co0, v);
+          }
         }
       }
       tc_fence_before();

@@ -229,7 +229,8 @@ int do_init() {
   HSIDM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::kSmemBytes));
   HSIDM_CUDA(cudaMalloc(&h.err_flag, sizeof(int)));
   HSIDM_CUDA(cudaMemset(h.err_flag, 0, sizeof(int)));
-  return conv_halo_init();
+  HSIDM_TRY(conv_halo_init());
+  return gemm_tc_init();
 }
 
 bool tile_geometry(int H, int W, int* bw, int* bh, int* bn) {

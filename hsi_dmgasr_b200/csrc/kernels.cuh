@@ -64,6 +64,21 @@ struct GemmOp {
 };
 int gemm_simt(const GemmOp& op, int prec, cudaStream_t stream);
 int softmax_rows(float* x, int64_t rows, int cols, cudaStream_t stream);  // in place, fp32
+int softmax_rows_bf16(const float* x, void* p_bf16, int64_t rows, int cols, cudaStream_t stream);  // fp32 in, bf16 out
+
+// gemm_tc.cu : the same contraction on tcgen05 (bf16 K-major operands, A/B batch stride 0 = shared operand).
+struct GemmTcOp {
+  const void* A = nullptr;
+  const void* B = nullptr;
+  void* C = nullptr;
+  int M = 0, N = 0, K = 0, batch = 1;
+  int64_t lda = 0, ldb = 0, ldc = 0, sA = 0, sB = 0, sC = 0;
+  int c_f32 = 0;
+  float alpha = 1.0f;
+};
+bool gemm_tc_supported(const GemmTcOp& op);
+int gemm_tc(const GemmTcOp& op, cudaStream_t stream);
+int gemm_tc_init();
 
 // GroupNorm over the (virtual) concatenation of two NHWC tensors with the same N,H,W (deterministic reduction).
 // scratch: gn_scratch_bytes() bytes = per-block partials followed by the published (mean, rstd) pairs.

@@ -189,6 +189,37 @@ __global__ void softmax_kernel(float* __restrict__ x, int64_t rows, int cols) {
   for (int i = lane; i < cols; i += 32) p[i] *= inv;
 }
 
+// one warp per row: fp32 scores in, normalised bf16 probabilities out (operand of the P*V tensor-core GEMM)
+__global__ void softmax_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, int64_t rows, int cols) {
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* p = reinterpret_cast<const float4*>(x + row * cols);
+  const int n4 = cols >> 2;
+  float m = -INFINITY;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = p[i];
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  m = warp_max(m);
+  float s = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = p[i];
+    s += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+  }
+  s = warp_sum(s);
+  const float inv = 1.0f / s;
+  uint2* o = reinterpret_cast<uint2*>(out + row * cols);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = p[i];
+    uint2 w;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&w);
+    h[0] = __floats2bfloat162_rn(__expf(v.x - m) * inv, __expf(v.y - m) * inv);
+    h[1] = __floats2bfloat162_rn(__expf(v.z - m) * inv, __expf(v.w - m) * inv);
+    o[i] = w;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // GAE: CALayer global average pool. One block per image (deterministic: fixed-order fold, no float atomics);
 // thread -> (lane, channel), C <= 256.
@@ -324,6 +355,13 @@ int im2col_s2(const void* x, void* out, int N, int H, int W, int C, cudaStream_t
 int softmax_rows(float* x, int64_t rows, int cols, cudaStream_t stream) {
   softmax_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, stream>>>(x, rows, cols);
   return after_launch("softmax_kernel");
+}
+
+int softmax_rows_bf16(const float* x, void* p_bf16, int64_t rows, int cols, cudaStream_t stream) {
+  if (cols % 4) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "softmax_rows_bf16: cols=%d not a multiple of 4", cols);
+  ProfScope prof(PROF_OTHER, (double)rows * cols * 6, stream, "softmax");
+  softmax_bf16_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, stream>>>(x, static_cast<bf16*>(p_bf16), rows, cols);
+  return after_launch("softmax_bf16_kernel");
 }
 
 int channel_mean(const void* x, int N, int HW, int C, float* mean, int prec, cudaStream_t stream) {

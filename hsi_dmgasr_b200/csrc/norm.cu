@@ -17,6 +17,21 @@ namespace {
 constexpr int kMaxThreads = 256;
 constexpr int kUnroll = 4;
 
+// Swish.  fp32 mode keeps the exact x*sigmoid(x); bf16 mode uses the single-MUFU identity sigmoid(y) = 0.5 + 0.5*tanh(y/2)
+// (tanh.approx error ~2^-11, far below the bf16 rounding of the result) so the pass stays HBM-bound, not MUFU-bound.
+template <typename AT>
+__device__ __forceinline__ float swish_act(float y);
+template <>
+__device__ __forceinline__ float swish_act<float>(float y) {
+  return swish_f(y);
+}
+template <>
+__device__ __forceinline__ float swish_act<bf16>(float y) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+  return y * fmaf(0.5f, t, 0.5f);
+}
+
 template <typename AT>
 __device__ __forceinline__ const AT* src_ptr(const AT* x0, int C0, const AT* x1, int C1, int64_t pix, int c) {
   return c < C0 ? x0 + pix * C0 + c : x1 + pix * C1 + (c - C0);
@@ -24,7 +39,7 @@ __device__ __forceinline__ const AT* src_ptr(const AT* x0, int C0, const AT* x1,
 
 // grid = (slabs, N); block = lanes*CV threads, CV = C/8 channel-vectors, each thread owns one channel-vector.
 template <typename AT>
-__global__ void __launch_bounds__(kMaxThreads)
+__global__ void __launch_bounds__(kMaxThreads, 4)
 gn_stats_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, int C1, int HW, int groups, int CV,
                 int lanes, int pix_per_block, float eps, double* __restrict__ partial /*[N][slabs][groups][2]*/,
                 unsigned* __restrict__ tickets /*[N], zero on entry and on exit*/, float* __restrict__ stats) {
@@ -97,7 +112,7 @@ gn_stats_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, in
 }
 
 template <typename AT>
-__global__ void __launch_bounds__(kMaxThreads)
+__global__ void __launch_bounds__(kMaxThreads, 4)
 gn_apply_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, int C1, int HW, int groups, int CV,
                 int lanes, int pix_per_block, const float* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int swish, AT* __restrict__ out) {
@@ -128,7 +143,7 @@ gn_apply_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, in
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float y = fmaf(v[u][j], A[j], B[j]);
-        v[u][j] = swish ? swish_f(y) : y;
+        v[u][j] = swish ? swish_act<AT>(y) : y;
       }
       store8(out + (img + pix + u * lanes) * C + c, v[u]);
     }
@@ -139,7 +154,7 @@ gn_apply_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, in
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float y = fmaf(v[j], A[j], B[j]);
-      v[j] = swish ? swish_f(y) : y;
+      v[j] = swish ? swish_act<AT>(y) : y;
     }
     store8(out + (img + pix) * C + c, v);
   }
@@ -155,8 +170,9 @@ int gn_geometry(int C0, int C1, int N, int HW, GnGeo* g) {
   if (g->CV > kMaxThreads) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "GroupNorm over %d channels exceeds the supported 2048", C);
   g->lanes = kMaxThreads / g->CV;
   g->threads = g->lanes * g->CV;
-  // enough blocks to fill the 148 SMs several times over, but at least 2*kUnroll pixels per lane per block
-  int slabs = (int)ceil_div(148 * 8, N);
+  // many more blocks than resident slots (148 SMs x 4) so the last wave is a small fraction of the run, but at
+  // least 2*kUnroll pixels per lane per block
+  int slabs = (int)ceil_div(148 * 4 * 10, N);
   const int min_pix = g->lanes * 2 * kUnroll;
   slabs = (int)std::min<int64_t>(slabs, ceil_div(HW, min_pix));
   if (slabs < 1) slabs = 1;

@@ -181,6 +181,94 @@ static __device__ __forceinline__ void epilogue16(const EpiP& p, const float* nb
   }
 }
 
+// Coalesced epilogue for 64 consecutive output channels [co0, co0+64) of the 32 accumulator rows one warp owns.
+// `taddr` addresses column 0 of those 64 columns for this warp's TMEM lane quarter; `stage` is this warp's 4 KB
+// shared-memory buffer (32 rows x 128 B, 16-byte chunks XOR-swizzled by row to stay bank-conflict free);
+// pix(R) maps accumulator row R (0..127) to (image n, flat pixel index m).  Global traffic is fully coalesced:
+// 8 lanes cover the 128 contiguous bytes of one pixel, 4 pixels per instruction, for both the residual read and
+// the output write; the per-thread row work happens in registers in between.  NHWC bf16 output only.
+template <typename PixFn>
+static __device__ __forceinline__ void epilogue_rows64(const EpiP& p, const float* nbias, uint32_t taddr, int quarter,
+                                                       int lane, int co0, uint4* stage, PixFn pix) {
+  const int sub = lane >> 3, chunk = lane & 7;
+  // phase 1: residual tile -> staging (coalesced)
+  if (p.resid) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + sub;
+      int n;
+      long long m;
+      pix(quarter * 32 + r, n, m);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (n < p.N_img) v = __ldg(reinterpret_cast<const uint4*>(p.resid + m * p.Cout + co0) + chunk);
+      stage[r * 8 + (chunk ^ (r & 7))] = v;
+    }
+    __syncwarp();
+  }
+  // phase 2: own row in registers
+  {
+    int n;
+    long long m;
+    pix(quarter * 32 + lane, n, m);
+    uint32_t acc[4][16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tmem_ld16(taddr + q * 16, acc[q]);
+    tmem_ld_wait();
+    const float* nb = nbias ? nbias + (long long)n * p.nbs + co0 : nullptr;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {   // 8 channels per 16-byte chunk
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[c >> 1][(c & 1) * 8 + j]);
+      if (p.bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + c * 8 + 4));
+        v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+      }
+      if (nb && n < p.N_img) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(nb + c * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(nb + c * 8 + 4));
+        v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+      }
+      if (p.act == ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
+      }
+      if (p.scale != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= p.scale;
+      }
+      uint4* slot = &stage[lane * 8 + (c ^ (lane & 7))];
+      if (p.resid) {
+        const uint4 rv = *slot;
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          v[2 * j] += f.x, v[2 * j + 1] += f.y;
+        }
+      }
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      *slot = o;
+    }
+    __syncwarp();
+  }
+  // phase 3: staging -> global (coalesced)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + sub;
+    int n;
+    long long m;
+    pix(quarter * 32 + r, n, m);
+    const uint4 v = stage[r * 8 + (chunk ^ (r & 7))];
+    if (n < p.N_img) *(reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + m * p.Cout + co0) + chunk) = v;
+  }
+  __syncwarp();
+}
+
 // ---- host side shared state ----------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

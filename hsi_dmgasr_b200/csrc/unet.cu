@@ -235,9 +235,71 @@ ConvOp conv_op_nhwc(const Act& in, const Act* in2, const Act& out) {
   return op;
 }
 
-// SelfAttention.forward (unet.py:124-143), n_head = 1.
+// SelfAttention.forward (unet.py:124-143), n_head = 1, on tensor cores (BF16 mode).  Every contraction is a K-major
+// "NT" GEMM: the V projection is computed transposed (V^T = W_v X^T) so that O = P V contracts over contiguous keys.
+bool attention_tc(hsidm_ctx* c, const ResW& r, const Act& x, Act* result) {
+  Exec& ex = c->ex;
+  const int C = x.C, S = x.H * x.W, N = x.N;
+  if (ex.prec != HSIDM_BF16 || !r.qkv.w_bf16) return false;
+  GemmTcOp probe;
+  probe.M = S, probe.N = S, probe.K = C, probe.lda = 2 * C, probe.ldb = 2 * C, probe.ldc = S, probe.c_f32 = 1;
+  probe.sA = probe.sB = (int64_t)S * 2 * C, probe.sC = (int64_t)S * S;
+  if (!gemm_tc_supported(probe) || C % 64 || S % 64) return false;
+  Act nrm = gn_act(c, x, nullptr, r.an_w, r.an_b, false);
+  // q, k = first 2C rows of the packed qkv weight
+  Act qk = ex.alloc_act(N, x.H, x.W, 2 * C);
+  {
+    ConvW w2 = r.qkv;
+    w2.Cout = 2 * C;
+    ConvOp op = conv_op_nhwc(nrm, nullptr, qk);
+    if (!conv_tc_supported([&] { ConvOp t = op; t.w_bf16 = w2.w_bf16; t.ksize = 1; t.Cout = 2 * C; return t; }(), ex.prec)) {
+      ex.release(qk);
+      ex.release(nrm);
+      return false;
+    }
+    run_conv(ex, op, w2, c->ps);
+  }
+  const bf16* wv = r.qkv.w_bf16 + (int64_t)2 * C * C;   // rows [2C, 3C) of the K-major [3C][C] matrix
+  bf16* qkp = static_cast<bf16*>(qk.p);
+  bf16* vt = static_cast<bf16*>(ex.alloc_raw(sizeof(bf16) * (int64_t)N * C * S));        // [N][C][S]
+  float* scores = static_cast<float*>(ex.alloc_raw(sizeof(float) * (int64_t)N * S * S));  // [N][S][S]
+  GemmTcOp g;
+  g.A = wv, g.B = nrm.p, g.C = vt, g.M = C, g.N = S, g.K = C, g.batch = N;
+  g.lda = C, g.sA = 0, g.ldb = C, g.sB = (int64_t)S * C, g.ldc = S, g.sC = (int64_t)C * S, g.c_f32 = 0;
+  ex.run([&] { return gemm_tc(g, ex.stream); });
+  GemmTcOp qkT;
+  qkT.A = qkp, qkT.B = qkp + C, qkT.C = scores, qkT.M = S, qkT.N = S, qkT.K = C, qkT.batch = N;
+  qkT.lda = qkT.ldb = 2 * C, qkT.sA = qkT.sB = (int64_t)S * 2 * C, qkT.ldc = S, qkT.sC = (int64_t)S * S;
+  qkT.c_f32 = 1, qkT.alpha = 1.0f / std::sqrt((float)C);
+  ex.run([&] { return gemm_tc(qkT, ex.stream); });
+  ex.release(nrm);
+  ex.release(qk);
+  bf16* prob = static_cast<bf16*>(ex.alloc_raw(sizeof(bf16) * (int64_t)N * S * S));
+  ex.run([&] { return softmax_rows_bf16(scores, prob, (int64_t)N * S, S, ex.stream); });
+  ex.release_raw(scores);
+  Act av = ex.alloc_act(N, x.H, x.W, C);
+  GemmTcOp pv;
+  pv.A = prob, pv.B = vt, pv.C = av.p, pv.M = S, pv.N = C, pv.K = S, pv.batch = N;
+  pv.lda = S, pv.sA = (int64_t)S * S, pv.ldb = S, pv.sB = (int64_t)C * S, pv.ldc = C, pv.sC = (int64_t)S * C, pv.c_f32 = 0;
+  ex.run([&] { return gemm_tc(pv, ex.stream); });
+  ex.release_raw(prob);
+  ex.release_raw(vt);
+  Act out = ex.alloc_act(N, x.H, x.W, C);
+  ConvOp op = conv_op_nhwc(av, nullptr, out);
+  op.resid = x.p;
+  run_conv(ex, op, r.aout, c->ps);
+  ex.release(av);
+  *result = out;
+  return true;
+}
+
+// Same on CUDA cores (F32 mode, or shapes the tensor-core GEMM does not take).
 Act attention(hsidm_ctx* c, const ResW& r, Act x) {
   Exec& ex = c->ex;
+  {
+    Act fast;
+    if (attention_tc(c, r, x, &fast)) return fast;
+  }
   const int C = x.C, S = x.H * x.W;
   Act nrm = gn_act(c, x, nullptr, r.an_w, r.an_b, false);
   Act qkv = ex.alloc_act(x.N, x.H, x.W, 3 * C);
