@@ -284,8 +284,8 @@ def main() -> None:
                 "gn_stats_gbs": (shares["gn_stats"]["work_per_step"] / (shares["gn_stats"]["ms_per_step"] * 1e-3) / 1e9
                                  if shares["gn_stats"]["ms_per_step"] > 0 else None),
                 "hbm_peak_gbs": pk["hbm_gbs"],
-                "whole_step_tflops": UNET_GFLOP * n_lat / ms_per_step / 1e3,
-                "whole_step_frac_of_peak": UNET_GFLOP * n_lat / ms_per_step / 1e3 / pk["tf_sustained"]}
+                "whole_step_tflops": UNET_GFLOP * n_lat / ms_per_step,
+                "whole_step_frac_of_peak": UNET_GFLOP * n_lat / ms_per_step / pk["tf_sustained"]}
 
     cpu = None
     if rank == 0 and not args.no_cpu:

@@ -84,14 +84,17 @@ int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const void* x1,
                           const float* gamma, const float* beta, float eps, int swish, void* out) {
   void* scratch = nullptr;
   unsigned* tickets = nullptr;
+  float* stats = nullptr;
   HSIDM_CUDA(cudaMalloc(&scratch, gn_scratch_bytes(c0, c1, N, HW, groups) + 16));
   HSIDM_CUDA(cudaMalloc(&tickets, sizeof(unsigned) * N));
+  HSIDM_CUDA(cudaMalloc(&stats, sizeof(float) * 2 * N * groups));
   HSIDM_CUDA(cudaMemset(tickets, 0, sizeof(unsigned) * N));
-  int s = gn_stats(x0, c0, x1, c1, N, HW, groups, eps, scratch, tickets, precision, nullptr);
-  if (s == HSIDM_OK) s = gn_apply(x0, c0, x1, c1, N, HW, groups, scratch, gamma, beta, swish, out, precision, nullptr);
+  int s = gn_stats(x0, c0, x1, c1, N, HW, groups, eps, scratch, tickets, stats, precision, nullptr);
+  if (s == HSIDM_OK) s = gn_apply(x0, c0, x1, c1, N, HW, groups, stats, gamma, beta, swish, out, precision, nullptr);
   cudaError_t e = cudaDeviceSynchronize();
   cudaFree(scratch);
   cudaFree(tickets);
+  cudaFree(stats);
   if (e != cudaSuccess && s == HSIDM_OK) {
     set_last_error("kernel failed: %s", cudaGetErrorString(e));
     s = HSIDM_CUDA_ERROR;

@@ -148,6 +148,8 @@ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 struct Act {
   void* p = nullptr;
   int N = 0, H = 0, W = 0, C = 0;
+  float* stats = nullptr;  // [N][slots][C][2] partial (sum, sumsq) left by the producing convolution, or null
+  int slots = 0;
   int64_t numel() const { return (int64_t)N * H * W * C; }
 };
 

@@ -14,8 +14,9 @@
 //   * one B tile (BN x 64 weights of one tap) feeds MT*4 MMAs instead of 4.
 // L2->SMEM bytes per MMA cycle drop from ~95 to ~35-40 B/clk/SM.
 // Accumulators: MT x BN fp32 columns per tile, double buffered (2*MT*BN <= 512 TMEM columns).
-// Warp roles as in conv_tc.cu: warp 0 TMA producer (A ring of 2 halo buffers + B ring), warp 1 MMA issuer,
-// warps 2..5 epilogue.
+// Warp roles: warp 0 TMA producer (A ring of 2 halo buffers + B ring), warp 1 MMA issuer, warps 2..9 epilogue (two per
+// TMEM lane quarter, splitting the tile's channel halves or sub-tiles).  The epilogue also leaves per-slot (sum, sumsq)
+// of what it stored, so the consumer's GroupNorm never re-reads the tensor for statistics.
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -25,7 +26,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kRows = 16;          // output rows per tile
 constexpr int kHaloRows = kRows + 2;
 constexpr int kAStages = 2;
@@ -45,9 +47,8 @@ struct HCfg {
   static constexpr int kABox = kHaloRows * kPW * 128;                      // bytes one TMA box writes
   static constexpr int kAStage = (kABox + 1023) / 1024 * 1024;             // keep every stage 1024-B aligned
   static constexpr int kBStage = BN * 128;
-  static constexpr int kStageBytes = 4 * 4096;                             // epilogue staging, 4 KB per epilogue warp
-  static constexpr int kBudget = 212 * 1024 - kStageBytes;
-  static constexpr int kBStagesRaw = (kBudget - kAStages * kAStage) / kBStage;
+  static constexpr int kStageBytes = kEpiWarps * 4096;                     // epilogue staging, 4 KB per epilogue warp
+  static constexpr int kBStagesRaw = (232448 - 1536 - kStageBytes - kAStages * kAStage) / kBStage;
   static constexpr int kBStages = kBStagesRaw > 10 ? 10 : kBStagesRaw;
   static constexpr int kTmemCols = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;
   static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + kStageBytes + 1024 + 512;
@@ -84,7 +85,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kAStages; ++s) mbar_init(smem_u32(&a_full[s]), 1), mbar_init(smem_u32(&a_empty[s]), 1);
     for (int s = 0; s < C::kBStages; ++s) mbar_init(smem_u32(&b_full[s]), 1), mbar_init(smem_u32(&b_empty[s]), 1);
-    for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&tfull_bar[s]), 1), mbar_init(smem_u32(&tempty_bar[s]), 4);
+    for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&tfull_bar[s]), 1), mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
@@ -167,9 +168,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5) ===============================
+    // =============================== epilogue (warps 2..9) ===============================
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;      // which of the two warps of this lane quarter
     const int row = quarter * 32 + lane;   // accumulator row: pixel (row/8, row%8) of a sub-tile
+    constexpr int nC = BN / 64;            // 64-channel chunks per tile (0 for the small-Cout instantiation)
     int acc = 0;
     uint32_t acc_phase = 0;
     const float* nbias = p.e.nbias ? p.e.nbias + (p.e.nb_t ? (long long)(*p.e.nb_t) * p.e.nb_ts : 0) : nullptr;
@@ -183,22 +186,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (!ok) break;
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * (MT * BN) + ((uint32_t)(quarter * 32) << 16);
-      if constexpr (BN % 64 == 0) {
+      if constexpr (nC >= 1) {
         uint4* stage = reinterpret_cast<uint4*>(smem_stage + (warp - 2) * 4096);
         const int ty0 = (r / p.tiles_x) * kRows, tx0 = (r % p.tiles_x) * (8 * MT);
+        // split between the two warps of a quarter: by channel chunk when there are several, else by sub-tile
+        constexpr bool by_chunk = nC >= 2;
+        const int c_first = by_chunk ? half : 0, c_step = by_chunk ? 2 : 1;
+        const int s_first = by_chunk ? 0 : half, s_step = by_chunk ? 1 : 2;
 #pragma unroll 1
-        for (int s = 0; s < MT; ++s) {
-          auto pix = [&](int R, int& pn, long long& pm) {
-            pn = n;
-            pm = ((long long)n * p.e.H + ty0 + (R >> 3)) * p.e.W + tx0 + 8 * s + (R & 7);
-          };
+        for (int ci = c_first; ci < nC; ci += c_step) {
+          float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 64)
-            epilogue_rows64(p.e, nbias, taddr + s * BN + c0, quarter, lane, nt * BN + c0, stage, pix);
+          for (int s = s_first; s < MT; s += s_step) {
+            auto pix = [&](int R, int& pn, long long& pm) {
+              pn = n;
+              pm = ((long long)n * p.e.H + ty0 + (R >> 3)) * p.e.W + tx0 + 8 * s + (R & 7);
+            };
+            epilogue_rows64(p.e, nbias, taddr + s * BN + ci * 64, quarter, lane, nt * BN + ci * 64, stage, pix, st);
+          }
+          if (p.e.stats) stats_store(p.e, n, r * (by_chunk ? 4 : 8) + quarter + (by_chunk ? 0 : 4 * half), nt * BN + ci * 64, lane, st);
         }
       } else {
 #pragma unroll 1
-        for (int s = 0; s < MT; ++s) {
+        for (int s = half; s < MT; s += 2) {
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 16) {
             uint32_t v[16];
@@ -274,6 +284,14 @@ int conv_halo_init() {
   HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
   HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 16>::kSmemBytes));
   return HSIDM_OK;
+}
+
+int conv_halo_stats_slots(const ConvOp& op) {
+  int MT, BN;
+  pick_shape(op, &MT, &BN);
+  if (MT == 0 || BN % 64 || op.out_layout != L_NHWC) return 0;
+  const int tpi = (op.Win / (8 * MT)) * (op.Hin / kRows);
+  return tpi * (BN / 64 >= 2 ? 4 : 8);
 }
 
 // Assumes conv_tc_supported(op) already holds (bf16 NHWC sources with 64-multiple channels, Cout fits an N tile).

@@ -25,8 +25,9 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 192;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kEpiWarps = 8;      // two per TMEM lane quarter
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kSmemBudget = 196 * 1024;
 
 struct TcP {
   int M;
@@ -34,6 +35,7 @@ struct TcP {
   int tiles_x, tiles_y;    // tiles per image along x / y (bn == 1)
   int m_tiles, n_tiles;
   int taps;                // 1 or 9
+  int bw_shift, ppi_shift; // log2(bw), log2(bw*bh): tile extents are powers of two below 128
   int chunks0, chunks1;    // 64-channel chunks taken from source 0 / source 1
   EpiP e;
   int* err;                // device flag set when a barrier wait times out (never in a healthy run)
@@ -46,7 +48,8 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiBytes = BN % 64 == 0 ? kEpiWarps * 4096 : 0;   // staging for the coalesced epilogue
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
@@ -56,7 +59,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* tail = smem + C::kStages * C::kStageBytes;
+  uint8_t* smem_epi = smem + C::kStages * C::kStageBytes;
+  uint8_t* tail = smem_epi + C::kEpiBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tfull_bar = empty_bar + C::kStages;   // [2] accumulator ready
@@ -77,7 +81,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 4);   // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -158,37 +162,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else {
     // =============================== epilogue (warps 2..5) ===============================
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;        // which of the two warps of this quarter
     const int row = quarter * 32 + lane;     // accumulator row = pixel within the tile
     int acc = 0;
     uint32_t acc_phase = 0;
     const float* nbias = p.e.nbias ? p.e.nbias + (p.e.nb_t ? (long long)(*p.e.nb_t) * p.e.nb_ts : 0) : nullptr;
+    const int tpi = p.tiles_x * p.tiles_y;
+    const int bw_mask = p.bw - 1, ppi_mask = (1 << p.ppi_shift) - 1;
     bool ok = true;
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      int n, y, x;
+      // tile origin: image n0 and pixel (y0, x0); rows then decode with shifts only
+      int n0, y0, x0;
       if (p.bn > 1) {
-        n = mt * p.bn + row / (p.bw * p.bh);
-        const int r = row % (p.bw * p.bh);
-        y = r / p.bw, x = r % p.bw;
+        n0 = mt * p.bn, y0 = 0, x0 = 0;
       } else {
-        const int tpi = p.tiles_x * p.tiles_y;
-        n = mt / tpi;
-        const int r = mt - n * tpi;
-        y = (r / p.tiles_x) * p.bh + row / p.bw;
-        x = (r % p.tiles_x) * p.bw + row % p.bw;
+        n0 = mt / tpi;
+        const int q = mt - n0 * tpi;
+        y0 = (q / p.tiles_x) * p.bh, x0 = (q % p.tiles_x) * p.bw;
       }
-      const bool valid = n < p.e.N_img;
+      auto pix = [&](int R, int& pn, long long& pm) {
+        pn = n0 + (R >> p.ppi_shift);
+        const int q = R & ppi_mask;
+        pm = ((long long)pn * p.e.H + y0 + (q >> p.bw_shift)) * p.e.W + x0 + (q & bw_mask);
+      };
       ok = mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 4);
       if (!ok) break;
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      bool staged = false;
+      if constexpr (BN % 64 == 0) {
+        if (p.e.out_layout == L_NHWC) {
+          staged = true;
+          uint4* stage = reinterpret_cast<uint4*>(smem_epi + (warp - 2) * 4096);
+          // statistics slot of this warp's 32 rows (all of one image, see pertap_stats_slots)
+          int sn, sslot;
+          if (p.bn > 1) {
+            const int qpi = 4 / p.bn;             // lane quarters per image
+            sn = n0 + quarter / qpi, sslot = quarter % qpi;
+          } else {
+            sn = n0, sslot = (mt - n0 * tpi) * 4 + quarter;
+          }
+          constexpr int nC = BN / 64;
+          // the two warps of a quarter alternate over the 64-channel chunks (a single chunk goes to the first warp)
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        const int co0 = nt * BN + c0;
-        if (valid && co0 < p.e.Cout) epilogue16(p.e, nbias, n, y, x, co0, r);
+          for (int ci = half; ci < nC; ci += 2) {
+            const int co0 = nt * BN + ci * 64;
+            if (co0 >= p.e.Cout) break;
+            float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
+            epilogue_rows64(p.e, nbias, taddr + ci * 64, quarter, lane, co0, stage, pix, st);
+            if (p.e.stats) stats_store(p.e, sn, sslot, co0, lane, st);
+          }
+        }
+      }
+      if (!staged && half == 0) {
+        int n;
+        long long m;
+        pix(row, n, m);
+        const int q = row & ppi_mask;
+        const int y = y0 + (q >> p.bw_shift), x = x0 + (q & bw_mask);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          const int co0 = nt * BN + c0;
+          if (n < p.e.N_img && co0 < p.e.Cout) epilogue16(p.e, nbias, n, y, x, co0, r);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -290,6 +330,14 @@ void fill_epilogue(EpiP* e, const ConvOp& op) {
   e->bias = op.bias, e->nbias = op.nbias, e->nbs = op.nbias_stride, e->nb_t = op.nbias_t, e->nb_ts = op.nbias_t_stride;
   e->act = op.act, e->scale = op.scale, e->resid = static_cast<const bf16*>(op.resid), e->out = op.out;
   e->out_layout = op.out_layout, e->clamp01 = op.clamp01;
+  e->stats = op.stats_out, e->stats_slots = op.stats_slots;
+}
+
+int pertap_stats_slots(const ConvOp& op) {
+  int bw, bh, bn;
+  if (op.out_layout != L_NHWC || op.Cout % 64 || !tile_geometry(op.Hin, op.Win, &bw, &bh, &bn)) return 0;
+  if (bn > 1) return (bn <= 4) ? 4 / bn : 0;     // a warp's 32 rows must stay inside one image
+  return (op.Win / bw) * (op.Hin / bh) * 4;
 }
 
 int pick_bn(int Cout) {
@@ -308,6 +356,12 @@ int conv_tc_init() {
     if (std::getenv("HSIDM_NO_HALO")) tc::host().no_halo = 1;   // A/B switch for profiling runs
   });
   return g_init_status;
+}
+
+int conv_tc_stats_slots(const ConvOp& op) {
+  if (!conv_tc_supported(op, HSIDM_BF16)) return 0;
+  if (!tc::host().no_halo && conv_halo_supported(op)) return conv_halo_stats_slots(op);
+  return tc::pertap_stats_slots(op);
 }
 
 void conv_tc_set_mode(int no_halo, int base_offset_mode) {
@@ -346,6 +400,9 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
   p.m_tiles = p.bn > 1 ? (int)ceil_div(op.N, p.bn) : op.N * p.tiles_x * p.tiles_y;
   p.n_tiles = (int)ceil_div(op.Cout, BN);
   p.taps = op.ksize * op.ksize;
+  p.bw_shift = 0, p.ppi_shift = 0;
+  while ((1 << p.bw_shift) < p.bw) ++p.bw_shift;
+  while ((1 << p.ppi_shift) < p.bw * p.bh) ++p.ppi_shift;
   p.chunks0 = op.src[0].C / kBK;
   p.chunks1 = op.src[1].C / kBK;
   p.err = host().err_flag;

@@ -160,6 +160,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         e.bias = nullptr, e.nbias = nullptr, e.nbs = 0, e.nb_t = nullptr, e.nb_ts = 0;
         e.act = ACT_NONE, e.scale = p.alpha, e.resid = nullptr;
         e.out = static_cast<bf16*>(p.C) + b * p.sC, e.out_layout = L_NHWC, e.clamp01 = 0;
+        e.stats = nullptr, e.stats_slots = 0;
+        float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
         const int m0 = mt * kBM, M = p.M;
         auto pix = [&](int R, int& pn, long long& pm) {
           pn = (m0 + R) < M ? 0 : 1;   // rows past M are masked like images past N_img
@@ -167,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 64)
-          if (nt * BN + c0 < p.N) epilogue_rows64(e, nullptr, taddr + c0, quarter, lane, nt * BN + c0, stage, pix);
+          if (nt * BN + c0 < p.N) epilogue_rows64(e, nullptr, taddr + c0, quarter, lane, nt * BN + c0, stage, pix, st);
       }
       tc_fence_before();
       __syncwarp();

@@ -37,6 +37,10 @@ struct ConvOp {
   void* out = nullptr;
   int out_layout = L_NHWC;
   int clamp01 = 0;
+  // optional fused GroupNorm statistics of the output: [N][stats_slots][Cout][2]; stats_slots must equal
+  // conv_tc_stats_slots(op) (tensor-core kernels only)
+  float* stats_out = nullptr;
+  int stats_slots = 0;
   int K() const { return ksize * ksize * (src[0].C + src[1].C); }
 };
 
@@ -46,6 +50,7 @@ int conv_simt(const ConvOp& op, int prec, cudaStream_t stream);
 // fits the tensor-core kernel's constraints; conv_tc() fails loudly otherwise.
 bool conv_tc_supported(const ConvOp& op, int prec);
 int conv_tc(const ConvOp& op, cudaStream_t stream);
+int conv_tc_stats_slots(const ConvOp& op);  // slots per image the kernel chosen for `op` fills (0 = no fused statistics)
 int conv_tc_init();               // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int conv_tc_bn_rows(int Cout);    // N-tile height; packed bf16 weights are padded to a multiple of it (0 = unsupported)
 void conv_tc_set_mode(int no_halo, int base_offset_mode);  // test knobs
@@ -91,9 +96,14 @@ int64_t gn_scratch_bytes(int C0, int C1, int N, int HW, int groups);
 inline float* gn_stats_ptr(void* scratch, int N, int slabs, int groups) {
   return reinterpret_cast<float*>(static_cast<double*>(scratch) + (int64_t)2 * N * slabs * groups);
 }
+// Standalone statistics pass (reads the tensors): stats[N][groups][2] = (mean, rstd).
 int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, float eps, void* scratch,
-             unsigned* tickets, int prec, cudaStream_t stream);
-int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const void* scratch,
+             unsigned* tickets, float* stats, int prec, cudaStream_t stream);
+// Statistics from the per-slot partial sums the producing convolutions left behind (no pass over the tensors).
+// part0/part1: [N][slots][C][2] (sum, sumsq) for the two concatenated sources.
+int gn_finalize(const float* part0, int slots0, int C0, const float* part1, int slots1, int C1, int N, int HW, int groups,
+                float eps, float* stats, cudaStream_t stream);
+int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const float* stats,
              const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream);
 
 int upsample2x(const void* x, void* out, int N, int H, int W, int C, int prec, cudaStream_t stream);

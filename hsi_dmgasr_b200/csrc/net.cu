@@ -131,53 +131,82 @@ int pack_conv(const ParamStore& ps, ConvW& c, bool bf16_too) {
 }
 
 // ---- dispatcher -----------------------------------------------------------------------------------------------
-void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps) {
+namespace {
+enum Route { R_TC, R_DOWN, R_UP, R_SIMT };
+
+// Decides how `op` runs and, for the lowered routes, fills `g` with the tensor-core op (its source pointer is patched
+// once the temporary exists).
+Route plan_conv(const Exec& ex, const ConvOp& op, const ConvW& w, ConvOp* g) {
+  const int prec = ex.prec;
+  *g = op;
+  if (prec != HSIDM_BF16 || !w.w_bf16) return R_SIMT;
+  if (conv_tc_supported(op, prec)) return R_TC;
+  const bool nhwc1 = op.src[0].layout == L_NHWC && op.src[1].C == 0 && op.src[0].C % 64 == 0;
+  if (nhwc1 && op.stride == 2 && op.ksize == 3 && !op.up && op.Hin % 2 == 0 && op.Win % 2 == 0) {
+    // Downsample (unet.py:68-74): gather the 9 taps once, then a 1x1 tensor-core GEMM with K = 9*C.
+    g->src[0].C = 9 * op.src[0].C;
+    g->Hin = op.Hout, g->Win = op.Wout, g->stride = 1, g->ksize = 1;
+    if (conv_tc_supported(*g, prec)) return R_DOWN;
+  } else if (nhwc1 && op.up && op.stride == 1) {
+    // Upsample (unet.py:58-65): materialise the nearest-2x tensor, then the ordinary 3x3 tensor-core conv.
+    g->Hin = 2 * op.Hin, g->Win = 2 * op.Win, g->up = 0;
+    if (conv_tc_supported(*g, prec)) return R_UP;
+  }
+  *g = op;
+  return R_SIMT;
+}
+
+void fill_weights(ConvOp& op, const ConvW& w, const ParamStore& ps) {
   op.w_f32 = w.w_f32;
   op.w_bf16 = w.w_bf16;
   op.bias = ps.dev(w.pb);
   op.ksize = w.ks;
   op.Cout = w.Cout;
+}
+}  // namespace
+
+void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps) {
+  fill_weights(op, w, ps);
   cudaStream_t st = ex.stream;
   const int prec = ex.prec;
-  if (prec == HSIDM_BF16 && w.w_bf16) {
-    if (conv_tc_supported(op, prec)) {
-      ex.run([&] { return conv_tc(op, st); });
-      return;
-    }
-    const bool nhwc1 = op.src[0].layout == L_NHWC && op.src[1].C == 0 && op.src[0].C % 64 == 0;
-    if (nhwc1 && op.stride == 2 && op.ksize == 3 && !op.up && op.Hin % 2 == 0 && op.Win % 2 == 0) {
-      // Downsample (unet.py:68-74): gather the 9 taps once, then a 1x1 tensor-core GEMM with K = 9*C.
-      const int C = op.src[0].C;
-      Act col = ex.alloc_act(op.N, op.Hout, op.Wout, 9 * C);
-      const void* src = op.src[0].p;
-      ex.run([&] { return im2col_s2(src, col.p, op.N, op.Hin, op.Win, C, st); });
-      ConvOp g = op;
-      g.src[0].p = col.p, g.src[0].C = 9 * C;
-      g.Hin = op.Hout, g.Win = op.Wout, g.stride = 1, g.ksize = 1;
-      if (conv_tc_supported(g, prec)) {
-        ex.run([&] { return conv_tc(g, st); });
-        ex.release(col);
-        return;
-      }
-      ex.release(col);
-    } else if (nhwc1 && op.up && op.stride == 1) {
-      // Upsample (unet.py:58-65): materialise the nearest-2x tensor, then the ordinary 3x3 tensor-core conv.
-      const int C = op.src[0].C;
-      Act big = ex.alloc_act(op.N, 2 * op.Hin, 2 * op.Win, C);
-      const void* src = op.src[0].p;
-      ex.run([&] { return upsample2x(src, big.p, op.N, op.Hin, op.Win, C, prec, st); });
-      ConvOp g = op;
-      g.src[0].p = big.p;
-      g.Hin = 2 * op.Hin, g.Win = 2 * op.Win, g.up = 0;
-      if (conv_tc_supported(g, prec)) {
-        ex.run([&] { return conv_tc(g, st); });
-        ex.release(big);
-        return;
-      }
-      ex.release(big);
-    }
+  ConvOp g;
+  const Route route = plan_conv(ex, op, w, &g);
+  if (route == R_TC) {
+    ex.run([&] { return conv_tc(op, st); });
+  } else if (route == R_DOWN) {
+    const int C = op.src[0].C;
+    Act col = ex.alloc_act(op.N, op.Hout, op.Wout, 9 * C);
+    const void* src = op.src[0].p;
+    ex.run([&] { return im2col_s2(src, col.p, op.N, op.Hin, op.Win, C, st); });
+    g.src[0].p = col.p;
+    ex.run([&] { return conv_tc(g, st); });
+    ex.release(col);
+  } else if (route == R_UP) {
+    const int C = op.src[0].C;
+    Act big = ex.alloc_act(op.N, 2 * op.Hin, 2 * op.Win, C);
+    const void* src = op.src[0].p;
+    ex.run([&] { return upsample2x(src, big.p, op.N, op.Hin, op.Win, C, prec, st); });
+    g.src[0].p = big.p;
+    ex.run([&] { return conv_tc(g, st); });
+    ex.release(big);
+  } else {
+    op.stats_out = nullptr, op.stats_slots = 0;   // the CUDA-core kernel has no fused statistics
+    ex.run([&] { return conv_simt(op, prec, st); });
   }
-  ex.run([&] { return conv_simt(op, prec, st); });
+}
+
+void run_conv_stats(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps, Act& out) {
+  fill_weights(op, w, ps);
+  ConvOp g;
+  const Route route = plan_conv(ex, op, w, &g);
+  int slots = 0;
+  if (route != R_SIMT && op.out_layout == L_NHWC) slots = conv_tc_stats_slots(route == R_TC ? op : g);
+  if (slots > 0) {
+    out.stats = static_cast<float*>(ex.alloc_raw(sizeof(float) * 2 * (int64_t)op.N * slots * op.Cout));
+    out.slots = slots;
+    op.stats_out = out.stats, op.stats_slots = slots;
+  }
+  run_conv(ex, op, w, ps);
 }
 
 }  // namespace hsidm

@@ -89,7 +89,8 @@ struct Exec {
   }
   void release(Act& a) {
     arena.free(a.p);
-    a.p = nullptr;
+    arena.free(a.stats);
+    a.p = nullptr, a.stats = nullptr, a.slots = 0;
   }
   void release_raw(void* p) { arena.free(p); }
   // run a launcher unless this is a dry (measuring) pass or an earlier step already failed
@@ -104,5 +105,8 @@ struct Exec {
 // Fills the weight/bias fields of `op` from `w` and dispatches it. In BF16 mode stride-2 and upsampled convs
 // whose channels fit the tensor-core kernel are lowered to (im2col | upsample) + tensor-core GEMM.
 void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps);
+// Same, additionally asking the kernel to leave GroupNorm partial statistics of its output in `out` (out.stats / out.slots
+// stay null/0 when the chosen kernel cannot produce them, e.g. on the CUDA-core path).
+void run_conv_stats(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps, Act& out);
 
 }  // namespace hsidm

@@ -188,13 +188,12 @@ int64_t gn_scratch_bytes(int C0, int C1, int N, int HW, int groups) {
 }
 
 int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, float eps, void* scratch,
-             unsigned* tickets, int prec, cudaStream_t stream) {
+             unsigned* tickets, float* stats, int prec, cudaStream_t stream) {
   GnGeo g;
   HSIDM_TRY(gn_geometry(C0, C1, N, HW, &g));
   const int C = C0 + C1;
   if (C % groups) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "GroupNorm: %d channels not divisible by %d groups", C, groups);
   double* partial = static_cast<double*>(scratch);
-  float* stats = gn_stats_ptr(scratch, N, g.slabs, groups);
   dim3 grid(g.slabs, N);
   const size_t smem = sizeof(float) * 2 * C * g.lanes;
   ProfScope prof(PROF_GN_STATS, (double)N * HW * C * (prec == HSIDM_BF16 ? 2 : 4), stream);
@@ -208,11 +207,73 @@ int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int 
   return after_launch("gn_stats_kernel");
 }
 
-int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const void* scratch,
+// grid = N, block = 256: thread -> (slot lane, channel); fixed-order folds only.
+__global__ void gn_finalize_kernel(const float* __restrict__ part0, int slots0, int C0, const float* __restrict__ part1,
+                                   int slots1, int C1, int groups, double cnt, float eps, float* __restrict__ stats) {
+  extern __shared__ float fsm[];   // [lanes][2][C] then [2][C]
+  const int C = C0 + C1, n = blockIdx.x, tid = threadIdx.x;
+  const int lanes = blockDim.x / 64;                     // channels are walked 64 at a time
+  const int cl = tid & 63, lane = tid >> 6;
+  for (int cb = 0; cb < C; cb += 64) {
+    const int c = cb + cl;
+    const bool second = c >= C0;
+    const float* base = second ? part1 + ((long long)n * slots1 * C1 + (c - C0)) * 2 : part0 + ((long long)n * slots0 * C0 + c) * 2;
+    const int slots = second ? slots1 : slots0, stride = (second ? C1 : C0) * 2;
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    int sl = lane;
+    for (; sl + lanes < slots; sl += 2 * lanes) {
+      const float2 u = *reinterpret_cast<const float2*>(base + (long long)sl * stride);
+      const float2 v = *reinterpret_cast<const float2*>(base + (long long)(sl + lanes) * stride);
+      a0 += u.x, b0 += u.y, a1 += v.x, b1 += v.y;
+    }
+    if (sl < slots) {
+      const float2 u = *reinterpret_cast<const float2*>(base + (long long)sl * stride);
+      a0 += u.x, b0 += u.y;
+    }
+    fsm[(lane * 2 + 0) * C + c] = a0 + a1;
+    fsm[(lane * 2 + 1) * C + c] = b0 + b1;
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += blockDim.x) {
+    const int which = i / C, c = i - which * C;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += fsm[(l * 2 + which) * C + c];
+    fsm[which * C + c] = acc;   // lane 0's own slot: read above by this thread only, no other thread touches it
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = tid; g < groups; g += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int j = 0; j < cpg; ++j) a += (double)fsm[g * cpg + j], b += (double)fsm[C + g * cpg + j];
+    const double mean = a / cnt;
+    double var = b / cnt - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    stats[((long long)n * groups + g) * 2] = (float)mean;
+    stats[((long long)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+int gn_finalize(const float* part0, int slots0, int C0, const float* part1, int slots1, int C1, int N, int HW, int groups,
+                float eps, float* stats, cudaStream_t stream) {
+  const int C = C0 + C1;
+  if (C0 % 64 || C1 % 64 || C % groups || C > 4096)
+    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "gn_finalize: channel counts %d+%d must be multiples of 64 and of the group count", C0, C1);
+  // as many slot lanes as 48 KB of shared memory allows (16 for C = 64 ... 2 for C = 1536)
+  int lanes = 16;
+  while (lanes > 1 && sizeof(float) * 2 * C * lanes > 48 * 1024) lanes >>= 1;
+  const int threads = 64 * lanes;
+  const size_t smem = sizeof(float) * 2 * C * lanes;
+  if (smem > 48 * 1024) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "gn_finalize: %d channels need too much shared memory", C);
+  ProfScope prof(PROF_GN_STATS, 8.0 * N * ((double)slots0 * C0 + (double)slots1 * C1), stream, "finalize");
+  gn_finalize_kernel<<<N, threads, smem, stream>>>(part0, slots0, C0, part1, slots1, C1, groups, (double)(C / groups) * HW, eps,
+                                                   stats);
+  return after_launch("gn_finalize_kernel");
+}
+
+int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const float* stats,
              const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream) {
   GnGeo g;
   HSIDM_TRY(gn_geometry(C0, C1, N, HW, &g));
-  const float* stats = gn_stats_ptr(const_cast<void*>(scratch), N, g.slabs, groups);
   dim3 grid(g.slabs, N);
   ProfScope prof(PROF_GN_APPLY, 2.0 * N * HW * (C0 + C1) * (prec == HSIDM_BF16 ? 2 : 4), stream);
   if (prec == HSIDM_BF16)

@@ -25,6 +25,8 @@ struct EpiP {
   const bf16* resid;
   void* out;
   int out_layout, clamp01;
+  float* stats;      // optional [N][slots][Cout][2] per-slot (sum, sumsq) of the stored bf16 outputs, for the consumer's GroupNorm
+  int stats_slots;   // slots per image
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -187,9 +189,10 @@ static __device__ __forceinline__ void epilogue16(const EpiP& p, const float* nb
 // pix(R) maps accumulator row R (0..127) to (image n, flat pixel index m).  Global traffic is fully coalesced:
 // 8 lanes cover the 128 contiguous bytes of one pixel, 4 pixels per instruction, for both the residual read and
 // the output write; the per-thread row work happens in registers in between.  NHWC bf16 output only.
+// If p.stats is set, `st` (x,y = sums of channels co0+2*lane, +1; z,w = sums of squares) accumulates this warp's 32 rows.
 template <typename PixFn>
 static __device__ __forceinline__ void epilogue_rows64(const EpiP& p, const float* nbias, uint32_t taddr, int quarter,
-                                                       int lane, int co0, uint4* stage, PixFn pix) {
+                                                       int lane, int co0, uint4* stage, PixFn pix, float4& st) {
   const int sub = lane >> 3, chunk = lane & 7;
   // phase 1: residual tile -> staging (coalesced)
   if (p.resid) {
@@ -252,9 +255,21 @@ static __device__ __forceinline__ void epilogue_rows64(const EpiP& p, const floa
       __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      if (n >= p.N_img) o = make_uint4(0, 0, 0, 0);   // rows past the batch must not reach the statistics
       *slot = o;
     }
     __syncwarp();
+  }
+  // phase 2b: column sums of the stored values (lane -> channel pair 2*lane, 2*lane+1); conflict-free word reads
+  if (p.stats) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(stage);
+    const int cw = lane >> 2, ww = lane & 3;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const uint32_t u = w[r * 32 + ((cw ^ (r & 7)) << 2) + ww];
+      const float a = __uint_as_float(u << 16), b = __uint_as_float(u & 0xffff0000u);
+      st.x += a, st.y += b, st.z = fmaf(a, a, st.z), st.w = fmaf(b, b, st.w);
+    }
   }
   // phase 3: staging -> global (coalesced)
 #pragma unroll
@@ -267,6 +282,13 @@ static __device__ __forceinline__ void epilogue_rows64(const EpiP& p, const floa
     if (n < p.N_img) *(reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + m * p.Cout + co0) + chunk) = v;
   }
   __syncwarp();
+}
+
+// Publishes one warp's accumulated statistics for 64 channels into its slot.
+static __device__ __forceinline__ void stats_store(const EpiP& p, int n, int slot, int co0, int lane, const float4& st) {
+  if (n < p.N_img)
+    *reinterpret_cast<float4*>(p.stats + (((long long)n * p.stats_slots + slot) * p.Cout + co0 + 2 * lane) * 2) =
+        make_float4(st.x, st.z, st.y, st.w);   // (sum, sumsq) of channel 2*lane, then of channel 2*lane+1
 }
 
 // ---- host side shared state ----------------------------------------------------------------------------------------
@@ -286,12 +308,14 @@ int encode_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int 
 // K-major bf16 weights [rows][K] with box {64, bn_rows}.
 int encode_weight_map(CUtensorMap* map, const void* base, int K, int rows, int bn_rows);
 void fill_epilogue(EpiP* e, const ConvOp& op);
+int pertap_stats_slots(const ConvOp& op);   // statistic slots per image the per-tap kernel produces (0 = cannot)
 int pick_bn(int Cout);
 
 }  // namespace tc
 
 // conv_halo.cu
 bool conv_halo_supported(const ConvOp& op);
+int conv_halo_stats_slots(const ConvOp& op);
 int conv_halo(const ConvOp& op, cudaStream_t stream);
 int conv_halo_init();
 

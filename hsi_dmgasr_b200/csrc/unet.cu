@@ -206,22 +206,33 @@ struct NoiseRef {
   int64_t t_stride;
 };
 
-// GroupNorm(+Swish) over cat(a, b) -> new tensor with a.C + b.C channels.
+// GroupNorm(+Swish) over cat(a, b) -> new tensor with a.C + b.C channels.  Statistics come from the partial sums the
+// producing convolutions left behind when both inputs carry them; otherwise from a pass over the tensors.
 Act gn_act(hsidm_ctx* c, const Act& a, const Act* b, int gw, int gb, bool swish) {
   Exec& ex = c->ex;
   const int C1 = b ? b->C : 0;
   const int groups = c->cfg.norm_groups;
-  void* scratch = ex.alloc_raw(gn_scratch_bytes(a.C, C1, a.N, a.H * a.W, groups));
+  const int HW = a.H * a.W;
+  float* stats = static_cast<float*>(ex.alloc_raw(sizeof(float) * 2 * a.N * groups));
   Act out = ex.alloc_act(a.N, a.H, a.W, a.C + C1);
   const void* p1 = b ? b->p : nullptr;
+  const bool fused = a.stats && (!b || b->stats) && a.C % 64 == 0 && C1 % 64 == 0;
+  if (fused) {
+    const float* s1 = b ? b->stats : nullptr;
+    const int sl1 = b ? b->slots : 0;
+    ex.run([&] { return gn_finalize(a.stats, a.slots, a.C, s1, sl1, C1, a.N, HW, groups, kGnEps, stats, ex.stream); });
+  } else {
+    void* scratch = ex.alloc_raw(gn_scratch_bytes(a.C, C1, a.N, HW, groups));
+    ex.run([&] {
+      return gn_stats(a.p, a.C, p1, C1, a.N, HW, groups, kGnEps, scratch, ex.tickets, stats, ex.prec, ex.stream);
+    });
+    ex.release_raw(scratch);
+  }
   ex.run([&] {
-    return gn_stats(a.p, a.C, p1, C1, a.N, a.H * a.W, groups, kGnEps, scratch, ex.tickets, ex.prec, ex.stream);
+    return gn_apply(a.p, a.C, p1, C1, a.N, HW, groups, stats, c->ps.dev(gw), c->ps.dev(gb), swish ? 1 : 0, out.p, ex.prec,
+                    ex.stream);
   });
-  ex.run([&] {
-    return gn_apply(a.p, a.C, p1, C1, a.N, a.H * a.W, groups, scratch, c->ps.dev(gw), c->ps.dev(gb), swish ? 1 : 0, out.p,
-                    ex.prec, ex.stream);
-  });
-  ex.release_raw(scratch);
+  ex.release_raw(stats);
   return out;
 }
 
@@ -287,7 +298,7 @@ bool attention_tc(hsidm_ctx* c, const ResW& r, const Act& x, Act* result) {
   Act out = ex.alloc_act(N, x.H, x.W, C);
   ConvOp op = conv_op_nhwc(av, nullptr, out);
   op.resid = x.p;
-  run_conv(ex, op, r.aout, c->ps);
+  run_conv_stats(ex, op, r.aout, c->ps, out);
   ex.release(av);
   *result = out;
   return true;
@@ -326,7 +337,7 @@ Act attention(hsidm_ctx* c, const ResW& r, Act x) {
   Act out = ex.alloc_act(x.N, x.H, x.W, C);
   ConvOp op = conv_op_nhwc(av, nullptr, out);
   op.resid = x.p;
-  run_conv(ex, op, r.aout, c->ps);
+  run_conv_stats(ex, op, r.aout, c->ps, out);
   ex.release(av);
   return out;
 }
@@ -340,7 +351,7 @@ Act res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const 
     ConvOp op = conv_op_nhwc(a1, nullptr, h);
     op.nbias = nz.base + r.noise_off, op.nbias_stride = nz.n_stride;
     op.nbias_t = nz.t_dev, op.nbias_t_stride = nz.t_stride;
-    run_conv(ex, op, r.c1, c->ps);
+    run_conv_stats(ex, op, r.c1, c->ps, h);
   }
   ex.release(a1);
   Act a2 = gn_act(c, h, nullptr, r.gn2_w, r.gn2_b, true);
@@ -356,7 +367,7 @@ Act res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const 
   {
     ConvOp op = conv_op_nhwc(a2, nullptr, out);
     op.resid = resid;
-    run_conv(ex, op, r.c2, c->ps);
+    run_conv_stats(ex, op, r.c2, c->ps, out);
   }
   if (r.has_res) ex.release(shortcut);
   ex.release(a2);
@@ -391,7 +402,7 @@ void unet_forward_pass(hsidm_ctx* c, const float* x0, int c0, const float* x1, i
       y = ex.alloc_act(N, (x.H + 1) / 2, (x.W + 1) / 2, L.conv.Cout);
       ConvOp op = conv_op_nhwc(x, nullptr, y);
       op.stride = 2;
-      run_conv(ex, op, L.conv, c->ps);
+      run_conv_stats(ex, op, L.conv, c->ps, y);
     }
     feats.push_back(y);  // every downs output is a skip tensor (unet.py:243-249): keep it alive
     x = y;
@@ -413,7 +424,7 @@ void unet_forward_pass(hsidm_ctx* c, const float* x0, int c0, const float* x1, i
       y = ex.alloc_act(N, x.H * 2, x.W * 2, L.conv.Cout);
       ConvOp op = conv_op_nhwc(x, nullptr, y);
       op.up = 1;
-      run_conv(ex, op, L.conv, c->ps);
+      run_conv_stats(ex, op, L.conv, c->ps, y);
     }
     if (x_owned) ex.release(x);
     x = y, x_owned = true;
