@@ -14,7 +14,9 @@
 //   * one B tile (BN x 64 weights of one tap) feeds MT*4 MMAs instead of 4.
 // L2->SMEM bytes per MMA cycle drop from ~95 to ~35-40 B/clk/SM.
 // Accumulators: MT x BN fp32 columns per tile, double buffered (2*MT*BN <= 512 TMEM columns).
-// Warp roles: warp 0 TMA producer (A ring of 2 halo buffers + B ring), warp 1 MMA issuer, warps 2..9 epilogue (two per
+// Warp roles: warp 0 TMA producer of the A ring (2 halo buffers), warp 1 TMA producer of the B ring (independent, so the
+// next tile's halo is requested a whole tile ahead instead of queueing behind the weight tiles), warp 2 MMA issuer,
+// warps 3..10 epilogue (two per
 // TMEM lane quarter, splitting the tile's channel halves or sub-tiles).  The epilogue also leaves per-slot (sum, sumsq)
 // of what it stored, so the consumer's GroupNorm never re-reads the tensor for statistics.
 #include <cstdlib>
@@ -27,7 +29,8 @@ namespace {
 using namespace tc;
 
 constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kFirstEpiWarp = 3;    // warp 0: A (halo) producer, warp 1: B (weights) producer, warp 2: MMA issuer
+constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
 constexpr int kRows = 16;          // output rows per tile
 constexpr int kHaloRows = kRows + 2;
 constexpr int kAStages = 2;
@@ -36,7 +39,6 @@ struct HaloP {
   int tiles_x, tiles_y;   // tiles per image
   int m_tiles, n_tiles;
   int chunks0, chunks1;   // 64-channel chunks of source 0 / 1
-  int base_offset_mode;   // debug knob: 1 -> put (addr>>7)&7 into the descriptor base_offset field
   EpiP e;
   int* err;
 };
@@ -88,23 +90,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&tfull_bar[s]), 1), mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
+    // =============================== TMA producer: halo tiles (A) ===============================
     if (lane == 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+      int as = 0;
+      uint32_t aph = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        const int mt = tile / p.n_tiles;
         const int n = mt / tpi, r = mt - n * tpi;
         const int y0 = (r / p.tiles_x) * kRows, x0 = (r % p.tiles_x) * (8 * MT);
-        for (int ch = 0; ch < chunks && ok; ++ch) {
+        for (int ch = 0; ch < chunks; ++ch) {
           ok = mbar_wait(smem_u32(&a_empty[as]), aph ^ 1, p.err, 1);
           if (!ok) break;
           const uint32_t fb = smem_u32(&a_full[as]);
@@ -114,6 +116,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           else
             tma_load_4d(smem_u32(smem + as * C::kAStage), &tmA1, fb, (ch - p.chunks0) * kBK, x0 - 1, y0 - 1, n);
           if (++as == kAStages) as = 0, aph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== TMA producer: weight tiles (B) ===============================
+    if (lane == 0) {
+      int bs = 0;
+      uint32_t bph = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        for (int ch = 0; ch < chunks && ok; ++ch) {
           for (int tap = 0; tap < 9; ++tap) {
             ok = mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.err, 5);
             if (!ok) break;
@@ -125,7 +139,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 2) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
@@ -151,8 +165,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
             for (int s = 0; s < MT; ++s) {
               const uint32_t a_addr = a_base + (uint32_t)((dy * C::kPW + 8 * s + dx) * 128);
-              uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
-              if (p.base_offset_mode) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+              const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k)
                 umma_f16(d_tmem + s * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | tap | k) ? 1u : 0u);
@@ -168,9 +181,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   } else {
-    // =============================== epilogue (warps 2..9) ===============================
+    // =============================== epilogue (warps 3..10) ===============================
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;      // which of the two warps of this lane quarter
+    const int half = (warp - kFirstEpiWarp) >> 2;      // which of the two warps of this lane quarter
     const int row = quarter * 32 + lane;   // accumulator row: pixel (row/8, row%8) of a sub-tile
     constexpr int nC = BN / 64;            // 64-channel chunks per tile (0 for the small-Cout instantiation)
     int acc = 0;
@@ -187,23 +200,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * (MT * BN) + ((uint32_t)(quarter * 32) << 16);
       if constexpr (nC >= 1) {
-        uint4* stage = reinterpret_cast<uint4*>(smem_stage + (warp - 2) * 4096);
+        const uint32_t stage = smem_u32(smem_stage + (warp - kFirstEpiWarp) * 4096);
         const int ty0 = (r / p.tiles_x) * kRows, tx0 = (r % p.tiles_x) * (8 * MT);
+        // one pre-combined bias vector per image: the bias-folded noise embedding if present, else the conv bias
+        const float* cb = nbias ? nbias + (long long)n * p.e.nbs : p.e.bias;
+        const float* cb2 = nbias ? p.e.bias : nullptr;
         // split between the two warps of a quarter: by channel chunk when there are several, else by sub-tile
         constexpr bool by_chunk = nC >= 2;
         const int c_first = by_chunk ? half : 0, c_step = by_chunk ? 2 : 1;
         const int s_first = by_chunk ? 0 : half, s_step = by_chunk ? 1 : 2;
+        // flat pixel index of this warp's first accumulator row in sub-tile 0: 4 image rows per lane quarter
+        const long long m_q = ((long long)n * p.e.H + ty0 + quarter * 4) * p.e.W + tx0;
 #pragma unroll 1
         for (int ci = c_first; ci < nC; ci += c_step) {
           float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-          for (int s = s_first; s < MT; s += s_step) {
-            auto pix = [&](int R, int& pn, long long& pm) {
-              pn = n;
-              pm = ((long long)n * p.e.H + ty0 + (R >> 3)) * p.e.W + tx0 + 8 * s + (R & 7);
-            };
-            epilogue_rows64(p.e, nbias, taddr + s * BN + ci * 64, quarter, lane, nt * BN + ci * 64, stage, pix, st);
-          }
+          for (int s = s_first; s < MT; s += s_step)
+            epilogue_halo64(p.e, cb, cb2, taddr + s * BN + ci * 64, lane, nt * BN + ci * 64, stage, m_q + 8 * s, st);
           if (p.e.stats) stats_store(p.e, n, r * (by_chunk ? 4 : 8) + quarter + (by_chunk ? 0 : 4 * half), nt * BN + ci * 64, lane, st);
         }
       } else {
@@ -228,7 +241,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
@@ -258,7 +271,6 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   p.n_tiles = (int)ceil_div(op.Cout, BN);
   p.chunks0 = op.src[0].C / kBK;
   p.chunks1 = op.src[1].C / kBK;
-  p.base_offset_mode = host().base_offset_mode;
   fill_epilogue(&p.e, op);
   p.err = host().err_flag;
   CUtensorMap tmA0, tmA1, tmB;
@@ -271,7 +283,8 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, BN));
   const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
   char tag[96];
-  snprintf(tag, sizeof(tag), "halo MT%d BN%d cin%d+%d cout%d %dx%d n%d", MT, BN, op.src[0].C, op.src[1].C, op.Cout, op.Hin, op.Win, op.N);
+  snprintf(tag, sizeof(tag), "halo MT%d BN%d cin%d+%d cout%d %dx%d n%d%s%s%s", MT, BN, op.src[0].C, op.src[1].C, op.Cout, op.Hin, op.Win, op.N,
+           op.resid ? " +res" : "", op.nbias ? " +nb" : "", op.stats_out ? " +st" : "");
   ProfScope prof(PROF_CONV_TC, 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * K, stream, tag);
   conv_halo_kernel<MT, BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p);
   return after_launch("conv_halo_kernel");

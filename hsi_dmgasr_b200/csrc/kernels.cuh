@@ -112,8 +112,9 @@ int im2col_s2(const void* x, void* out, int N, int H, int W, int C, cudaStream_t
 
 // Noise-level embedding (unet.py:18-31, 182-187) followed by every FeatureWiseAffine linear (unet.py:34-50).
 struct NoiseLayer {
-  const float* w;  // [C][dim]
-  const float* b;  // [C]
+  const float* w;      // [C][dim]
+  const float* b;      // [C]
+  const float* cbias;  // bias of the conv the embedding is added to (folded in so the epilogue adds one vector), or null
   int C, off;
 };
 int noise_embed(const float* level, int level_stride, int n, int dim, const float* w1, const float* b1,

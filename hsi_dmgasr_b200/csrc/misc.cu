@@ -127,6 +127,7 @@ __global__ void noise_embed_kernel(const float* __restrict__ level, int level_st
     for (int o = threadIdx.x; o < L.C; o += blockDim.x) {
       float acc = L.b[o];
       for (int k = 0; k < dim; ++k) acc = fmaf(L.w[o * dim + k], tv[k], acc);
+      if (L.cbias) acc += L.cbias[o];
       nbias[(int64_t)n * total + L.off + o] = acc;
     }
   }

@@ -1,5 +1,6 @@
 #include "net.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace hsidm {
@@ -195,12 +196,36 @@ void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps) {
   }
 }
 
+Act alloc_conv_out(Exec& ex, ConvOp proto, const ConvW& w, const ParamStore& ps) {
+  fill_weights(proto, w, ps);
+  Act out = ex.alloc_act(proto.N, proto.Hout, proto.Wout, w.Cout);
+  ConvOp g;
+  const Route route = plan_conv(ex, proto, w, &g);
+  static const bool no_stats = std::getenv("HSIDM_NO_STATS") != nullptr;   // A/B switch for profiling
+  int slots = 0;
+  if (!no_stats && route != R_SIMT) slots = conv_tc_stats_slots(route == R_TC ? proto : g);
+  if (slots > 0) {
+    out.stats = static_cast<float*>(ex.alloc_raw(sizeof(float) * 2 * (int64_t)proto.N * slots * w.Cout));
+    out.slots = slots;
+  }
+  return out;
+}
+
+Act act_slice(const Act& a, int n0, int cnt, size_t esize) {
+  Act s = a;
+  s.N = cnt;
+  s.p = static_cast<char*>(a.p) + (int64_t)n0 * a.H * a.W * a.C * (int64_t)esize;
+  if (a.stats) s.stats = a.stats + (int64_t)n0 * a.slots * a.C * 2;
+  return s;
+}
+
 void run_conv_stats(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps, Act& out) {
   fill_weights(op, w, ps);
   ConvOp g;
   const Route route = plan_conv(ex, op, w, &g);
   int slots = 0;
-  if (route != R_SIMT && op.out_layout == L_NHWC) slots = conv_tc_stats_slots(route == R_TC ? op : g);
+  static const bool no_stats = std::getenv("HSIDM_NO_STATS") != nullptr;   // A/B switch for profiling
+  if (!no_stats && route != R_SIMT && op.out_layout == L_NHWC) slots = conv_tc_stats_slots(route == R_TC ? op : g);
   if (slots > 0) {
     out.stats = static_cast<float*>(ex.alloc_raw(sizeof(float) * 2 * (int64_t)op.N * slots * op.Cout));
     out.slots = slots;

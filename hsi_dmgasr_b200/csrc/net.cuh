@@ -105,6 +105,11 @@ struct Exec {
 // Fills the weight/bias fields of `op` from `w` and dispatches it. In BF16 mode stride-2 and upsampled convs
 // whose channels fit the tensor-core kernel are lowered to (im2col | upsample) + tensor-core GEMM.
 void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps);
+// Allocates the NHWC output of `proto` (shape fields and source channel counts/layouts filled, pointers irrelevant)
+// together with the statistics buffer the kernel chosen for it will fill (none on the CUDA-core path).
+Act alloc_conv_out(Exec& ex, ConvOp proto, const ConvW& w, const ParamStore& ps);
+// View of images [n0, n0+cnt) of an activation (and of its statistics). Never release a view.
+Act act_slice(const Act& a, int n0, int cnt, size_t esize);
 // Same, additionally asking the kernel to leave GroupNorm partial statistics of its output in `out` (out.stats / out.slots
 // stay null/0 when the chosen kernel cannot produce them, e.g. on the CUDA-core path).
 void run_conv_stats(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps, Act& out);

@@ -284,6 +284,136 @@ static __device__ __forceinline__ void epilogue_rows64(const EpiP& p, const floa
   __syncwarp();
 }
 
+// ---- shared-memory accessors with 32-bit addresses (the staging buffer must not decay to generic LD/ST) ----
+static __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+static __device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+static __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+static __device__ __forceinline__ float2 bf16x2_to_f2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+// Lean epilogue of the halo kernel for 64 output channels [co0, co0+64) of one warp's 32 accumulator rows, which are
+// 4 image rows x 8 pixels starting at flat pixel index m_warp (row pitch W pixels).  Same three phases as
+// epilogue_rows64 (coalesced residual read -> per-row math in registers -> coalesced write, plus column statistics)
+// but with LDS/STS on 32-bit addresses, packed FADD2/FFMA2 arithmetic, one pre-combined bias vector `cb` (conv bias or
+// bias-folded noise embedding) and incremental global addressing: ~1/3 of the instructions, which is what bounds the
+// K = 576 layers at 128x128.
+static __device__ __forceinline__ void epilogue_halo64(const EpiP& p, const float* __restrict__ cb,
+                                                       const float* __restrict__ cb2, uint32_t taddr, int lane, int co0,
+                                                       uint32_t stage, long long m_warp, float4& st) {
+  const int sub = lane >> 3, chunk = lane & 7;
+  const long long pitch = (long long)p.W * p.Cout;   // elements between image rows
+  // element offset of (row 4i+sub, 16-byte chunk `chunk`) relative to pixel m_warp: (i>>1) image rows + 4*(i&1)+sub pixels
+  const long long lane_off = (long long)sub * p.Cout + co0 + chunk * 8;
+  const long long odd_off = 4LL * p.Cout;
+  // phase 1: residual tile -> staging (coalesced)
+  if (p.resid) {
+    const bf16* base = p.resid + m_warp * p.Cout + lane_off;
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(base + (i >> 1) * pitch + (i & 1) * odd_off));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r7 = (4 * (i & 1) + sub) & 7;   // (4i+sub) & 7
+      sts128(stage + (uint32_t)((4 * i + sub) * 128 + ((chunk ^ r7) << 4)), v[i]);
+    }
+    __syncwarp();
+  }
+  // phase 2: own row in registers
+  {
+    uint32_t acc[4][16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tmem_ld16(taddr + q * 16, acc[q]);
+    float4 bias[16];
+    if (cb) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bias[j] = __ldg(reinterpret_cast<const float4*>(cb + co0) + j);
+      if (cb2) {   // conv bias AND noise embedding given separately (not the executor's case, which folds them)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(cb2 + co0) + j);
+          bias[j].x += b.x, bias[j].y += b.y, bias[j].z += b.z, bias[j].w += b.w;
+        }
+      }
+    }
+    tmem_ld_wait();
+    const uint32_t my_row = stage + (uint32_t)(lane * 128);
+    const int l7 = lane & 7;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {   // 8 channels per 16-byte chunk
+      float2 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        v[j] = make_float2(__uint_as_float(acc[c >> 1][(c & 1) * 8 + 2 * j]), __uint_as_float(acc[c >> 1][(c & 1) * 8 + 2 * j + 1]));
+      if (cb) {
+        v[0] = __fadd2_rn(v[0], make_float2(bias[2 * c].x, bias[2 * c].y));
+        v[1] = __fadd2_rn(v[1], make_float2(bias[2 * c].z, bias[2 * c].w));
+        v[2] = __fadd2_rn(v[2], make_float2(bias[2 * c + 1].x, bias[2 * c + 1].y));
+        v[3] = __fadd2_rn(v[3], make_float2(bias[2 * c + 1].z, bias[2 * c + 1].w));
+      }
+      if (p.act == ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j].x = v[j].x > 0.f ? v[j].x : 0.01f * v[j].x, v[j].y = v[j].y > 0.f ? v[j].y : 0.01f * v[j].y;
+      }
+      if (p.scale != 1.0f) {
+        const float2 sc = make_float2(p.scale, p.scale);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __fmul2_rn(v[j], sc);
+      }
+      const uint32_t slot = my_row + (uint32_t)((c ^ l7) << 4);
+      if (p.resid) {
+        const uint4 rv = lds128(slot);
+        v[0] = __fadd2_rn(v[0], bf16x2_to_f2(rv.x));
+        v[1] = __fadd2_rn(v[1], bf16x2_to_f2(rv.y));
+        v[2] = __fadd2_rn(v[2], bf16x2_to_f2(rv.z));
+        v[3] = __fadd2_rn(v[3], bf16x2_to_f2(rv.w));
+      }
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[j].x, v[j].y);
+      sts128(slot, o);
+    }
+    __syncwarp();
+  }
+  // phase 2b: column sums of the stored values (lane -> channel pair 2*lane, 2*lane+1); conflict-free word reads
+  if (p.stats) {
+    const int cw = lane >> 2, ww = lane & 3;
+    uint32_t base[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) base[k] = stage + (uint32_t)(((cw ^ k) << 4) + ww * 4);
+    float2 s = make_float2(st.x, st.y), q = make_float2(st.z, st.w);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const float2 a = bf16x2_to_f2(lds32(base[r & 7] + r * 128));
+      s = __fadd2_rn(s, a);
+      q = __ffma2_rn(a, a, q);
+    }
+    st = make_float4(s.x, s.y, q.x, q.y);
+  }
+  // phase 3: staging -> global (coalesced)
+  {
+    bf16* base = static_cast<bf16*>(p.out) + m_warp * p.Cout + lane_off;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r7 = (4 * (i & 1) + sub) & 7;
+      const uint4 v = lds128(stage + (uint32_t)((4 * i + sub) * 128 + ((chunk ^ r7) << 4)));
+      *reinterpret_cast<uint4*>(base + (i >> 1) * pitch + (i & 1) * odd_off) = v;
+    }
+  }
+  __syncwarp();
+}
+
 // Publishes one warp's accumulated statistics for 64 channels into its slot.
 static __device__ __forceinline__ void stats_store(const EpiP& p, int n, int slot, int co0, int lane, const float4& st) {
   if (n < p.N_img)

@@ -7,6 +7,7 @@
 // timestep lives in device memory so the graph is identical for every step.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "net.cuh"
@@ -236,6 +237,7 @@ Act gn_act(hsidm_ctx* c, const Act& a, const Act* b, int gw, int gb, bool swish)
   return out;
 }
 
+// Conv descriptor with NHWC sources; the output (and its statistics buffer, if it has one) is `out`.
 ConvOp conv_op_nhwc(const Act& in, const Act* in2, const Act& out) {
   ConvOp op;
   op.src[0].p = in.p, op.src[0].C = in.C;
@@ -243,12 +245,23 @@ ConvOp conv_op_nhwc(const Act& in, const Act* in2, const Act& out) {
   op.N = in.N, op.Hin = in.H, op.Win = in.W;
   op.Hout = out.H, op.Wout = out.W;
   op.out = out.p;
+  op.stats_out = out.stats, op.stats_slots = out.slots;
   return op;
+}
+
+// Output tensor of a conv over a source of shape (N, Hin, Win, C0+C1) with the given geometry.
+Act conv_out(hsidm_ctx* c, const ConvW& w, int N, int Hin, int Win, int C0, int C1, int stride = 1, int up = 0) {
+  ConvOp proto;
+  proto.src[0].C = C0, proto.src[1].C = C1;
+  proto.N = N, proto.Hin = Hin, proto.Win = Win, proto.stride = stride, proto.up = up;
+  const int He = up ? 2 * Hin : Hin, We = up ? 2 * Win : Win;
+  proto.Hout = stride == 2 ? (He + 1) / 2 : He, proto.Wout = stride == 2 ? (We + 1) / 2 : We;
+  return alloc_conv_out(c->ex, proto, w, c->ps);
 }
 
 // SelfAttention.forward (unet.py:124-143), n_head = 1, on tensor cores (BF16 mode).  Every contraction is a K-major
 // "NT" GEMM: the V projection is computed transposed (V^T = W_v X^T) so that O = P V contracts over contiguous keys.
-bool attention_tc(hsidm_ctx* c, const ResW& r, const Act& x, Act* result) {
+bool attention_tc(hsidm_ctx* c, const ResW& r, const Act& x, Act& out) {
   Exec& ex = c->ex;
   const int C = x.C, S = x.H * x.W, N = x.N;
   if (ex.prec != HSIDM_BF16 || !r.qkv.w_bf16) return false;
@@ -256,19 +269,18 @@ bool attention_tc(hsidm_ctx* c, const ResW& r, const Act& x, Act* result) {
   probe.M = S, probe.N = S, probe.K = C, probe.lda = 2 * C, probe.ldb = 2 * C, probe.ldc = S, probe.c_f32 = 1;
   probe.sA = probe.sB = (int64_t)S * 2 * C, probe.sC = (int64_t)S * S;
   if (!gemm_tc_supported(probe) || C % 64 || S % 64) return false;
+  {
+    ConvOp t;
+    t.src[0].C = C, t.N = N, t.Hin = t.Hout = x.H, t.Win = t.Wout = x.W, t.ksize = 1, t.Cout = 2 * C, t.w_bf16 = r.qkv.w_bf16;
+    if (!conv_tc_supported(t, ex.prec)) return false;
+  }
   Act nrm = gn_act(c, x, nullptr, r.an_w, r.an_b, false);
   // q, k = first 2C rows of the packed qkv weight
   Act qk = ex.alloc_act(N, x.H, x.W, 2 * C);
   {
     ConvW w2 = r.qkv;
     w2.Cout = 2 * C;
-    ConvOp op = conv_op_nhwc(nrm, nullptr, qk);
-    if (!conv_tc_supported([&] { ConvOp t = op; t.w_bf16 = w2.w_bf16; t.ksize = 1; t.Cout = 2 * C; return t; }(), ex.prec)) {
-      ex.release(qk);
-      ex.release(nrm);
-      return false;
-    }
-    run_conv(ex, op, w2, c->ps);
+    run_conv(ex, conv_op_nhwc(nrm, nullptr, qk), w2, c->ps);
   }
   const bf16* wv = r.qkv.w_bf16 + (int64_t)2 * C * C;   // rows [2C, 3C) of the K-major [3C][C] matrix
   bf16* qkp = static_cast<bf16*>(qk.p);
@@ -295,22 +307,17 @@ bool attention_tc(hsidm_ctx* c, const ResW& r, const Act& x, Act* result) {
   ex.run([&] { return gemm_tc(pv, ex.stream); });
   ex.release_raw(prob);
   ex.release_raw(vt);
-  Act out = ex.alloc_act(N, x.H, x.W, C);
   ConvOp op = conv_op_nhwc(av, nullptr, out);
   op.resid = x.p;
-  run_conv_stats(ex, op, r.aout, c->ps, out);
+  run_conv(ex, op, r.aout, c->ps);
   ex.release(av);
-  *result = out;
   return true;
 }
 
-// Same on CUDA cores (F32 mode, or shapes the tensor-core GEMM does not take).
-Act attention(hsidm_ctx* c, const ResW& r, Act x) {
+// Same on CUDA cores (F32 mode, or shapes the tensor-core GEMM does not take).  Writes into `out`.
+void attention(hsidm_ctx* c, const ResW& r, const Act& x, Act& out) {
   Exec& ex = c->ex;
-  {
-    Act fast;
-    if (attention_tc(c, r, x, &fast)) return fast;
-  }
+  if (attention_tc(c, r, x, out)) return;
   const int C = x.C, S = x.H * x.W;
   Act nrm = gn_act(c, x, nullptr, r.an_w, r.an_b, false);
   Act qkv = ex.alloc_act(x.N, x.H, x.W, 3 * C);
@@ -334,29 +341,33 @@ Act attention(hsidm_ctx* c, const ResW& r, Act x) {
   ex.run([&] { return gemm_simt(pv, ex.prec, ex.stream); });
   ex.release_raw(scores);
   ex.release(qkv);
-  Act out = ex.alloc_act(x.N, x.H, x.W, C);
   ConvOp op = conv_op_nhwc(av, nullptr, out);
   op.resid = x.p;
-  run_conv_stats(ex, op, r.aout, c->ps, out);
+  run_conv(ex, op, r.aout, c->ps);
   ex.release(av);
-  return out;
 }
 
-// ResnetBlocWithAttn.forward (unet.py:105-111, 155-159) on cat(x, skip).  Does not release its inputs.
-Act res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const NoiseRef& nz) {
+// ResnetBlocWithAttn.forward (unet.py:105-111, 155-159) on cat(x, skip), written into `out`.  Inputs are not released.
+void res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const NoiseRef& nz, Act& out) {
   Exec& ex = c->ex;
+  const int C1 = skip ? skip->C : 0;
   Act a1 = gn_act(c, x, skip, r.gn1_w, r.gn1_b, true);
-  Act h = ex.alloc_act(x.N, x.H, x.W, r.cout);
+  Act h = conv_out(c, r.c1, x.N, x.H, x.W, r.cin, 0);
   {
     ConvOp op = conv_op_nhwc(a1, nullptr, h);
     op.nbias = nz.base + r.noise_off, op.nbias_stride = nz.n_stride;
     op.nbias_t = nz.t_dev, op.nbias_t_stride = nz.t_stride;
-    run_conv_stats(ex, op, r.c1, c->ps, h);
+    ConvW w1 = r.c1;
+    w1.pb = -1;   // conv1's bias is folded into the noise-embedding vector (see hsidm_unet_commit)
+    run_conv(ex, op, w1, c->ps);
   }
   ex.release(a1);
   Act a2 = gn_act(c, h, nullptr, r.gn2_w, r.gn2_b, true);
   ex.release(h);
-  Act out = ex.alloc_act(x.N, x.H, x.W, r.cout);
+  // with attention the block output is an intermediate; otherwise conv2 writes straight into `out`
+  Act mid;
+  if (r.attn) mid = conv_out(c, r.c2, x.N, x.H, x.W, r.cout, 0);
+  Act& y = r.attn ? mid : out;
   Act shortcut;
   const void* resid = x.p;
   if (r.has_res) {
@@ -365,80 +376,177 @@ Act res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const 
     resid = shortcut.p;
   }
   {
-    ConvOp op = conv_op_nhwc(a2, nullptr, out);
+    ConvOp op = conv_op_nhwc(a2, nullptr, y);
     op.resid = resid;
-    run_conv_stats(ex, op, r.c2, c->ps, out);
+    run_conv(ex, op, r.c2, c->ps);
   }
   if (r.has_res) ex.release(shortcut);
   ex.release(a2);
   if (r.attn) {
-    Act o2 = attention(c, r, out);
-    ex.release(out);
-    out = o2;
+    attention(c, r, mid, out);
+    ex.release(mid);
   }
-  return out;
+  (void)C1;
+}
+
+// Output tensor of a res layer: written by conv2, or by the attention out-projection.
+Act res_out(hsidm_ctx* c, const ResW& r, int N, int H, int W) {
+  return r.attn ? conv_out(c, r.aout, N, H, W, r.cout, 0) : conv_out(c, r.c2, N, H, W, r.cout, 0);
+}
+
+NoiseRef noise_slice(const NoiseRef& nz, int n0) {
+  NoiseRef s = nz;
+  if (s.base) s.base += (int64_t)n0 * s.n_stride;
+  return s;
+}
+
+// Images per sub-batch at a level whose tensors have `per_image_bytes` bytes: consecutive layers of a level run
+// sub-batch by sub-batch so that producer -> consumer traffic stays in the 126 MB L2 instead of round-tripping HBM.
+int chunk_images(int N, int64_t per_image_bytes) {
+  static const int64_t target = [] {
+    const char* e = std::getenv("HSIDM_CHUNK_MB");
+    return (int64_t)(e ? std::atoi(e) : 0) << 20;   // off by default: measured slower on B200 (see profiles/README.md)
+  }();
+  if (target <= 0) return N;
+  int chunk = (int)std::max<int64_t>(1, target / std::max<int64_t>(1, per_image_bytes));
+  if (chunk >= N) return N;
+  const int nchunks = (N + chunk - 1) / chunk;
+  return (N + nchunks - 1) / nchunks;   // balanced
 }
 
 // UNet.forward (unet.py:239-263).  x0/x1: fp32 NCHW halves of the input; eps: fp32 NCHW.
+// Layers are grouped into stages of equal resolution; each stage is executed sub-batch by sub-batch (see chunk_images).
 void unet_forward_pass(hsidm_ctx* c, const float* x0, int c0, const float* x1, int c1, const NoiseRef& nz, float* eps,
                        int N, int H, int W) {
   Exec& ex = c->ex;
+  const size_t es = ex.esize();
   std::vector<Act> feats;
-  Act x = ex.alloc_act(N, H, W, c->cfg.inner_channel);
-  {
-    ConvOp op;
-    op.src[0].p = x0, op.src[0].C = c0, op.src[0].layout = L_NCHW_F32;
-    if (c1) op.src[1].p = x1, op.src[1].C = c1, op.src[1].layout = L_NCHW_F32;
-    op.N = N, op.Hin = H, op.Win = W, op.Hout = H, op.Wout = W, op.out = x.p;
-    run_conv(ex, op, c->downs[0].conv, c->ps);
-  }
-  feats.push_back(x);
-  for (size_t i = 1; i < c->downs.size(); ++i) {
-    const LayerW& L = c->downs[i];
-    Act y;
-    if (L.kind == LayerW::RES) {
-      y = res_block(c, L.rb, x, nullptr, nz);
-    } else {
-      y = ex.alloc_act(N, (x.H + 1) / 2, (x.W + 1) / 2, L.conv.Cout);
-      ConvOp op = conv_op_nhwc(x, nullptr, y);
-      op.stride = 2;
-      run_conv_stats(ex, op, L.conv, c->ps, y);
+  // ------------------------------------------------ down path ------------------------------------------------
+  Act stage_in;   // full-N input of the current stage (empty for the first: raw NCHW halves)
+  int Hc = H, Wc = W;
+  size_t i = 0;
+  while (i < c->downs.size()) {
+    size_t j = i;
+    while (j < c->downs.size() && c->downs[j].kind != LayerW::DOWN) ++j;
+    if (j < c->downs.size()) ++j;   // the Downsample conv closes the stage
+    std::vector<Act> outs;
+    int cin = i == 0 ? 0 : stage_in.C;
+    for (size_t k = i; k < j; ++k) {
+      const LayerW& L = c->downs[k];
+      if (L.kind == LayerW::CONV) {
+        ConvOp proto;
+        proto.src[0].C = c0, proto.src[0].layout = L_NCHW_F32, proto.src[1].C = c1, proto.src[1].layout = L_NCHW_F32;
+        proto.N = N, proto.Hin = proto.Hout = Hc, proto.Win = proto.Wout = Wc;
+        outs.push_back(alloc_conv_out(ex, proto, L.conv, c->ps));
+      } else if (L.kind == LayerW::RES) {
+        outs.push_back(res_out(c, L.rb, N, Hc, Wc));
+      } else {
+        outs.push_back(conv_out(c, L.conv, N, Hc, Wc, cin, 0, /*stride=*/2));
+      }
+      cin = outs.back().C;
     }
-    feats.push_back(y);  // every downs output is a skip tensor (unet.py:243-249): keep it alive
-    x = y;
+    const int chunk = chunk_images(N, (int64_t)Hc * Wc * outs[0].C * (int64_t)es);
+    for (int n0 = 0; n0 < N; n0 += chunk) {
+      const int cnt = std::min(chunk, N - n0);
+      const NoiseRef nzs = noise_slice(nz, n0);
+      Act xs = i == 0 ? Act() : act_slice(stage_in, n0, cnt, es);
+      for (size_t k = i; k < j; ++k) {
+        const LayerW& L = c->downs[k];
+        Act ys = act_slice(outs[k - i], n0, cnt, es);
+        if (L.kind == LayerW::CONV) {
+          ConvOp op;
+          op.src[0].p = x0 ? x0 + (int64_t)n0 * c0 * H * W : nullptr, op.src[0].C = c0, op.src[0].layout = L_NCHW_F32;
+          if (c1) op.src[1].p = x1 ? x1 + (int64_t)n0 * c1 * H * W : nullptr, op.src[1].C = c1, op.src[1].layout = L_NCHW_F32;
+          op.N = cnt, op.Hin = H, op.Win = W, op.Hout = H, op.Wout = W, op.out = ys.p;
+          op.stats_out = ys.stats, op.stats_slots = ys.slots;
+          run_conv(ex, op, L.conv, c->ps);
+        } else if (L.kind == LayerW::RES) {
+          res_block(c, L.rb, xs, nullptr, nzs, ys);
+        } else {
+          ConvOp op = conv_op_nhwc(xs, nullptr, ys);
+          op.stride = 2;
+          run_conv(ex, op, L.conv, c->ps);
+        }
+        xs = ys;
+      }
+    }
+    for (auto& o : outs) feats.push_back(o);   // every downs output is a skip tensor (unet.py:243-249)
+    stage_in = outs.back();
+    Hc = stage_in.H, Wc = stage_in.W;
+    i = j;
   }
-  bool x_owned = false;  // x aliases feats.back() here
+  // ------------------------------------------------ middle ------------------------------------------------
+  Act x = stage_in;       // aliases feats.back()
+  bool x_owned = false;
   for (const LayerW& L : c->mid) {
-    Act y = res_block(c, L.rb, x, nullptr, nz);
+    Act y = res_out(c, L.rb, N, x.H, x.W);
+    res_block(c, L.rb, x, nullptr, nz, y);
     if (x_owned) ex.release(x);
     x = y, x_owned = true;
   }
-  for (const LayerW& L : c->ups) {
-    Act y;
-    if (L.kind == LayerW::RES) {
-      Act skip = feats.back();
-      feats.pop_back();
-      y = res_block(c, L.rb, x, &skip, nz);
-      ex.release(skip);
-    } else {
-      y = ex.alloc_act(N, x.H * 2, x.W * 2, L.conv.Cout);
-      ConvOp op = conv_op_nhwc(x, nullptr, y);
-      op.up = 1;
-      run_conv_stats(ex, op, L.conv, c->ps, y);
+  // ------------------------------------------------ up path ------------------------------------------------
+  const int out_ch = c->cfg.out_channel;
+  i = 0;
+  while (i < c->ups.size()) {
+    size_t j = i + 1;   // a stage = [optional leading Upsample conv] + res blocks up to the next Upsample
+    while (j < c->ups.size() && c->ups[j].kind != LayerW::UP) ++j;
+    const bool last_stage = j == c->ups.size();
+    const bool lead_up = c->ups[i].kind == LayerW::UP;
+    const int Hs = lead_up ? 2 * x.H : x.H, Ws = lead_up ? 2 * x.W : x.W;
+    // skips consumed by this stage, in pop order
+    std::vector<Act> skips;
+    for (size_t k = i; k < j; ++k)
+      if (c->ups[k].kind == LayerW::RES) skips.push_back(feats.back()), feats.pop_back();
+    const ResW& tail = c->ups[j - 1].rb;   // a stage always ends with a res block
+    Act stage_out;
+    if (!last_stage) stage_out = res_out(c, tail, N, Hs, Ws);
+    const int chunk = chunk_images(N, (int64_t)Hs * Ws * tail.cout * (int64_t)es);
+    for (int n0 = 0; n0 < N; n0 += chunk) {
+      const int cnt = std::min(chunk, N - n0);
+      const NoiseRef nzs = noise_slice(nz, n0);
+      Act xs = act_slice(x, n0, cnt, es);
+      bool xs_owned = false;
+      size_t sk = 0;
+      for (size_t k = i; k < j; ++k) {
+        const LayerW& L = c->ups[k];
+        const bool is_tail = k + 1 == j;
+        Act ys;
+        if (L.kind == LayerW::UP) {
+          ys = conv_out(c, L.conv, cnt, xs.H, xs.W, xs.C, 0, 1, /*up=*/1);
+          ConvOp op = conv_op_nhwc(xs, nullptr, ys);
+          op.up = 1;
+          run_conv(ex, op, L.conv, c->ps);
+        } else {
+          const Act skip = act_slice(skips[sk++], n0, cnt, es);
+          const bool into_stage_out = is_tail && !last_stage;
+          ys = into_stage_out ? act_slice(stage_out, n0, cnt, es) : res_out(c, L.rb, cnt, xs.H, xs.W);
+          res_block(c, L.rb, xs, &skip, nzs, ys);
+          if (into_stage_out) {
+            if (xs_owned) ex.release(xs);
+            xs = ys, xs_owned = false;
+            continue;
+          }
+        }
+        if (xs_owned) ex.release(xs);
+        xs = ys, xs_owned = true;
+      }
+      if (last_stage) {
+        // final_conv = GroupNorm -> Swish -> conv to out_channel, fp32 NCHW (unet.py:236, 263)
+        Act a = gn_act(c, xs, nullptr, c->fin_gn_w, c->fin_gn_b, true);
+        if (xs_owned) ex.release(xs);
+        ConvOp op;
+        op.src[0].p = a.p, op.src[0].C = a.C;
+        op.N = cnt, op.Hin = a.H, op.Win = a.W, op.Hout = a.H, op.Wout = a.W;
+        op.out = eps ? eps + (int64_t)n0 * out_ch * a.H * a.W : nullptr, op.out_layout = L_NCHW_F32;
+        run_conv(ex, op, c->fin_conv, c->ps);
+        ex.release(a);
+      }
     }
+    for (auto& s : skips) ex.release(s);
     if (x_owned) ex.release(x);
-    x = y, x_owned = true;
+    x = stage_out, x_owned = true;
+    i = j;
   }
-  Act a = gn_act(c, x, nullptr, c->fin_gn_w, c->fin_gn_b, true);
-  ex.release(x);
-  {
-    ConvOp op;
-    op.src[0].p = a.p, op.src[0].C = a.C;
-    op.N = N, op.Hin = a.H, op.Win = a.W, op.Hout = a.H, op.Wout = a.W;
-    op.out = eps, op.out_layout = L_NCHW_F32;
-    run_conv(ex, op, c->fin_conv, c->ps);
-  }
-  ex.release(a);
 }
 
 int check_shape(hsidm_ctx* c, int c0, int c1, int N, int H, int W) {
@@ -592,7 +700,8 @@ int hsidm_unet_commit(hsidm_ctx* c) {
   auto visit = [&](std::vector<LayerW>& v) {
     for (auto& L : v)
       if (L.kind == LayerW::RES)
-        c->noise_layers_host.push_back(NoiseLayer{c->ps.dev(L.rb.nf_w), c->ps.dev(L.rb.nf_b), L.rb.cout, L.rb.noise_off});
+        c->noise_layers_host.push_back(
+            NoiseLayer{c->ps.dev(L.rb.nf_w), c->ps.dev(L.rb.nf_b), c->ps.dev(L.rb.c1.pb), L.rb.cout, L.rb.noise_off});
   };
   visit(c->downs), visit(c->mid), visit(c->ups);
   if (c->noise_layers_dev) cudaFree(c->noise_layers_dev);
