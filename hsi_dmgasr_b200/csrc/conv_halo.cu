@@ -39,6 +39,7 @@ struct HaloP {
   int tiles_x, tiles_y;   // tiles per image
   int m_tiles, n_tiles;
   int chunks0, chunks1;   // 64-channel chunks of source 0 / 1
+  int rchunks0, rchunks1; // 64-channel chunks of the shortcut sources (centre tap only; K columns after the 3x3 part)
   EpiP e;
   int* err;
 };
@@ -61,6 +62,7 @@ struct HCfg {
 template <int MT, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                  const __grid_constant__ CUtensorMap tmB, const HaloP p) {
   using C = HCfg<MT, BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -79,11 +81,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int chunks = p.chunks0 + p.chunks1;
+  const int rchunks = p.rchunks0 + p.rchunks1;
   const int tpi = p.tiles_x * p.tiles_y;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     if (p.chunks1) tma_prefetch_desc(&tmA1);
+    if (p.rchunks0) tma_prefetch_desc(&tmR0);
+    if (p.rchunks1) tma_prefetch_desc(&tmR1);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kAStages; ++s) mbar_init(smem_u32(&a_full[s]), 1), mbar_init(smem_u32(&a_empty[s]), 1);
     for (int s = 0; s < C::kBStages; ++s) mbar_init(smem_u32(&b_full[s]), 1), mbar_init(smem_u32(&b_empty[s]), 1);
@@ -106,15 +111,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int mt = tile / p.n_tiles;
         const int n = mt / tpi, r = mt - n * tpi;
         const int y0 = (r / p.tiles_x) * kRows, x0 = (r % p.tiles_x) * (8 * MT);
-        for (int ch = 0; ch < chunks; ++ch) {
+        for (int ch = 0; ch < chunks + rchunks; ++ch) {
           ok = mbar_wait(smem_u32(&a_empty[as]), aph ^ 1, p.err, 1);
           if (!ok) break;
           const uint32_t fb = smem_u32(&a_full[as]);
+          const uint32_t dst = smem_u32(smem + as * C::kAStage);
           mbar_expect_tx(fb, C::kABox);
           if (ch < p.chunks0)
-            tma_load_4d(smem_u32(smem + as * C::kAStage), &tmA0, fb, ch * kBK, x0 - 1, y0 - 1, n);
+            tma_load_4d(dst, &tmA0, fb, ch * kBK, x0 - 1, y0 - 1, n);
+          else if (ch < chunks)
+            tma_load_4d(dst, &tmA1, fb, (ch - p.chunks0) * kBK, x0 - 1, y0 - 1, n);
+          else if (ch < chunks + p.rchunks0)
+            tma_load_4d(dst, &tmR0, fb, (ch - chunks) * kBK, x0 - 1, y0 - 1, n);
           else
-            tma_load_4d(smem_u32(smem + as * C::kAStage), &tmA1, fb, (ch - p.chunks0) * kBK, x0 - 1, y0 - 1, n);
+            tma_load_4d(dst, &tmR1, fb, (ch - chunks - p.rchunks0) * kBK, x0 - 1, y0 - 1, n);
           if (++as == kAStages) as = 0, aph ^= 1;
         }
       }
@@ -136,6 +146,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_load_2d(smem_u32(smem_b + bs * C::kBStage), &tmB, bb, (tap * chunks + ch) * kBK, nt * BN);
             if (++bs == C::kBStages) bs = 0, bph ^= 1;
           }
+        }
+        for (int rc = 0; rc < rchunks && ok; ++rc) {   // shortcut columns follow the 9*chunks 3x3 columns
+          ok = mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.err, 5);
+          if (!ok) break;
+          const uint32_t bb = smem_u32(&b_full[bs]);
+          mbar_expect_tx(bb, C::kBStage);
+          tma_load_2d(smem_u32(smem_b + bs * C::kBStage), &tmB, bb, (9 * chunks + rc) * kBK, nt * BN);
+          if (++bs == C::kBStages) bs = 0, bph ^= 1;
         }
       }
     }
@@ -173,6 +191,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             umma_commit(smem_u32(&b_empty[bs]));
             if (++bs == C::kBStages) bs = 0, bph ^= 1;
           }
+          umma_commit(smem_u32(&a_empty[as]));
+          if (++as == kAStages) as = 0, aph ^= 1;
+        }
+        for (int rc = 0; rc < rchunks && ok; ++rc) {   // shortcut: centre tap of the un-normalised block input
+          ok = mbar_wait(smem_u32(&a_full[as]), aph, p.err, 3);
+          if (!ok) break;
+          ok = mbar_wait(smem_u32(&b_full[bs]), bph, p.err, 6);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + as * C::kAStage);
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + bs * C::kBStage));
+#pragma unroll
+          for (int s = 0; s < MT; ++s) {
+            const uint32_t a_addr = a_base + (uint32_t)((1 * C::kPW + 8 * s + 1) * 128);
+            const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) umma_f16(d_tmem + s * BN, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+          }
+          umma_commit(smem_u32(&b_empty[bs]));
+          if (++bs == C::kBStages) bs = 0, bph ^= 1;
           umma_commit(smem_u32(&a_empty[as]));
           if (++as == kAStages) as = 0, aph ^= 1;
         }
@@ -271,6 +309,8 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   p.n_tiles = (int)ceil_div(op.Cout, BN);
   p.chunks0 = op.src[0].C / kBK;
   p.chunks1 = op.src[1].C / kBK;
+  p.rchunks0 = op.rsrc[0].C / kBK;
+  p.rchunks1 = op.rsrc[1].C / kBK;
   fill_epilogue(&p.e, op);
   p.err = host().err_flag;
   CUtensorMap tmA0, tmA1, tmB;
@@ -279,6 +319,9 @@ int launch(const ConvOp& op, cudaStream_t stream) {
     HSIDM_TRY(encode_act_map(&tmA1, op.src[1].p, op.N, op.Hin, op.Win, op.src[1].C, C::kPW, kHaloRows, 1));
   else
     tmA1 = tmA0;
+  CUtensorMap tmR0 = tmA0, tmR1 = tmA0;
+  if (p.rchunks0) HSIDM_TRY(encode_act_map(&tmR0, op.rsrc[0].p, op.N, op.Hin, op.Win, op.rsrc[0].C, C::kPW, kHaloRows, 1));
+  if (p.rchunks1) HSIDM_TRY(encode_act_map(&tmR1, op.rsrc[1].p, op.N, op.Hin, op.Win, op.rsrc[1].C, C::kPW, kHaloRows, 1));
   const int K = op.K();
   HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, BN));
   const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
@@ -286,7 +329,7 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   snprintf(tag, sizeof(tag), "halo MT%d BN%d cin%d+%d cout%d %dx%d n%d%s%s%s", MT, BN, op.src[0].C, op.src[1].C, op.Cout, op.Hin, op.Win, op.N,
            op.resid ? " +res" : "", op.nbias ? " +nb" : "", op.stats_out ? " +st" : "");
   ProfScope prof(PROF_CONV_TC, 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * K, stream, tag);
-  conv_halo_kernel<MT, BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p);
+  conv_halo_kernel<MT, BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmR0, tmR1, tmB, p);
   return after_launch("conv_halo_kernel");
 }
 
@@ -312,6 +355,8 @@ bool conv_halo_supported(const ConvOp& op) {
   int MT, BN;
   pick_shape(op, &MT, &BN);
   if (MT == 0) return false;
+  for (int i = 0; i < 2; ++i)
+    if (op.rsrc[i].C && (op.rsrc[i].C % kBK || op.rsrc[i].layout != L_NHWC)) return false;
   // the packed weight rows are padded to pick_bn(Cout); the halo kernel's BN must divide that padding
   return tc::pick_bn(op.Cout) % BN == 0;
 }

@@ -212,6 +212,7 @@ int launch(const SimtP& p, cudaStream_t stream) {
 int conv_simt(const ConvOp& op, int prec, cudaStream_t stream) {
   if (!op.w_f32) HSIDM_FAIL(HSIDM_BAD_STATE, "conv_simt: fp32 weights were not packed");
   if (op.ksize != 1 && op.ksize != 3) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_simt: kernel size %d", op.ksize);
+  if (op.rsrc[0].C || op.rsrc[1].C) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_simt: fused shortcut sources are a tensor-core feature");
   SimtP p;
   for (int i = 0; i < 2; ++i) {
     p.s[i] = op.src[i].p;

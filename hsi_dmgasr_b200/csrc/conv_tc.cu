@@ -358,6 +358,8 @@ int conv_tc_init() {
   return g_init_status;
 }
 
+bool conv_halo_ok(const ConvOp& op) { return !tc::host().no_halo && conv_halo_supported(op); }
+
 int conv_tc_stats_slots(const ConvOp& op) {
   if (!conv_tc_supported(op, HSIDM_BF16)) return 0;
   if (!tc::host().no_halo && conv_halo_supported(op)) return conv_halo_stats_slots(op);
@@ -390,6 +392,8 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: op (Cin %d+%d, Cout %d, k%d s%d, %dx%d) does not fit the tensor-core kernel",
                op.src[0].C, op.src[1].C, op.Cout, op.ksize, op.stride, op.Hin, op.Win);
   if (!host().no_halo && conv_halo_supported(op)) return conv_halo(op, stream);
+  if (op.rsrc[0].C || op.rsrc[1].C)
+    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: fused shortcut sources need the halo kernel, which does not take this shape");
   TcP p;
   tile_geometry(op.Hin, op.Win, &p.bw, &p.bh, &p.bn);
   const int BN = pick_bn(op.Cout);

@@ -20,6 +20,9 @@ struct ConvSrc {
 // out = [clamp01]( act(conv(cat(src0,src1)) + bias + nbias[n]) * scale + resid )
 struct ConvOp {
   ConvSrc src[2];
+  // optional shortcut sources (halo tensor-core kernel only): un-normalised NHWC tensors whose 1x1 projection (or
+  // identity) is accumulated into the same output: their channels are extra K columns after the k*k*(C0+C1) ones
+  ConvSrc rsrc[2];
   int N = 0, Hin = 0, Win = 0;  // source spatial size
   int up = 0;                   // 1: source is nearest-2x upsampled on the fly (unet.py:58-65)
   int ksize = 3, stride = 1;    // padding = ksize/2
@@ -41,7 +44,7 @@ struct ConvOp {
   // conv_tc_stats_slots(op) (tensor-core kernels only)
   float* stats_out = nullptr;
   int stats_slots = 0;
-  int K() const { return ksize * ksize * (src[0].C + src[1].C); }
+  int K() const { return ksize * ksize * (src[0].C + src[1].C) + rsrc[0].C + rsrc[1].C; }
 };
 
 // conv_simt.cu : CUDA-core implicit GEMM, fp32 accumulate; handles every ConvOp.
@@ -50,6 +53,7 @@ int conv_simt(const ConvOp& op, int prec, cudaStream_t stream);
 // fits the tensor-core kernel's constraints; conv_tc() fails loudly otherwise.
 bool conv_tc_supported(const ConvOp& op, int prec);
 int conv_tc(const ConvOp& op, cudaStream_t stream);
+bool conv_halo_ok(const ConvOp& op);         // the halo kernel (and with it fused shortcut sources) takes this op
 int conv_tc_stats_slots(const ConvOp& op);  // slots per image the kernel chosen for `op` fills (0 = no fused statistics)
 int conv_tc_init();               // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int conv_tc_bn_rows(int Cout);    // N-tile height; packed bf16 weights are padded to a multiple of it (0 = unsupported)

@@ -131,6 +131,51 @@ int pack_conv(const ParamStore& ps, ConvW& c, bool bf16_too) {
   return after_launch("pack_kernel");
 }
 
+namespace {
+// out[co][k]: k < 9*C -> conv2 weight (k = tap*C + c); k >= 9*C -> shortcut weight (res_conv, or identity when wr == null)
+__global__ void pack_fused_kernel(const float* __restrict__ w2, const float* __restrict__ wr, const float* __restrict__ b2,
+                                  const float* __restrict__ br, int Cout, int C, int Cr, bf16* __restrict__ out,
+                                  float* __restrict__ bias) {
+  const int K = 9 * C + Cr;
+  const int64_t total = (int64_t)Cout * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i / K), k = (int)(i % K);
+    float v;
+    if (k < 9 * C) {
+      const int tap = k / C, c = k - tap * C;
+      v = w2[((int64_t)co * C + c) * 9 + tap];
+    } else {
+      const int c = k - 9 * C;
+      v = wr ? wr[(int64_t)co * Cr + c] : (c == co ? 1.0f : 0.0f);
+    }
+    out[i] = __float2bfloat16_rn(v);
+    if (k == 0) bias[co] = b2[co] + (br ? br[co] : 0.0f);
+  }
+}
+}  // namespace
+
+void free_fused(FusedW& f) {
+  if (f.w) cudaFree(f.w);
+  if (f.bias) cudaFree(f.bias);
+  f.w = nullptr, f.bias = nullptr, f.bytes = 0;
+}
+
+int pack_fused(const ParamStore& ps, const ConvW& c2, const ConvW* rc, FusedW& f) {
+  free_fused(f);
+  f.C = c2.Cin, f.Cout = c2.Cout, f.Cr = rc ? rc->Cin : c2.Cout;
+  const int bn = conv_tc_bn_rows(f.Cout);
+  if (bn <= 0 || f.C % 64 || f.Cr % 64 || f.Cout % 64) return HSIDM_OK;   // not a tensor-core shape: leave unfused
+  const int64_t K = 9LL * f.C + f.Cr, rows = round_up(f.Cout, bn);
+  HSIDM_CUDA(cudaMalloc(&f.w, sizeof(bf16) * rows * K));
+  HSIDM_CUDA(cudaMemset(f.w, 0, sizeof(bf16) * rows * K));
+  HSIDM_CUDA(cudaMalloc(&f.bias, sizeof(float) * f.Cout));
+  f.bytes = sizeof(bf16) * rows * K + sizeof(float) * f.Cout;
+  const int grid = (int)std::min<int64_t>(ceil_div((int64_t)f.Cout * K, 256), 4096);
+  pack_fused_kernel<<<grid, 256>>>(ps.dev(c2.pw), rc ? ps.dev(rc->pw) : nullptr, ps.dev(c2.pb), rc ? ps.dev(rc->pb) : nullptr,
+                                   f.Cout, f.C, f.Cr, f.w, f.bias);
+  return after_launch("pack_fused_kernel");
+}
+
 // ---- dispatcher -----------------------------------------------------------------------------------------------
 namespace {
 enum Route { R_TC, R_DOWN, R_UP, R_SIMT };
@@ -160,7 +205,7 @@ Route plan_conv(const Exec& ex, const ConvOp& op, const ConvW& w, ConvOp* g) {
 void fill_weights(ConvOp& op, const ConvW& w, const ParamStore& ps) {
   op.w_f32 = w.w_f32;
   op.w_bf16 = w.w_bf16;
-  op.bias = ps.dev(w.pb);
+  op.bias = w.bias_override ? w.bias_override : ps.dev(w.pb);
   op.ksize = w.ks;
   op.Cout = w.Cout;
 }

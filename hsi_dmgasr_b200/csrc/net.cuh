@@ -47,7 +47,19 @@ struct ConvW {
   float* w_f32 = nullptr;  // [k*k*Cin][Cout]
   bf16* w_bf16 = nullptr;  // [rows >= Cout][k*k*Cin], zero padded rows
   int64_t packed_bytes = 0;
+  const float* bias_override = nullptr;  // used instead of the parameter bias when set (fused weights)
 };
+
+// conv2 of a res block with its shortcut folded in as extra K columns: W = [ W_conv2 (k = tap*C + c) | W_shortcut ],
+// W_shortcut = res_conv weight, or the identity when the block has no res_conv; bias = b_conv2 (+ b_res_conv).
+struct FusedW {
+  bf16* w = nullptr;     // [rows >= Cout][9*C + Cr]
+  float* bias = nullptr; // [Cout]
+  int C = 0, Cr = 0, Cout = 0;
+  int64_t bytes = 0;
+};
+int pack_fused(const ParamStore& ps, const ConvW& c2, const ConvW* rc, FusedW& f);
+void free_fused(FusedW& f);
 
 // Registers "<prefix>.weight" / "<prefix>.bias" and returns the ConvW.
 ConvW make_conv(ParamStore& ps, const std::string& prefix, int Cin, int Cout, int ks, bool bias = true);

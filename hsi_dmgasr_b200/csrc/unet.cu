@@ -20,6 +20,7 @@ struct ResW {
   int gn1_w = -1, gn1_b = -1, gn2_w = -1, gn2_b = -1;
   int nf_w = -1, nf_b = -1, noise_off = 0;
   ConvW c1, c2, rc;
+  FusedW fused;   // conv2 + shortcut as one tensor-core GEMM (BF16 mode)
   int an_w = -1, an_b = -1;
   ConvW qkv, aout;
 };
@@ -368,19 +369,35 @@ void res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const
   Act mid;
   if (r.attn) mid = conv_out(c, r.c2, x.N, x.H, x.W, r.cout, 0);
   Act& y = r.attn ? mid : out;
+  // Shortcut: folded into conv2 as extra K columns on the halo tensor-core kernel (res_conv always; the identity only
+  // for the narrow layers whose epilogue, not the MMA pipe, is the bottleneck); otherwise a 1x1 conv / epilogue add.
+  bool fused = false;
+  if (ex.prec == HSIDM_BF16 && r.fused.w && (r.has_res || r.cout <= 128)) {
+    ConvOp op = conv_op_nhwc(a2, nullptr, y);
+    op.rsrc[0].p = x.p, op.rsrc[0].C = x.C;
+    if (skip) op.rsrc[1].p = skip->p, op.rsrc[1].C = skip->C;
+    ConvW wf;
+    wf.Cin = r.cout, wf.Cout = r.cout, wf.ks = 3, wf.w_bf16 = r.fused.w, wf.bias_override = r.fused.bias;
+    ConvOp probe = op;
+    probe.w_bf16 = wf.w_bf16, probe.Cout = wf.Cout;
+    if (conv_tc_supported(probe, ex.prec) && conv_halo_ok(probe)) {
+      run_conv(ex, op, wf, c->ps);
+      fused = true;
+    }
+  }
   Act shortcut;
   const void* resid = x.p;
-  if (r.has_res) {
+  if (!fused && r.has_res) {
     shortcut = ex.alloc_act(x.N, x.H, x.W, r.cout);
     run_conv(ex, conv_op_nhwc(x, skip, shortcut), r.rc, c->ps);
     resid = shortcut.p;
   }
-  {
+  if (!fused) {
     ConvOp op = conv_op_nhwc(a2, nullptr, y);
     op.resid = resid;
     run_conv(ex, op, r.c2, c->ps);
   }
-  if (r.has_res) ex.release(shortcut);
+  if (!fused && r.has_res) ex.release(shortcut);
   ex.release(a2);
   if (r.attn) {
     attention(c, r, mid, out);
@@ -657,6 +674,9 @@ int hsidm_ctx_destroy(hsidm_ctx* c) {
   cudaDeviceSynchronize();
   drop_graph(c);
   for_each_conv(c, [](ConvW& w) { free_conv(w); });
+  for (auto* v : {&c->downs, &c->mid, &c->ups})
+    for (auto& L : *v)
+      if (L.kind == LayerW::RES) free_fused(L.rb.fused);
   if (c->noise_layers_dev) cudaFree(c->noise_layers_dev);
   if (c->coef_dev) cudaFree(c->coef_dev);
   if (c->levels_dev) cudaFree(c->levels_dev);
@@ -696,6 +716,17 @@ int hsidm_unet_commit(hsidm_ctx* c) {
     c->packed_bytes += w.packed_bytes;
   });
   HSIDM_TRY(status);
+  if (c->cfg.precision == HSIDM_BF16) {
+    auto fuse = [&](std::vector<LayerW>& v) {
+      for (auto& L : v)
+        if (L.kind == LayerW::RES && status == HSIDM_OK) {
+          status = pack_fused(c->ps, L.rb.c2, L.rb.has_res ? &L.rb.rc : nullptr, L.rb.fused);
+          c->packed_bytes += L.rb.fused.bytes;
+        }
+    };
+    fuse(c->downs), fuse(c->mid), fuse(c->ups);
+    HSIDM_TRY(status);
+  }
   c->noise_layers_host.clear();
   auto visit = [&](std::vector<LayerW>& v) {
     for (auto& L : v)
