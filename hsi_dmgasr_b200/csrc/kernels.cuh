@@ -111,6 +111,9 @@ int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int 
              const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream);
 
 int upsample2x(const void* x, void* out, int N, int H, int W, int C, int prec, cudaStream_t stream);
+// 3x3/pad-1 im2col of up to two NCHW fp32 sources with 9*(C0+C1) <= 64 into [N,H,W,64] bf16 rows (k = tap*(C0+C1) + c,
+// zero padded): lets the first UNet conv (6 -> 64) run as a K = 64 tensor-core GEMM.
+int im2col_small(const float* x0, int C0, const float* x1, int C1, void* out, int N, int H, int W, cudaStream_t stream);
 // Stride-2 3x3 im2col for the tensor-core path: out [N,H/2,W/2,9*C] (bf16).
 int im2col_s2(const void* x, void* out, int N, int H, int W, int C, cudaStream_t stream);
 

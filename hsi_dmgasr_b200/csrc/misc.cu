@@ -170,6 +170,39 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
   }
 }
 
+// one thread per output pixel: 64 bf16 = 128 B per row; sources are read plane by plane (coalesced along x)
+__global__ void im2col_small_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                                    bf16* __restrict__ out, int H, int W, int64_t total) {
+  const int Ct = C0 + C1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int64_t n = i / ((int64_t)W * H);
+    uint32_t packed[32];
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) {
+      float f[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = 2 * k2 + h;
+        float v = 0.f;
+        if (k < 9 * Ct) {
+          const int tap = k / Ct, c = k - tap * Ct;
+          const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+            v = c < C0 ? __ldg(x0 + ((n * C0 + c) * H + iy) * (int64_t)W + ix) : __ldg(x1 + ((n * C1 + (c - C0)) * H + iy) * (int64_t)W + ix);
+        }
+        f[h] = v;
+      }
+      __nv_bfloat162 b = __floats2bfloat162_rn(f[0], f[1]);
+      packed[k2] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + i * 64);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+  }
+}
+
 // one warp per row, in place
 __global__ void softmax_kernel(float* __restrict__ x, int64_t rows, int cols) {
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -344,6 +377,14 @@ int upsample2x(const void* x, void* out, int N, int H, int W, int C, int prec, c
   else
     upsample2x_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>((const float*)x, (float*)out, H, W, C / 8, total);
   return after_launch("upsample2x_kernel");
+}
+
+int im2col_small(const float* x0, int C0, const float* x1, int C1, void* out, int N, int H, int W, cudaStream_t stream) {
+  if (9 * (C0 + C1) > 64) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "im2col_small: 9*(%d+%d) > 64", C0, C1);
+  const int64_t total = (int64_t)N * H * W;
+  ProfScope prof(PROF_OTHER, (double)total * (128 + 4.0 * (C0 + C1)), stream, "im2col_small");
+  im2col_small_kernel<<<grid_for(total, 128), 128, 0, stream>>>(x0, C0, x1, C1, static_cast<bf16*>(out), H, W, total);
+  return after_launch("im2col_small_kernel");
 }
 
 int im2col_s2(const void* x, void* out, int N, int H, int W, int C, cudaStream_t stream) {

@@ -104,12 +104,26 @@ __global__ void pack_kernel(const float* __restrict__ w, int Cout, int Cin, int 
     if (o16) o16[(int64_t)co * K + tap * Cin + ci] = __float2bfloat16_rn(v);
   }
 }
+// w[co][ci][tap] -> col[co*64 + tap*Cin + ci], zero padded to 64 columns
+__global__ void pack_col_kernel(const float* __restrict__ w, int Cout, int Cin, bf16* __restrict__ o) {
+  const int total = Cout * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i / 64, k = i % 64;
+    float v = 0.f;
+    if (k < 9 * Cin) {
+      const int tap = k / Cin, ci = k - tap * Cin;
+      v = w[((int64_t)co * Cin + ci) * 9 + tap];
+    }
+    o[i] = __float2bfloat16_rn(v);
+  }
+}
 }  // namespace
 
 void free_conv(ConvW& c) {
   if (c.w_f32) cudaFree(c.w_f32);
   if (c.w_bf16) cudaFree(c.w_bf16);
-  c.w_f32 = nullptr, c.w_bf16 = nullptr, c.packed_bytes = 0;
+  if (c.w_col) cudaFree(c.w_col);
+  c.w_f32 = nullptr, c.w_bf16 = nullptr, c.w_col = nullptr, c.packed_bytes = 0;
 }
 
 int pack_conv(const ParamStore& ps, ConvW& c, bool bf16_too) {
@@ -124,6 +138,14 @@ int pack_conv(const ParamStore& ps, ConvW& c, bool bf16_too) {
     HSIDM_CUDA(cudaMalloc(&c.w_bf16, sizeof(bf16) * rows * K));
     HSIDM_CUDA(cudaMemset(c.w_bf16, 0, sizeof(bf16) * rows * K));
     c.packed_bytes += sizeof(bf16) * rows * K;
+  }
+  if (bf16_too && bn > 0 && c.ks == 3 && 9 * c.Cin <= 64) {
+    const int64_t rows = round_up(c.Cout, bn);
+    HSIDM_CUDA(cudaMalloc(&c.w_col, sizeof(bf16) * rows * 64));
+    HSIDM_CUDA(cudaMemset(c.w_col, 0, sizeof(bf16) * rows * 64));
+    pack_col_kernel<<<(unsigned)ceil_div(c.Cout * 64, 256), 256>>>(ps.dev(c.pw), c.Cout, c.Cin, c.w_col);
+    HSIDM_TRY(after_launch("pack_col_kernel"));
+    c.packed_bytes += sizeof(bf16) * rows * 64;
   }
   const int64_t total = K * c.Cout;
   const int grid = (int)std::min<int64_t>(ceil_div(total, 256), 4096);
@@ -178,13 +200,23 @@ int pack_fused(const ParamStore& ps, const ConvW& c2, const ConvW* rc, FusedW& f
 
 // ---- dispatcher -----------------------------------------------------------------------------------------------
 namespace {
-enum Route { R_TC, R_DOWN, R_UP, R_SIMT };
+enum Route { R_TC, R_DOWN, R_UP, R_COL, R_SIMT };
 
 // Decides how `op` runs and, for the lowered routes, fills `g` with the tensor-core op (its source pointer is patched
 // once the temporary exists).
 Route plan_conv(const Exec& ex, const ConvOp& op, const ConvW& w, ConvOp* g) {
   const int prec = ex.prec;
   *g = op;
+  if (prec == HSIDM_BF16 && w.w_col && op.ksize == 3 && op.stride == 1 && !op.up && op.src[0].layout == L_NCHW_F32 &&
+      !op.src[0].img_off && (op.src[1].C == 0 || (op.src[1].layout == L_NCHW_F32 && !op.src[1].img_off)) &&
+      9 * (op.src[0].C + op.src[1].C) <= 64) {
+    // tiny-Cin first conv (unet.py:196-197): im2col to K = 64, then a 1x1 tensor-core GEMM
+    g->src[0] = ConvSrc();
+    g->src[0].C = 64, g->src[1] = ConvSrc();
+    g->ksize = 1, g->w_bf16 = w.w_col;
+    if (conv_tc_supported(*g, prec)) return R_COL;
+    *g = op;
+  }
   if (prec != HSIDM_BF16 || !w.w_bf16) return R_SIMT;
   if (conv_tc_supported(op, prec)) return R_TC;
   const bool nhwc1 = op.src[0].layout == L_NHWC && op.src[1].C == 0 && op.src[0].C % 64 == 0;
@@ -224,6 +256,14 @@ void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps) {
     Act col = ex.alloc_act(op.N, op.Hout, op.Wout, 9 * C);
     const void* src = op.src[0].p;
     ex.run([&] { return im2col_s2(src, col.p, op.N, op.Hin, op.Win, C, st); });
+    g.src[0].p = col.p;
+    ex.run([&] { return conv_tc(g, st); });
+    ex.release(col);
+  } else if (route == R_COL) {
+    Act col = ex.alloc_act(op.N, op.Hin, op.Win, 64);
+    const float* s0 = static_cast<const float*>(op.src[0].p);
+    const float* s1 = static_cast<const float*>(op.src[1].p);
+    ex.run([&] { return im2col_small(s0, op.src[0].C, s1, op.src[1].C, col.p, op.N, op.Hin, op.Win, st); });
     g.src[0].p = col.p;
     ex.run([&] { return conv_tc(g, st); });
     ex.release(col);

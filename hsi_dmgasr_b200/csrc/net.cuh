@@ -46,6 +46,7 @@ struct ConvW {
   int Cin = 0, Cout = 0, ks = 3;
   float* w_f32 = nullptr;  // [k*k*Cin][Cout]
   bf16* w_bf16 = nullptr;  // [rows >= Cout][k*k*Cin], zero padded rows
+  bf16* w_col = nullptr;   // [rows >= Cout][64]: the same weights for the im2col route of tiny-Cin 3x3 convs (9*Cin <= 64)
   int64_t packed_bytes = 0;
   const float* bias_override = nullptr;  // used instead of the parameter bias when set (fused weights)
 };

@@ -32,6 +32,34 @@ __device__ __forceinline__ float swish_act<bf16>(float y) {
   return y * fmaf(0.5f, t, 0.5f);
 }
 
+// 8 consecutive activations kept in their storage format while in flight (4 registers for bf16, 8 for fp32)
+template <typename AT>
+struct Raw8;
+template <>
+struct Raw8<bf16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x, v[2 * i + 1] = f.y;
+    }
+  }
+};
+template <>
+struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  }
+};
+
 template <typename AT>
 __device__ __forceinline__ const AT* src_ptr(const AT* x0, int C0, const AT* x1, int C1, int64_t pix, int c) {
   return c < C0 ? x0 + pix * C0 + c : x1 + pix * C1 + (c - C0);
@@ -122,6 +150,17 @@ gn_apply_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, in
   const int cpg = C / groups;
   const int cv = tid % CV, lane = tid / CV;
   const int c = cv * 8;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const int64_t img = (int64_t)n * HW;
+  int pix = p0 + lane;
+  // first batch of loads goes out before the (dependent) statistics / affine prologue
+  Raw8<AT> v[kUnroll];
+  bool have = pix + (kUnroll - 1) * lanes < p1;
+  if (have) {
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) v[u].load(src_ptr<AT>(x0, C0, x1, C1, img + pix + u * lanes, c));
+  }
   float A[8], B[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -130,22 +169,27 @@ gn_apply_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, in
     A[j] = rstd * __ldg(gamma + c + j);
     B[j] = __ldg(beta + c + j) - mean * A[j];
   }
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(HW, p0 + pix_per_block);
-  const int64_t img = (int64_t)n * HW;
-  int pix = p0 + lane;
-  for (; pix + (kUnroll - 1) * lanes < p1; pix += kUnroll * lanes) {
-    float v[kUnroll][8];
+  while (have) {
+    const int cur = pix;
+    pix += kUnroll * lanes;
+    Raw8<AT> w[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) load8(src_ptr<AT>(x0, C0, x1, C1, img + pix + u * lanes, c), v[u]);
+    for (int u = 0; u < kUnroll; ++u) w[u] = v[u];
+    have = pix + (kUnroll - 1) * lanes < p1;
+    if (have) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) v[u].load(src_ptr<AT>(x0, C0, x1, C1, img + pix + u * lanes, c));
+    }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
+      float f[8];
+      w[u].unpack(f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float y = fmaf(v[u][j], A[j], B[j]);
-        v[u][j] = swish ? swish_act<AT>(y) : y;
+        const float y = fmaf(f[j], A[j], B[j]);
+        f[j] = swish ? swish_act<AT>(y) : y;
       }
-      store8(out + (img + pix + u * lanes) * C + c, v[u]);
+      store8(out + (img + cur + u * lanes) * C + c, f);
     }
   }
   for (; pix < p1; pix += lanes) {
@@ -181,6 +225,17 @@ int gn_geometry(int C0, int C1, int N, int HW, GnGeo* g) {
   return HSIDM_OK;
 }
 
+// gn_apply geometry: about one resident wave (148 SMs x 4 blocks) of long-lived blocks, so the per-block prologue
+// (statistics + affine -> A, B) is amortised over hundreds of KB and there is no partial last wave.
+static void apply_geometry(const GnGeo& base, int N, int HW, GnGeo* g) {
+  *g = base;
+  int slabs = std::max(1, (148 * 4) / std::max(1, N));
+  const int min_pix = g->lanes * 2 * kUnroll;
+  slabs = (int)std::min<int64_t>(slabs, std::max<int64_t>(1, HW / min_pix));
+  g->pix_per_block = (int)ceil_div(HW, slabs);
+  g->slabs = (int)ceil_div(HW, g->pix_per_block);
+}
+
 int64_t gn_scratch_bytes(int C0, int C1, int N, int HW, int groups) {
   GnGeo g;
   if (gn_geometry(C0, C1, N, HW, &g) != HSIDM_OK) return 0;
@@ -207,44 +262,57 @@ int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int 
   return after_launch("gn_stats_kernel");
 }
 
-// grid = N, block = 256: thread -> (slot lane, channel); fixed-order folds only.
-__global__ void gn_finalize_kernel(const float* __restrict__ part0, int slots0, int C0, const float* __restrict__ part1,
-                                   int slots1, int C1, int groups, double cnt, float eps, float* __restrict__ stats) {
-  extern __shared__ float fsm[];   // [lanes][2][C] then [2][C]
+// grid = N; thread -> (slot lane, channel pair), float4 loads = (sum, sumsq) of two channels; fixed-order folds only.
+__global__ void __launch_bounds__(1024)
+gn_finalize_kernel(const float* __restrict__ part0, int slots0, int C0, const float* __restrict__ part1, int slots1, int C1,
+                   int groups, int lanes, double cnt, float eps, float* __restrict__ stats) {
+  extern __shared__ float4 fsm4[];   // [lanes][C/2], then reused as float[2][C]
   const int C = C0 + C1, n = blockIdx.x, tid = threadIdx.x;
-  const int lanes = blockDim.x / 64;                     // channels are walked 64 at a time
-  const int cl = tid & 63, lane = tid >> 6;
-  for (int cb = 0; cb < C; cb += 64) {
-    const int c = cb + cl;
+  const int pairs = C >> 1;
+  const int pr = tid % pairs, lane = tid / pairs;
+  if (lane < lanes) {
+    const int c = 2 * pr;
     const bool second = c >= C0;
     const float* base = second ? part1 + ((long long)n * slots1 * C1 + (c - C0)) * 2 : part0 + ((long long)n * slots0 * C0 + c) * 2;
-    const int slots = second ? slots1 : slots0, stride = (second ? C1 : C0) * 2;
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    const int slots = second ? slots1 : slots0;
+    const long long stride = (long long)(second ? C1 : C0) * 2;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
     int sl = lane;
-    for (; sl + lanes < slots; sl += 2 * lanes) {
-      const float2 u = *reinterpret_cast<const float2*>(base + (long long)sl * stride);
-      const float2 v = *reinterpret_cast<const float2*>(base + (long long)(sl + lanes) * stride);
-      a0 += u.x, b0 += u.y, a1 += v.x, b1 += v.y;
+    for (; sl + 3 * lanes < slots; sl += 4 * lanes) {
+      const float4 u0 = *reinterpret_cast<const float4*>(base + (long long)sl * stride);
+      const float4 u1 = *reinterpret_cast<const float4*>(base + (long long)(sl + lanes) * stride);
+      const float4 u2 = *reinterpret_cast<const float4*>(base + (long long)(sl + 2 * lanes) * stride);
+      const float4 u3 = *reinterpret_cast<const float4*>(base + (long long)(sl + 3 * lanes) * stride);
+      a0.x += u0.x, a0.y += u0.y, a0.z += u0.z, a0.w += u0.w;
+      a1.x += u1.x, a1.y += u1.y, a1.z += u1.z, a1.w += u1.w;
+      a2.x += u2.x, a2.y += u2.y, a2.z += u2.z, a2.w += u2.w;
+      a3.x += u3.x, a3.y += u3.y, a3.z += u3.z, a3.w += u3.w;
     }
-    if (sl < slots) {
-      const float2 u = *reinterpret_cast<const float2*>(base + (long long)sl * stride);
-      a0 += u.x, b0 += u.y;
+    for (; sl < slots; sl += lanes) {
+      const float4 u0 = *reinterpret_cast<const float4*>(base + (long long)sl * stride);
+      a0.x += u0.x, a0.y += u0.y, a0.z += u0.z, a0.w += u0.w;
     }
-    fsm[(lane * 2 + 0) * C + c] = a0 + a1;
-    fsm[(lane * 2 + 1) * C + c] = b0 + b1;
+    fsm4[lane * pairs + pr] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                                          (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
   }
   __syncthreads();
-  for (int i = tid; i < 2 * C; i += blockDim.x) {
-    const int which = i / C, c = i - which * C;
-    float acc = 0.f;
-    for (int l = 0; l < lanes; ++l) acc += fsm[(l * 2 + which) * C + c];
-    fsm[which * C + c] = acc;   // lane 0's own slot: read above by this thread only, no other thread touches it
+  float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid < pairs)
+    for (int l = 0; l < lanes; ++l) {
+      const float4 u = fsm4[l * pairs + tid];
+      tot.x += u.x, tot.y += u.y, tot.z += u.z, tot.w += u.w;
+    }
+  __syncthreads();
+  float* fs = reinterpret_cast<float*>(fsm4);   // [2][C]: sums then sums of squares
+  if (tid < pairs) {
+    fs[2 * tid] = tot.x, fs[2 * tid + 1] = tot.z;
+    fs[C + 2 * tid] = tot.y, fs[C + 2 * tid + 1] = tot.w;
   }
   __syncthreads();
   const int cpg = C / groups;
   for (int g = tid; g < groups; g += blockDim.x) {
     double a = 0.0, b = 0.0;
-    for (int j = 0; j < cpg; ++j) a += (double)fsm[g * cpg + j], b += (double)fsm[C + g * cpg + j];
+    for (int j = 0; j < cpg; ++j) a += (double)fs[g * cpg + j], b += (double)fs[C + g * cpg + j];
     const double mean = a / cnt;
     double var = b / cnt - mean * mean;
     var = var < 0.0 ? 0.0 : var;
@@ -256,26 +324,27 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part0, int slots0, 
 int gn_finalize(const float* part0, int slots0, int C0, const float* part1, int slots1, int C1, int N, int HW, int groups,
                 float eps, float* stats, cudaStream_t stream) {
   const int C = C0 + C1;
-  if (C0 % 64 || C1 % 64 || C % groups || C > 4096)
+  if (C0 % 64 || C1 % 64 || C % groups || C > 2048)
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "gn_finalize: channel counts %d+%d must be multiples of 64 and of the group count", C0, C1);
-  // as many slot lanes as 48 KB of shared memory allows (16 for C = 64 ... 2 for C = 1536)
-  int lanes = 16;
-  while (lanes > 1 && sizeof(float) * 2 * C * lanes > 48 * 1024) lanes >>= 1;
-  const int threads = 64 * lanes;
-  const size_t smem = sizeof(float) * 2 * C * lanes;
-  if (smem > 48 * 1024) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "gn_finalize: %d channels need too much shared memory", C);
+  const int pairs = C / 2;
+  const int lanes = std::max(1, std::min(32, 1024 / pairs));
+  const int threads = (int)round_up(lanes * pairs, 32);
+  const size_t smem = std::max<size_t>(sizeof(float4) * lanes * pairs, sizeof(float) * 2 * C);
   ProfScope prof(PROF_GN_STATS, 8.0 * N * ((double)slots0 * C0 + (double)slots1 * C1), stream, "finalize");
-  gn_finalize_kernel<<<N, threads, smem, stream>>>(part0, slots0, C0, part1, slots1, C1, groups, (double)(C / groups) * HW, eps,
-                                                   stats);
+  gn_finalize_kernel<<<N, threads, smem, stream>>>(part0, slots0, C0, part1, slots1, C1, groups, lanes,
+                                                   (double)(C / groups) * HW, eps, stats);
   return after_launch("gn_finalize_kernel");
 }
 
 int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const float* stats,
              const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream) {
-  GnGeo g;
-  HSIDM_TRY(gn_geometry(C0, C1, N, HW, &g));
+  GnGeo g0, g;
+  HSIDM_TRY(gn_geometry(C0, C1, N, HW, &g0));
+  apply_geometry(g0, N, HW, &g);
   dim3 grid(g.slabs, N);
-  ProfScope prof(PROF_GN_APPLY, 2.0 * N * HW * (C0 + C1) * (prec == HSIDM_BF16 ? 2 : 4), stream);
+  char tag[64];
+  snprintf(tag, sizeof(tag), "apply c%d+%d hw%d n%d grid%dx%d", C0, C1, HW, N, g.slabs, N);
+  ProfScope prof(PROF_GN_APPLY, 2.0 * N * HW * (C0 + C1) * (prec == HSIDM_BF16 ? 2 : 4), stream, tag);
   if (prec == HSIDM_BF16)
     gn_apply_kernel<bf16><<<grid, g.threads, 0, stream>>>((const bf16*)x0, C0, (const bf16*)x1, C1, HW, groups, g.CV,
                                                            g.lanes, g.pix_per_block, stats, gamma, beta, swish, (bf16*)out);
