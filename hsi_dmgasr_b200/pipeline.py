@@ -93,3 +93,58 @@ def gather_variable(mine: torch.Tensor, rank: int, world: int, dist) -> Optional
     if rank != 0:
         return None
     return torch.cat(objs, dim=0)
+
+
+# ---- overlapping-tile scene driver (BASELINE config 3) ------------------------------------------------
+# The reference only crops non-overlapping 128x128 blocks offline (GAE/crop.py:12-36, HStest.py:33-45); full-scene SR with
+# overlapping tiles and a feathered blend is the caller-side step the multi-GPU throughput config needs.
+def tile_starts(size: int, tile: int, overlap: int) -> List[int]:
+    """Tile origins along one axis: stride tile-overlap, last tile pulled back flush with the edge."""
+    if size < tile:
+        raise ValueError(f"scene side {size} is smaller than the tile {tile}")
+    stride = tile - overlap
+    starts = list(range(0, size - tile + 1, stride))
+    if starts[-1] != size - tile:
+        starts.append(size - tile)
+    return starts
+
+
+def tile_scene(scene: torch.Tensor, tile: int = 128, overlap: int = 16) -> Tuple[torch.Tensor, List[Tuple[int, int]]]:
+    """scene [C,H,W] -> (tiles [T,C,tile,tile], [(y0,x0)...]) in row-major tile order."""
+    _, h, w = scene.shape
+    pos = [(y, x) for y in tile_starts(h, tile, overlap) for x in tile_starts(w, tile, overlap)]
+    tiles = torch.stack([scene[:, y:y + tile, x:x + tile] for y, x in pos], dim=0)
+    return tiles, pos
+
+
+def feather_window(tile: int, overlap: int, device=None) -> torch.Tensor:
+    """Separable weight [tile,tile]: linear ramp over `overlap` pixels at every border, 1 inside (never zero)."""
+    ramp = torch.ones(tile, device=device)
+    if overlap > 0:
+        edge = (torch.arange(overlap, device=device, dtype=torch.float32) + 1.0) / (overlap + 1.0)
+        ramp[:overlap] = edge
+        ramp[tile - overlap:] = edge.flip(0)
+    return ramp[:, None] * ramp[None, :]
+
+
+def blend_tiles(tiles: torch.Tensor, pos: List[Tuple[int, int]], height: int, width: int, overlap: int = 16) -> torch.Tensor:
+    """Weighted overlap-add of [T,C,t,t] tiles back into a [C,H,W] scene (weights normalised per pixel)."""
+    t = tiles.shape[-1]
+    win = feather_window(t, overlap, tiles.device)
+    acc = torch.zeros((tiles.shape[1], height, width), device=tiles.device, dtype=torch.float32)
+    wsum = torch.zeros((height, width), device=tiles.device, dtype=torch.float32)
+    for k, (y, x) in enumerate(pos):
+        acc[:, y:y + t, x:x + t] += tiles[k].float() * win
+        wsum[y:y + t, x:x + t] += win
+    return acc / wsum
+
+
+def super_resolve_scene(pipeline: SRPipeline, sr_scene: torch.Tensor, device: torch.device, tile: int = 128, overlap: int = 16,
+                        batch: int = 8, rank: int = 0, world: int = 1, **kw) -> Optional[torch.Tensor]:
+    """Full-scene SR: tile the bicubic-upsampled scene [C,H,W] (host), shard the tiles over `world` ranks, super-resolve
+    them in batches, gather on rank 0 and blend.  Returns the [C,H,W] result on rank 0 (None elsewhere)."""
+    tiles, pos = tile_scene(sr_scene, tile, overlap)
+    mine = run_sharded(pipeline, tiles.contiguous(), device, rank, world, batch, gather=world > 1, **kw)
+    if rank != 0:
+        return None
+    return blend_tiles(mine, pos, sr_scene.shape[1], sr_scene.shape[2], overlap)
