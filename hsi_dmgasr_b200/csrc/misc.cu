@@ -170,36 +170,46 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
   }
 }
 
-// one thread per output pixel: 64 bf16 = 128 B per row; sources are read plane by plane (coalesced along x)
-__global__ void im2col_small_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
-                                    bf16* __restrict__ out, int H, int W, int64_t total) {
-  const int Ct = C0 + C1;
+// one thread per output pixel: 64 bf16 = 128 B per row; the 3x3 neighbourhood of every source plane is read with
+// coalesced loads (x is the fastest index across threads) and three row pointers per plane.
+template <int CT>
+__global__ void __launch_bounds__(128)
+im2col_small_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, bf16* __restrict__ out,
+                    int H, int W, int64_t total) {
+  const int64_t plane = (int64_t)H * W;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % W);
     const int y = (int)((i / W) % H);
-    const int64_t n = i / ((int64_t)W * H);
-    uint32_t packed[32];
+    const int64_t n = i / plane;
+    const bool xl = x > 0, xr = x + 1 < W, yt = y > 0, yb = y + 1 < H;
+    float nb[9][CT];   // [tap][channel]
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) {
-      float f[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int k = 2 * k2 + h;
-        float v = 0.f;
-        if (k < 9 * Ct) {
-          const int tap = k / Ct, c = k - tap * Ct;
-          const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
-          if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-            v = c < C0 ? __ldg(x0 + ((n * C0 + c) * H + iy) * (int64_t)W + ix) : __ldg(x1 + ((n * C1 + (c - C0)) * H + iy) * (int64_t)W + ix);
-        }
-        f[h] = v;
-      }
-      __nv_bfloat162 b = __floats2bfloat162_rn(f[0], f[1]);
-      packed[k2] = *reinterpret_cast<uint32_t*>(&b);
+    for (int c = 0; c < CT; ++c) {
+      const float* p = (c < C0 ? x0 + (n * C0 + c) * plane : x1 + (n * C1 + (c - C0)) * plane) + (int64_t)y * W + x;
+      nb[0][c] = (yt && xl) ? __ldg(p - W - 1) : 0.f;
+      nb[1][c] = yt ? __ldg(p - W) : 0.f;
+      nb[2][c] = (yt && xr) ? __ldg(p - W + 1) : 0.f;
+      nb[3][c] = xl ? __ldg(p - 1) : 0.f;
+      nb[4][c] = __ldg(p);
+      nb[5][c] = xr ? __ldg(p + 1) : 0.f;
+      nb[6][c] = (yb && xl) ? __ldg(p + W - 1) : 0.f;
+      nb[7][c] = yb ? __ldg(p + W) : 0.f;
+      nb[8][c] = (yb && xr) ? __ldg(p + W + 1) : 0.f;
     }
+    const float* flat = &nb[0][0];   // k = tap*CT + c, exactly the packed weight order
     uint4* o = reinterpret_cast<uint4*>(out + i * 64);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) o[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+    for (int q = 0; q < 8; ++q) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = q * 8 + 2 * j;
+        const float a = k < 9 * CT ? flat[k] : 0.f, b = k + 1 < 9 * CT ? flat[k + 1] : 0.f;
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      o[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
   }
 }
 
@@ -336,7 +346,7 @@ __global__ void overlap_average_kernel(const AT* __restrict__ dec, int G, int64_
 }
 
 inline int grid_for(int64_t work, int threads) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, threads), 148 * 16));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, threads), 148 * 32));
 }
 
 }  // namespace
@@ -372,6 +382,7 @@ int noise_embed(const float* level, int level_stride, int n, int dim, const floa
 int upsample2x(const void* x, void* out, int N, int H, int W, int C, int prec, cudaStream_t stream) {
   if (C % 8) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "upsample2x: C=%d not a multiple of 8", C);
   const int64_t total = (int64_t)N * 4 * H * W * (C / 8);
+  ProfScope prof(PROF_OTHER, (double)total * 8 * (prec == HSIDM_BF16 ? 2 : 4) * 1.25, stream, "upsample2x");
   if (prec == HSIDM_BF16)
     upsample2x_kernel<bf16><<<grid_for(total, 256), 256, 0, stream>>>((const bf16*)x, (bf16*)out, H, W, C / 8, total);
   else
@@ -383,13 +394,24 @@ int im2col_small(const float* x0, int C0, const float* x1, int C1, void* out, in
   if (9 * (C0 + C1) > 64) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "im2col_small: 9*(%d+%d) > 64", C0, C1);
   const int64_t total = (int64_t)N * H * W;
   ProfScope prof(PROF_OTHER, (double)total * (128 + 4.0 * (C0 + C1)), stream, "im2col_small");
-  im2col_small_kernel<<<grid_for(total, 128), 128, 0, stream>>>(x0, C0, x1, C1, static_cast<bf16*>(out), H, W, total);
+  bf16* o = static_cast<bf16*>(out);
+  const int grid = grid_for(total, 128);
+  switch (C0 + C1) {
+    case 1: im2col_small_kernel<1><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
+    case 2: im2col_small_kernel<2><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
+    case 3: im2col_small_kernel<3><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
+    case 4: im2col_small_kernel<4><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
+    case 5: im2col_small_kernel<5><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
+    case 6: im2col_small_kernel<6><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
+    default: im2col_small_kernel<7><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
+  }
   return after_launch("im2col_small_kernel");
 }
 
 int im2col_s2(const void* x, void* out, int N, int H, int W, int C, cudaStream_t stream) {
   if (C % 8) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "im2col_s2: C=%d not a multiple of 8", C);
   const int64_t total = (int64_t)N * (H / 2) * (W / 2) * 9 * (C / 8);
+  ProfScope prof(PROF_OTHER, (double)total * 16 * 1.45, stream, "im2col_s2");
   im2col_s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const bf16*)x, (bf16*)out, H, W, C / 8, total);
   return after_launch("im2col_s2_kernel");
 }
