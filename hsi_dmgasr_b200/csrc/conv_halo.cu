@@ -40,6 +40,11 @@ struct HaloP {
   int m_tiles, n_tiles;
   int chunks0, chunks1;   // 64-channel chunks of source 0 / 1
   int rchunks0, rchunks1; // 64-channel chunks of the shortcut sources (centre tap only; K columns after the 3x3 part)
+  int ntaps, tw;          // taps per chunk and taps per tap-row: 9/3 (3x3) or 4/2 (sub-pixel upsampling form)
+  int dy0, dx0;           // halo offset of tap (0,0): 0,0 for 3x3; (py,px) for the sub-pixel form
+  int kb0;                // first 64-wide k-block of this launch's weight columns (parity * 4 * chunks)
+  int oscale, oy, ox;     // output pixel of source-tile pixel (i,j) = (oscale*i + oy, oscale*j + ox)
+  int slot_base;          // first statistics slot of this launch
   EpiP e;
   int* err;
 };
@@ -138,12 +143,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         for (int ch = 0; ch < chunks && ok; ++ch) {
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < p.ntaps; ++tap) {
             ok = mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.err, 5);
             if (!ok) break;
             const uint32_t bb = smem_u32(&b_full[bs]);
             mbar_expect_tx(bb, C::kBStage);
-            tma_load_2d(smem_u32(smem_b + bs * C::kBStage), &tmB, bb, (tap * chunks + ch) * kBK, nt * BN);
+            tma_load_2d(smem_u32(smem_b + bs * C::kBStage), &tmB, bb, (p.kb0 + tap * chunks + ch) * kBK, nt * BN);
             if (++bs == C::kBStages) bs = 0, bph ^= 1;
           }
         }
@@ -152,7 +157,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (!ok) break;
           const uint32_t bb = smem_u32(&b_full[bs]);
           mbar_expect_tx(bb, C::kBStage);
-          tma_load_2d(smem_u32(smem_b + bs * C::kBStage), &tmB, bb, (9 * chunks + rc) * kBK, nt * BN);
+          tma_load_2d(smem_u32(smem_b + bs * C::kBStage), &tmB, bb, (p.kb0 + p.ntaps * chunks + rc) * kBK, nt * BN);
           if (++bs == C::kBStages) bs = 0, bph ^= 1;
         }
       }
@@ -174,12 +179,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           ok = mbar_wait(smem_u32(&a_full[as]), aph, p.err, 3);
           if (!ok) break;
           const uint32_t a_base = smem_u32(smem + as * C::kAStage);
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < p.ntaps; ++tap) {
             ok = mbar_wait(smem_u32(&b_full[bs]), bph, p.err, 6);
             if (!ok) break;
             tc_fence_after();
             const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + bs * C::kBStage));
-            const int dy = tap / 3, dx = tap % 3;   // already offset by the +1 halo
+            const int dy = p.dy0 + tap / p.tw, dx = p.dx0 + tap % p.tw;   // halo coordinates (already offset by +1)
 #pragma unroll
             for (int s = 0; s < MT; ++s) {
               const uint32_t a_addr = a_base + (uint32_t)((dy * C::kPW + 8 * s + dx) * 128);
@@ -248,14 +253,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int c_first = by_chunk ? half : 0, c_step = by_chunk ? 2 : 1;
         const int s_first = by_chunk ? 0 : half, s_step = by_chunk ? 1 : 2;
         // flat pixel index of this warp's first accumulator row in sub-tile 0: 4 image rows per lane quarter
-        const long long m_q = ((long long)n * p.e.H + ty0 + quarter * 4) * p.e.W + tx0;
+        const long long m_q = ((long long)n * p.e.H + p.oscale * (ty0 + quarter * 4) + p.oy) * p.e.W + p.oscale * tx0 + p.ox;
+        const long long xstep = (long long)p.oscale * p.e.Cout, pitch = (long long)p.oscale * p.e.W * p.e.Cout;
 #pragma unroll 1
         for (int ci = c_first; ci < nC; ci += c_step) {
           float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
           for (int s = s_first; s < MT; s += s_step)
-            epilogue_halo64(p.e, cb, cb2, taddr + s * BN + ci * 64, lane, nt * BN + ci * 64, stage, m_q + 8 * s, st);
-          if (p.e.stats) stats_store(p.e, n, r * (by_chunk ? 4 : 8) + quarter + (by_chunk ? 0 : 4 * half), nt * BN + ci * 64, lane, st);
+            epilogue_halo64(p.e, cb, cb2, taddr + s * BN + ci * 64, lane, nt * BN + ci * 64, stage, m_q + 8 * s * p.oscale, xstep,
+                            pitch, st);
+          if (p.e.stats)
+            stats_store(p.e, n, p.slot_base + r * (by_chunk ? 4 : 8) + quarter + (by_chunk ? 0 : 4 * half), nt * BN + ci * 64, lane, st);
         }
       } else {
 #pragma unroll 1
@@ -313,6 +321,13 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   p.rchunks1 = op.rsrc[1].C / kBK;
   fill_epilogue(&p.e, op);
   p.err = host().err_flag;
+  p.ntaps = 9, p.tw = 3, p.dy0 = p.dx0 = 0, p.kb0 = 0, p.oscale = 1, p.oy = p.ox = 0, p.slot_base = 0;
+  if (op.up_parity >= 0) {
+    const int py = op.up_parity >> 1, px = op.up_parity & 1;
+    p.ntaps = 4, p.tw = 2, p.dy0 = py, p.dx0 = px, p.kb0 = op.up_parity * 4 * (p.chunks0 + p.chunks1);
+    p.oscale = 2, p.oy = py, p.ox = px;
+    p.slot_base = op.up_parity * (p.tiles_x * p.tiles_y * (BN / 64 >= 2 ? 4 : 8));
+  }
   CUtensorMap tmA0, tmA1, tmB;
   HSIDM_TRY(encode_act_map(&tmA0, op.src[0].p, op.N, op.Hin, op.Win, op.src[0].C, C::kPW, kHaloRows, 1));
   if (p.chunks1)
@@ -326,9 +341,12 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, BN));
   const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
   char tag[96];
-  snprintf(tag, sizeof(tag), "halo MT%d BN%d cin%d+%d cout%d %dx%d n%d%s%s%s", MT, BN, op.src[0].C, op.src[1].C, op.Cout, op.Hin, op.Win, op.N,
-           op.resid ? " +res" : "", op.nbias ? " +nb" : "", op.stats_out ? " +st" : "");
-  ProfScope prof(PROF_CONV_TC, 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * K, stream, tag);
+  snprintf(tag, sizeof(tag), "halo MT%d BN%d cin%d+%d cout%d %dx%d n%d%s%s%s%s", MT, BN, op.src[0].C, op.src[1].C, op.Cout, op.Hin, op.Win, op.N,
+           op.resid ? " +res" : "", op.nbias ? " +nb" : "", op.stats_out ? " +st" : "", op.up_parity >= 0 ? " up2x" : "");
+  // algorithmic FLOPs: for the sub-pixel form, the share of the reference's 3x3 conv over the upsampled tensor
+  const double flops = op.up_parity >= 0 ? 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * 9 * (op.src[0].C + op.src[1].C)
+                                         : 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * K;
+  ProfScope prof(PROF_CONV_TC, flops, stream, tag);
   conv_halo_kernel<MT, BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmR0, tmR1, tmB, p);
   return after_launch("conv_halo_kernel");
 }
@@ -347,7 +365,7 @@ int conv_halo_stats_slots(const ConvOp& op) {
   pick_shape(op, &MT, &BN);
   if (MT == 0 || BN % 64 || op.out_layout != L_NHWC) return 0;
   const int tpi = (op.Win / (8 * MT)) * (op.Hin / kRows);
-  return tpi * (BN / 64 >= 2 ? 4 : 8);
+  return tpi * (BN / 64 >= 2 ? 4 : 8) * (op.up_parity >= 0 ? 4 : 1);
 }
 
 // Assumes conv_tc_supported(op) already holds (bf16 NHWC sources with 64-multiple channels, Cout fits an N tile).
@@ -357,6 +375,7 @@ bool conv_halo_supported(const ConvOp& op) {
   if (MT == 0) return false;
   for (int i = 0; i < 2; ++i)
     if (op.rsrc[i].C && (op.rsrc[i].C % kBK || op.rsrc[i].layout != L_NHWC)) return false;
+  if (op.up_parity >= 0 && (BN % 64 || op.rsrc[0].C || op.resid)) return false;
   // the packed weight rows are padded to pick_bn(Cout); the halo kernel's BN must divide that padding
   return tc::pick_bn(op.Cout) % BN == 0;
 }

@@ -378,7 +378,11 @@ bool conv_tc_supported(const ConvOp& op, int prec) {
   if (op.stride != 1 || op.up || (op.ksize != 1 && op.ksize != 3)) return false;
   if (op.src[0].layout != L_NHWC || op.src[0].C % kBK) return false;
   if (op.src[1].C && (op.src[1].layout != L_NHWC || op.src[1].C % kBK)) return false;
-  if (op.Hout != op.Hin || op.Wout != op.Win) return false;
+  if (op.up_parity >= 0) {
+    if (op.up_parity > 3 || op.ksize != 3 || op.Hout != 2 * op.Hin || op.Wout != 2 * op.Win) return false;
+  } else if (op.Hout != op.Hin || op.Wout != op.Win) {
+    return false;
+  }
   if (pick_bn(op.Cout) == 0) return false;
   if (op.out_layout == L_NHWC && op.Cout % 16) return false;
   if (op.out_layout != L_NHWC && op.resid) return false;
@@ -392,8 +396,8 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: op (Cin %d+%d, Cout %d, k%d s%d, %dx%d) does not fit the tensor-core kernel",
                op.src[0].C, op.src[1].C, op.Cout, op.ksize, op.stride, op.Hin, op.Win);
   if (!host().no_halo && conv_halo_supported(op)) return conv_halo(op, stream);
-  if (op.rsrc[0].C || op.rsrc[1].C)
-    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: fused shortcut sources need the halo kernel, which does not take this shape");
+  if (op.rsrc[0].C || op.rsrc[1].C || op.up_parity >= 0)
+    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: fused shortcut sources / sub-pixel upsampling need the halo kernel, which does not take this shape");
   TcP p;
   tile_geometry(op.Hin, op.Win, &p.bw, &p.bh, &p.bn);
   const int BN = pick_bn(op.Cout);

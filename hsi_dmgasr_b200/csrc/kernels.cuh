@@ -25,6 +25,10 @@ struct ConvOp {
   ConvSrc rsrc[2];
   int N = 0, Hin = 0, Win = 0;  // source spatial size
   int up = 0;                   // 1: source is nearest-2x upsampled on the fly (unet.py:58-65)
+  // >= 0: sub-pixel form of up + 3x3 conv (halo tensor-core kernel): parity p = 2*py + px computes the output pixels
+  // (2i+py, 2j+px) as a 2x2-tap conv over the LOW-RES source with pre-summed weights (w_bf16 = [Cout][4 parities][4 taps][C]);
+  // Hin/Win are the source size, Hout/Wout twice that.  2.25x fewer FLOPs and no upsampled tensor.
+  int up_parity = -1;
   int ksize = 3, stride = 1;    // padding = ksize/2
   int Hout = 0, Wout = 0, Cout = 0;
   const float* w_f32 = nullptr;  // [K][Cout], k = tap*(C0+C1) + c
@@ -44,7 +48,10 @@ struct ConvOp {
   // conv_tc_stats_slots(op) (tensor-core kernels only)
   float* stats_out = nullptr;
   int stats_slots = 0;
-  int K() const { return ksize * ksize * (src[0].C + src[1].C) + rsrc[0].C + rsrc[1].C; }
+  int K() const {
+    if (up_parity >= 0) return 16 * (src[0].C + src[1].C);
+    return ksize * ksize * (src[0].C + src[1].C) + rsrc[0].C + rsrc[1].C;
+  }
 };
 
 // conv_simt.cu : CUDA-core implicit GEMM, fp32 accumulate; handles every ConvOp.

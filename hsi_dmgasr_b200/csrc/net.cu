@@ -104,6 +104,26 @@ __global__ void pack_kernel(const float* __restrict__ w, int Cout, int Cin, int 
     if (o16) o16[(int64_t)co * K + tap * Cin + ci] = __float2bfloat16_rn(v);
   }
 }
+// Sub-pixel form of (nearest-2x upsample -> 3x3 conv, unet.py:58-65): output pixel (2i+py, 2j+px) only ever sees a 2x2
+// block of source pixels, so the 3x3 taps that land on the same source pixel are summed (in fp32) once, here.
+// o[co][((py*2+px)*4 + a*2+b)*Cin + ci] = sum_{dy in D(py,a)} sum_{dx in D(px,b)} w[co][ci][dy][dx],
+// D(0,0)={0}, D(0,1)={1,2}, D(1,0)={0,1}, D(1,1)={2}.
+__global__ void pack_up_kernel(const float* __restrict__ w, int Cout, int Cin, bf16* __restrict__ o) {
+  const int64_t total = (int64_t)Cout * 16 * Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int t = (int)((i / Cin) % 16);
+    const int co = (int)(i / ((int64_t)16 * Cin));
+    const int py = t >> 3, px = (t >> 2) & 1, a = (t >> 1) & 1, b = t & 1;
+    const int y0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), y1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+    const int x0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), x1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+    float acc = 0.f;
+    for (int dy = y0; dy <= y1; ++dy)
+      for (int dx = x0; dx <= x1; ++dx) acc += w[((int64_t)co * Cin + ci) * 9 + dy * 3 + dx];
+    o[i] = __float2bfloat16_rn(acc);
+  }
+}
+
 // w[co][ci][tap] -> col[co*64 + tap*Cin + ci], zero padded to 64 columns
 __global__ void pack_col_kernel(const float* __restrict__ w, int Cout, int Cin, bf16* __restrict__ o) {
   const int total = Cout * 64;
@@ -123,7 +143,20 @@ void free_conv(ConvW& c) {
   if (c.w_f32) cudaFree(c.w_f32);
   if (c.w_bf16) cudaFree(c.w_bf16);
   if (c.w_col) cudaFree(c.w_col);
-  c.w_f32 = nullptr, c.w_bf16 = nullptr, c.w_col = nullptr, c.packed_bytes = 0;
+  if (c.w_up) cudaFree(c.w_up);
+  c.w_f32 = nullptr, c.w_bf16 = nullptr, c.w_col = nullptr, c.w_up = nullptr, c.packed_bytes = 0;
+}
+
+int pack_conv_up(const ParamStore& ps, ConvW& c) {
+  const int bn = conv_tc_bn_rows(c.Cout);
+  if (c.ks != 3 || bn <= 0 || c.Cin % 64 || c.Cout % 64) return HSIDM_OK;
+  const int64_t rows = round_up(c.Cout, bn), K = 16LL * c.Cin;
+  if (c.w_up) cudaFree(c.w_up);
+  HSIDM_CUDA(cudaMalloc(&c.w_up, sizeof(bf16) * rows * K));
+  HSIDM_CUDA(cudaMemset(c.w_up, 0, sizeof(bf16) * rows * K));
+  c.packed_bytes += sizeof(bf16) * rows * K;
+  pack_up_kernel<<<(unsigned)std::min<int64_t>(ceil_div(c.Cout * K, 256), 4096), 256>>>(ps.dev(c.pw), c.Cout, c.Cin, c.w_up);
+  return after_launch("pack_up_kernel");
 }
 
 int pack_conv(const ParamStore& ps, ConvW& c, bool bf16_too) {
@@ -200,7 +233,7 @@ int pack_fused(const ParamStore& ps, const ConvW& c2, const ConvW* rc, FusedW& f
 
 // ---- dispatcher -----------------------------------------------------------------------------------------------
 namespace {
-enum Route { R_TC, R_DOWN, R_UP, R_COL, R_SIMT };
+enum Route { R_TC, R_DOWN, R_UP, R_UP_SUBPIX, R_COL, R_SIMT };
 
 // Decides how `op` runs and, for the lowered routes, fills `g` with the tensor-core op (its source pointer is patched
 // once the temporary exists).
@@ -226,7 +259,13 @@ Route plan_conv(const Exec& ex, const ConvOp& op, const ConvW& w, ConvOp* g) {
     g->Hin = op.Hout, g->Win = op.Wout, g->stride = 1, g->ksize = 1;
     if (conv_tc_supported(*g, prec)) return R_DOWN;
   } else if (nhwc1 && op.up && op.stride == 1) {
-    // Upsample (unet.py:58-65): materialise the nearest-2x tensor, then the ordinary 3x3 tensor-core conv.
+    // Upsample (unet.py:58-65), preferred: four sub-pixel 2x2-tap convs over the low-res source (no upsampled tensor)
+    if (w.w_up && op.ksize == 3) {
+      g->up = 0, g->up_parity = 0, g->w_bf16 = w.w_up;
+      if (conv_tc_supported(*g, prec) && conv_halo_ok(*g)) return R_UP_SUBPIX;
+      *g = op;
+    }
+    // else: materialise the nearest-2x tensor, then the ordinary 3x3 tensor-core conv.
     g->Hin = 2 * op.Hin, g->Win = 2 * op.Win, g->up = 0;
     if (conv_tc_supported(*g, prec)) return R_UP;
   }
@@ -259,6 +298,11 @@ void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps) {
     g.src[0].p = col.p;
     ex.run([&] { return conv_tc(g, st); });
     ex.release(col);
+  } else if (route == R_UP_SUBPIX) {
+    for (int parity = 0; parity < 4; ++parity) {
+      g.up_parity = parity;
+      ex.run([&] { return conv_tc(g, st); });
+    }
   } else if (route == R_COL) {
     Act col = ex.alloc_act(op.N, op.Hin, op.Win, 64);
     const float* s0 = static_cast<const float*>(op.src[0].p);

@@ -310,12 +310,14 @@ static __device__ __forceinline__ float2 bf16x2_to_f2(uint32_t u) {
 // K = 576 layers at 128x128.
 static __device__ __forceinline__ void epilogue_halo64(const EpiP& p, const float* __restrict__ cb,
                                                        const float* __restrict__ cb2, uint32_t taddr, int lane, int co0,
-                                                       uint32_t stage, long long m_warp, float4& st) {
+                                                       uint32_t stage, long long m_warp, long long xstep,
+                                                       long long pitch, float4& st) {
+  // xstep / pitch: elements between horizontally / vertically adjacent tile pixels in the output tensor
+  // (Cout and W*Cout for a plain conv; doubled for the sub-pixel upsampling form)
   const int sub = lane >> 3, chunk = lane & 7;
-  const long long pitch = (long long)p.W * p.Cout;   // elements between image rows
-  // element offset of (row 4i+sub, 16-byte chunk `chunk`) relative to pixel m_warp: (i>>1) image rows + 4*(i&1)+sub pixels
-  const long long lane_off = (long long)sub * p.Cout + co0 + chunk * 8;
-  const long long odd_off = 4LL * p.Cout;
+  // element offset of (row 4i+sub, 16-byte chunk `chunk`) relative to pixel m_warp: (i>>1) tile rows + 4*(i&1)+sub pixels
+  const long long lane_off = (long long)sub * xstep + co0 + chunk * 8;
+  const long long odd_off = 4LL * xstep;
   // phase 1: residual tile -> staging (coalesced)
   if (p.resid) {
     const bf16* base = p.resid + m_warp * p.Cout + lane_off;

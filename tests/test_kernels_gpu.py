@@ -152,6 +152,18 @@ def test_conv_tc_small_cout_nchw_out(conv_mode):
     assert tc_flag() == 0 and rel_l2(got, ref_conv(bf(x), None, bf(wt), b)) < 2e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 128, 16, 16, 128), (1, 64, 32, 64, 64), (3, 256, 16, 32, 256)])
+def test_upsample_conv_subpixel_form(shape, conv_mode):
+    """nearest-2x + 3x3 conv: halo mode runs the four sub-pixel 2x2 convs with pre-summed weights, per-tap mode the
+    materialised upsample; both must match torch (the weight sums are rounded to bf16 once, hence the looser bound)."""
+    n, c, h, w, co = shape
+    x = randn((n, c, h, w), 61)
+    wt, b = randn((co, c, 3, 3), 62, scale=(1.0 / (c * 9)) ** 0.5), randn((co,), 63)
+    got = conv2d(AUTO, "bf16", x, None, wt, b, ksize=3, up=1)
+    assert tc_flag() == 0 and got.shape == (n, co, 2 * h, 2 * w)
+    assert rel_l2(got, ref_conv(bf(x), None, bf(wt), b, up=1)) < 8e-3
+
+
 @pytest.mark.parametrize("kind", ["down", "up"])
 def test_conv_dispatch_lowerings(kind):
     x = randn((2, 128, 16, 16), 41)
