@@ -194,7 +194,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if constexpr (BN % 64 == 0) {
         if (p.e.out_layout == L_NHWC) {
           staged = true;
-          uint4* stage = reinterpret_cast<uint4*>(smem_epi + (warp - 2) * 4096);
+          const uint32_t stage = smem_u32(smem_epi + (warp - 2) * 4096);
+          // A tile's 128 accumulator rows are 128 CONSECUTIVE pixels of the NHWC tensor (x fastest, then y, then image;
+          // tiles span the full width whenever W < 128), so row R of this tile is flat pixel m_tile + R.
+          const long long m_tile = ((long long)n0 * p.e.H + y0) * p.e.W + x0;
+          const long long m_warp = m_tile + quarter * 32;
+          const long long m_total = (long long)p.e.N_img * p.e.H * p.e.W;
+          const int valid_rows = (int)max(0LL, min(32LL, m_total - m_warp));
           // statistics slot of this warp's 32 rows (all of one image, see pertap_stats_slots)
           int sn, sslot;
           if (p.bn > 1) {
@@ -203,6 +209,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           } else {
             sn = n0, sslot = (mt - n0 * tpi) * 4 + quarter;
           }
+          const float* cb = nbias ? nbias + (long long)sn * p.e.nbs : p.e.bias;
+          const float* cb2 = nbias ? p.e.bias : nullptr;
           constexpr int nC = BN / 64;
           // the two warps of a quarter alternate over the 64-channel chunks (a single chunk goes to the first warp)
 #pragma unroll 1
@@ -210,8 +218,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int co0 = nt * BN + ci * 64;
             if (co0 >= p.e.Cout) break;
             float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
-            epilogue_rows64(p.e, nbias, taddr + ci * 64, quarter, lane, co0, stage, pix, st);
-            if (p.e.stats) stats_store(p.e, sn, sslot, co0, lane, st);
+            if (p.bn <= 4) {
+              epilogue_halo64(p.e, cb, cb2, taddr + ci * 64, lane, co0, stage, m_warp, p.e.Cout, 8LL * p.e.Cout, st, valid_rows);
+              if (p.e.stats) stats_store(p.e, sn, sslot, co0, lane, st);
+            } else {
+              // images smaller than 32 pixels: a warp's rows span several images, so the noise bias is per row
+              epilogue_rows64(p.e, nbias, taddr + ci * 64, quarter, lane, co0, reinterpret_cast<uint4*>(smem_epi + (warp - 2) * 4096),
+                              pix, st);
+            }
           }
         }
       }

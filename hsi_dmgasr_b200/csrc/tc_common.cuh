@@ -311,7 +311,8 @@ static __device__ __forceinline__ float2 bf16x2_to_f2(uint32_t u) {
 static __device__ __forceinline__ void epilogue_halo64(const EpiP& p, const float* __restrict__ cb,
                                                        const float* __restrict__ cb2, uint32_t taddr, int lane, int co0,
                                                        uint32_t stage, long long m_warp, long long xstep,
-                                                       long long pitch, float4& st) {
+                                                       long long pitch, float4& st, int valid_rows = 32) {
+  // valid_rows: accumulator rows of this warp that map to real pixels (the per-tap kernel's last tile may be partial)
   // xstep / pitch: elements between horizontally / vertically adjacent tile pixels in the output tensor
   // (Cout and W*Cout for a plain conv; doubled for the sub-pixel upsampling form)
   const int sub = lane >> 3, chunk = lane & 7;
@@ -323,7 +324,9 @@ static __device__ __forceinline__ void epilogue_halo64(const EpiP& p, const floa
     const bf16* base = p.resid + m_warp * p.Cout + lane_off;
     uint4 v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(base + (i >> 1) * pitch + (i & 1) * odd_off));
+    for (int i = 0; i < 8; ++i)
+      v[i] = (4 * i + sub) < valid_rows ? __ldg(reinterpret_cast<const uint4*>(base + (i >> 1) * pitch + (i & 1) * odd_off))
+                                        : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r7 = (4 * (i & 1) + sub) & 7;   // (4i+sub) & 7
@@ -384,6 +387,7 @@ static __device__ __forceinline__ void epilogue_halo64(const EpiP& p, const floa
       __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[j].x, v[j].y);
+      if (lane >= valid_rows) o = make_uint4(0, 0, 0, 0);   // keep rows past the batch out of the statistics
       sts128(slot, o);
     }
     __syncwarp();
@@ -410,7 +414,7 @@ static __device__ __forceinline__ void epilogue_halo64(const EpiP& p, const floa
     for (int i = 0; i < 8; ++i) {
       const int r7 = (4 * (i & 1) + sub) & 7;
       const uint4 v = lds128(stage + (uint32_t)((4 * i + sub) * 128 + ((chunk ^ r7) << 4)));
-      *reinterpret_cast<uint4*>(base + (i >> 1) * pitch + (i & 1) * odd_off) = v;
+      if ((4 * i + sub) < valid_rows) *reinterpret_cast<uint4*>(base + (i >> 1) * pitch + (i & 1) * odd_off) = v;
     }
   }
   __syncwarp();

@@ -419,7 +419,12 @@ NoiseRef noise_slice(const NoiseRef& nz, int n0) {
 
 // Images per sub-batch at a level whose tensors have `per_image_bytes` bytes: consecutive layers of a level run
 // sub-batch by sub-batch so that producer -> consumer traffic stays in the 126 MB L2 instead of round-tripping HBM.
-int chunk_images(int N, int64_t per_image_bytes) {
+int chunk_images(int N, int64_t per_image_bytes, int hw = 1 << 30) {
+  static const int min_hw = [] {
+    const char* e = std::getenv("HSIDM_CHUNK_MIN_HW");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (hw < min_hw) return N;
   static const int64_t target = [] {
     const char* e = std::getenv("HSIDM_CHUNK_MB");
     return (int64_t)(e ? std::atoi(e) : 0) << 20;   // off by default: measured slower on B200 (see profiles/README.md)
@@ -462,7 +467,7 @@ void unet_forward_pass(hsidm_ctx* c, const float* x0, int c0, const float* x1, i
       }
       cin = outs.back().C;
     }
-    const int chunk = chunk_images(N, (int64_t)Hc * Wc * outs[0].C * (int64_t)es);
+    const int chunk = chunk_images(N, (int64_t)Hc * Wc * outs[0].C * (int64_t)es, Hc * Wc);
     for (int n0 = 0; n0 < N; n0 += chunk) {
       const int cnt = std::min(chunk, N - n0);
       const NoiseRef nzs = noise_slice(nz, n0);
@@ -517,7 +522,7 @@ void unet_forward_pass(hsidm_ctx* c, const float* x0, int c0, const float* x1, i
     const ResW& tail = c->ups[j - 1].rb;   // a stage always ends with a res block
     Act stage_out;
     if (!last_stage) stage_out = res_out(c, tail, N, Hs, Ws);
-    const int chunk = chunk_images(N, (int64_t)Hs * Ws * tail.cout * (int64_t)es);
+    const int chunk = chunk_images(N, (int64_t)Hs * Ws * tail.cout * (int64_t)es, Hs * Ws);
     for (int n0 = 0; n0 < N; n0 += chunk) {
       const int cnt = std::min(chunk, N - n0);
       const NoiseRef nzs = noise_slice(nz, n0);
