@@ -48,6 +48,16 @@ def peaks():
     return dict(hbm_gbs=6650.0, tf_sustained=1400.0, tf_burst=1590.0, src="fallback")
 
 
+def traffic_from_profiles():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture (profiles/r1_traffic.json); None if no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(path))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -276,7 +286,7 @@ def main() -> None:
         roof = {"kernel": "conv_tc_kernel<BN> (tcgen05/TMEM/TMA implicit-GEMM conv, all instantiations of one step)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sustained"], "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)",
-                "traffic": None, "launches_per_step": tc["launches_per_step"],
+                "traffic": traffic_from_profiles(), "launches_per_step": tc["launches_per_step"],
                 "algorithmic_flop_per_step": tc["work_per_step"], "kernel_ms_per_step": tc["ms_per_step"],
                 "step_breakdown_ms": {k: round(v["ms_per_step"], 3) for k, v in shares.items()},
                 "gn_apply_gbs": (shares["gn_apply"]["work_per_step"] / (shares["gn_apply"]["ms_per_step"] * 1e-3) / 1e9
