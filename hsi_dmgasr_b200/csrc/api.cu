@@ -103,8 +103,13 @@ int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const void* x1,
   return s;
 }
 
-int hsidm_debug_conv_mode(int no_halo, int base_offset_mode) {
-  conv_tc_set_mode(no_halo, base_offset_mode);
+int hsidm_debug_conv_mode(int no_halo, int variant) {
+  conv_tc_set_mode(no_halo, variant);
+  return HSIDM_OK;
+}
+
+int hsidm_debug_halo_timing(long long* device_counters) {
+  conv_halo_set_timing(device_counters);
   return HSIDM_OK;
 }
 

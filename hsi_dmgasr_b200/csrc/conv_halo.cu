@@ -2,7 +2,7 @@
 //
 // The per-tap kernel of conv_tc.cu re-fetches its A tile from L2 for each of the nine taps and streams one B tile
 // per 128 output pixels; at 1.4 PFLOP/s that is ~95 B/clk/SM of L2->SMEM traffic against the ~45 B/clk/SM the L2 can
-// deliver, which is what capped it at 20-47 % of tensor peak (profiles/r1_conv_tc_ncu.md).  This kernel raises the
+// deliver, which is what capped it at 20-47 % of tensor peak (profiles/r1_conv_pertap_ncu.md).  This kernel raises the
 // arithmetic intensity per byte fetched:
 //   * a CTA owns MT sub-tiles of 8 x 16 output pixels side by side (8*MT x 16 pixels) and BN output channels;
 //   * per 64-channel chunk ONE TMA box {64 ch, 8*MT+2, 18, 1} brings the tile plus its 1-pixel halo into smem (zero
@@ -40,14 +40,25 @@ struct HaloP {
   int m_tiles, n_tiles;
   int chunks0, chunks1;   // 64-channel chunks of source 0 / 1
   int rchunks0, rchunks1; // 64-channel chunks of the shortcut sources (centre tap only; K columns after the 3x3 part)
-  int ntaps, tw;          // taps per chunk and taps per tap-row: 9/3 (3x3) or 4/2 (sub-pixel upsampling form)
-  int dy0, dx0;           // halo offset of tap (0,0): 0,0 for 3x3; (py,px) for the sub-pixel form
+  int dy0, dx0;           // halo offset of tap (0,0): 0,0 for 3x3 (NT = 9); (py,px) for the 2x2 sub-pixel form (NT = 4)
   int kb0;                // first 64-wide k-block of this launch's weight columns (parity * 4 * chunks)
   int oscale, oy, ox;     // output pixel of source-tile pixel (i,j) = (oscale*i + oy, oscale*j + ox)
   int slot_base;          // first statistics slot of this launch
   EpiP e;
   int* err;
+  int variant;            // developer experiments (timing only, results invalid): 1 skip epilogue, 2 skip B loads, 4 skip A loads
+  long long* dbg;         // developer timing probe (null in production): per-CTA wait cycles of every role
 };
+
+// Wait that also accumulates the cycles it took when the timing probe is on.
+static __device__ __forceinline__ bool timed_wait(uint32_t bar, uint32_t parity, int* err, int code, const long long* dbg,
+                                                  long long& acc) {
+  if (!dbg) return mbar_wait(bar, parity, err, code);
+  const long long t0 = clock64();
+  const bool ok = mbar_wait(bar, parity, err, code);
+  acc += clock64() - t0;
+  return ok;
+}
 
 template <int MT, int BN>
 struct HCfg {
@@ -57,14 +68,19 @@ struct HCfg {
   static constexpr int kBStage = BN * 128;
   static constexpr int kStageBytes = kEpiWarps * 4096;                     // epilogue staging, 4 KB per epilogue warp
   static constexpr int kBStagesRaw = (232448 - 1536 - kStageBytes - kAStages * kAStage) / kBStage;
-  static constexpr int kBStages = kBStagesRaw > 10 ? 10 : kBStagesRaw;
+  // Weight tiles land in groups of kBGroup taps that share ONE full barrier: every barrier wait of the MMA issuer
+  // stalls the tensor pipe for ~160 clk (measured, scripts/mma_rate.cu), so it waits once per group, not per tap.
+  // Stages are still released (tcgen05.commit, free) and refilled one tap at a time.
+  static constexpr int kBGroup = kBStagesRaw >= 6 ? 3 : 2;
+  static constexpr int kBGroups = (kBStagesRaw > 9 ? 9 : kBStagesRaw) / kBGroup;
+  static constexpr int kBStages = kBGroups * kBGroup;
   static constexpr int kTmemCols = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;
   static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + kStageBytes + 1024 + 512;
-  static_assert(kBStages >= 3, "not enough shared memory for the B ring");
+  static_assert(kBGroups >= 2, "not enough shared memory for the B ring");
   static_assert(2 * MT * BN <= 512, "accumulators do not fit TMEM");
 };
 
-template <int MT, int BN>
+template <int MT, int BN, int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
@@ -96,7 +112,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (p.rchunks1) tma_prefetch_desc(&tmR1);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kAStages; ++s) mbar_init(smem_u32(&a_full[s]), 1), mbar_init(smem_u32(&a_empty[s]), 1);
-    for (int s = 0; s < C::kBStages; ++s) mbar_init(smem_u32(&b_full[s]), 1), mbar_init(smem_u32(&b_empty[s]), 1);
+    for (int s = 0; s < C::kBStages; ++s) mbar_init(smem_u32(&b_empty[s]), 1);
+    for (int g = 0; g < C::kBGroups; ++g) mbar_init(smem_u32(&b_full[g]), C::kBGroup);
     for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&tfull_bar[s]), 1), mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
     fence_barrier_init();
   }
@@ -112,15 +129,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       int as = 0;
       uint32_t aph = 0;
       bool ok = true;
+      long long w_ae = 0;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         const int mt = tile / p.n_tiles;
         const int n = mt / tpi, r = mt - n * tpi;
         const int y0 = (r / p.tiles_x) * kRows, x0 = (r % p.tiles_x) * (8 * MT);
         for (int ch = 0; ch < chunks + rchunks; ++ch) {
-          ok = mbar_wait(smem_u32(&a_empty[as]), aph ^ 1, p.err, 1);
+          ok = timed_wait(smem_u32(&a_empty[as]), aph ^ 1, p.err, 1, p.dbg, w_ae);
           if (!ok) break;
           const uint32_t fb = smem_u32(&a_full[as]);
           const uint32_t dst = smem_u32(smem + as * C::kAStage);
+          if (p.variant & 4) { mbar_arrive(fb); if (++as == kAStages) as = 0, aph ^= 1; continue; }
           mbar_expect_tx(fb, C::kABox);
           if (ch < p.chunks0)
             tma_load_4d(dst, &tmA0, fb, ch * kBK, x0 - 1, y0 - 1, n);
@@ -133,94 +152,122 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (++as == kAStages) as = 0, aph ^= 1;
         }
       }
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = w_ae;
     }
   } else if (warp == 1) {
     // =============================== TMA producer: weight tiles (B) ===============================
     if (lane == 0) {
-      int bs = 0;
+      int bs = 0, grp = 0, gcnt = 0;
       uint32_t bph = 0;
       bool ok = true;
+      long long w_be = 0;
+      // one weight tile: k-block kb of this tile's BN output channels, into the next stage of the ring
+      auto load_b = [&](int kb, int nt) {
+        ok = timed_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.err, 5, p.dbg, w_be);
+        if (!ok) return;
+        const uint32_t bb = smem_u32(&b_full[grp]);
+        if (p.variant & 2) {
+          mbar_arrive(bb);
+        } else {
+          mbar_expect_tx(bb, C::kBStage);
+          tma_load_2d(smem_u32(smem_b + bs * C::kBStage), &tmB, bb, kb * kBK, nt * BN);
+        }
+        if (++bs == C::kBStages) bs = 0, bph ^= 1;
+        if (++gcnt == C::kBGroup) gcnt = 0, grp = grp + 1 == C::kBGroups ? 0 : grp + 1;
+      };
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
-        for (int ch = 0; ch < chunks && ok; ++ch) {
-          for (int tap = 0; tap < p.ntaps; ++tap) {
-            ok = mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.err, 5);
-            if (!ok) break;
-            const uint32_t bb = smem_u32(&b_full[bs]);
-            mbar_expect_tx(bb, C::kBStage);
-            tma_load_2d(smem_u32(smem_b + bs * C::kBStage), &tmB, bb, (p.kb0 + tap * chunks + ch) * kBK, nt * BN);
-            if (++bs == C::kBStages) bs = 0, bph ^= 1;
-          }
-        }
-        for (int rc = 0; rc < rchunks && ok; ++rc) {   // shortcut columns follow the 9*chunks 3x3 columns
-          ok = mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.err, 5);
-          if (!ok) break;
-          const uint32_t bb = smem_u32(&b_full[bs]);
-          mbar_expect_tx(bb, C::kBStage);
-          tma_load_2d(smem_u32(smem_b + bs * C::kBStage), &tmB, bb, (p.kb0 + p.ntaps * chunks + rc) * kBK, nt * BN);
-          if (++bs == C::kBStages) bs = 0, bph ^= 1;
-        }
+        for (int ch = 0; ch < chunks && ok; ++ch)
+          for (int tap = 0; tap < NT && ok; ++tap) load_b(p.kb0 + tap * chunks + ch, nt);
+        for (int rc = 0; rc < rchunks && ok; ++rc) load_b(p.kb0 + NT * chunks + rc, nt);   // shortcut columns follow the 3x3 ones
       }
+      // the issuer waits for whole groups: complete the last, partly filled one
+      for (; ok && gcnt != 0 && gcnt < C::kBGroup; ++gcnt) mbar_arrive(smem_u32(&b_full[grp]));
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 1] = w_be;
     }
   } else if (warp == 2) {
     // =============================== MMA issuer ===============================
+    // The tensor pipe only stays busy while tcgen05.mma instructions arrive back to back: whatever else this thread
+    // does between two of them (a barrier wait, address arithmetic) shows up as idle pipe time.  Hence: taps unrolled
+    // with compile-time operand offsets, one weight-group wait per kBGroup taps, commits (free) per tap.
     if (lane == 0) {
+      constexpr int TW = NT == 9 ? 3 : 2;
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
       constexpr uint64_t desc_hi = (uint64_t)((C::kPW * 128) >> 4) << 32 | (1ull << 46) | (2ull << 61) | (1ull << 16);
-      int as = 0, bs = 0, acc = 0;
-      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      constexpr uint64_t bdesc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t tap0 = (uint32_t)((p.dy0 * C::kPW + p.dx0) * 128);   // halo offset of tap (0,0)
+      const uint32_t b_lo = smem_u32(smem_b) >> 4;
+      int as = 0, bs = 0, acc = 0, grp = 0, gcnt = 0;
+      uint32_t aph = 0, gph = 0, acc_phase = 0;
       bool ok = true;
+      long long w_te = 0, w_af = 0, w_bf = 0;
+      const long long t_start = p.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        ok = mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 2);
+        ok = timed_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 2, p.dbg, w_te);
         if (!ok) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (MT * BN);
         for (int ch = 0; ch < chunks && ok; ++ch) {
-          ok = mbar_wait(smem_u32(&a_full[as]), aph, p.err, 3);
+          ok = timed_wait(smem_u32(&a_full[as]), aph, p.err, 3, p.dbg, w_af);
           if (!ok) break;
-          const uint32_t a_base = smem_u32(smem + as * C::kAStage);
-          for (int tap = 0; tap < p.ntaps; ++tap) {
-            ok = mbar_wait(smem_u32(&b_full[bs]), bph, p.err, 6);
-            if (!ok) break;
-            tc_fence_after();
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + bs * C::kBStage));
-            const int dy = p.dy0 + tap / p.tw, dx = p.dx0 + tap % p.tw;   // halo coordinates (already offset by +1)
+          const uint64_t adesc0 = desc_hi | (uint64_t)((smem_u32(smem + as * C::kAStage) + tap0) >> 4);
+#pragma unroll
+          for (int tap = 0; tap < NT; ++tap) {
+            if (gcnt == 0) {
+              ok = timed_wait(smem_u32(&b_full[grp]), gph, p.err, 6, p.dbg, w_bf);
+              if (!ok) break;
+              tc_fence_after();
+            }
+            const uint64_t bdesc = bdesc_hi | (uint64_t)(b_lo + bs * (C::kBStage >> 4));
+            const int kTapOff = ((tap / TW) * C::kPW + tap % TW) * 128;   // halo coordinates of this tap (constant once unrolled)
 #pragma unroll
             for (int s = 0; s < MT; ++s) {
-              const uint32_t a_addr = a_base + (uint32_t)((dy * C::kPW + 8 * s + dx) * 128);
-              const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k)
-                umma_f16(d_tmem + s * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | tap | k) ? 1u : 0u);
+                umma_f16(d_tmem + s * BN, adesc0 + (uint64_t)((kTapOff + s * 1024) / 16 + 2 * k), bdesc + 2 * k, idesc,
+                         (tap | k) ? 1u : (ch ? 1u : 0u));
             }
             umma_commit(smem_u32(&b_empty[bs]));
-            if (++bs == C::kBStages) bs = 0, bph ^= 1;
+            if (++bs == C::kBStages) bs = 0;
+            if (++gcnt == C::kBGroup) {
+              gcnt = 0;
+              if (++grp == C::kBGroups) grp = 0, gph ^= 1;
+            }
           }
           umma_commit(smem_u32(&a_empty[as]));
           if (++as == kAStages) as = 0, aph ^= 1;
         }
         for (int rc = 0; rc < rchunks && ok; ++rc) {   // shortcut: centre tap of the un-normalised block input
-          ok = mbar_wait(smem_u32(&a_full[as]), aph, p.err, 3);
+          ok = timed_wait(smem_u32(&a_full[as]), aph, p.err, 3, p.dbg, w_af);
           if (!ok) break;
-          ok = mbar_wait(smem_u32(&b_full[bs]), bph, p.err, 6);
-          if (!ok) break;
+          if (gcnt == 0) {
+            ok = timed_wait(smem_u32(&b_full[grp]), gph, p.err, 6, p.dbg, w_bf);
+            if (!ok) break;
+          }
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + as * C::kAStage);
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + bs * C::kBStage));
+          const uint64_t adesc0 = desc_hi | (uint64_t)((smem_u32(smem + as * C::kAStage) + (1 * C::kPW + 1) * 128) >> 4);
+          const uint64_t bdesc = bdesc_hi | (uint64_t)(b_lo + bs * (C::kBStage >> 4));
 #pragma unroll
           for (int s = 0; s < MT; ++s) {
-            const uint32_t a_addr = a_base + (uint32_t)((1 * C::kPW + 8 * s + 1) * 128);
-            const uint64_t adesc = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) umma_f16(d_tmem + s * BN, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_f16(d_tmem + s * BN, adesc0 + (uint64_t)(s * 1024 / 16 + 2 * k), bdesc + 2 * k, idesc, 1u);
           }
           umma_commit(smem_u32(&b_empty[bs]));
-          if (++bs == C::kBStages) bs = 0, bph ^= 1;
+          if (++bs == C::kBStages) bs = 0;
+          if (++gcnt == C::kBGroup) {
+            gcnt = 0;
+            if (++grp == C::kBGroups) grp = 0, gph ^= 1;
+          }
           umma_commit(smem_u32(&a_empty[as]));
           if (++as == kAStages) as = 0, aph ^= 1;
         }
         umma_commit(smem_u32(&tfull_bar[acc]));
         if (++acc == 2) acc = 0, acc_phase ^= 1;
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 2] = w_te, p.dbg[blockIdx.x * 8 + 3] = w_af, p.dbg[blockIdx.x * 8 + 4] = w_bf;
+        p.dbg[blockIdx.x * 8 + 5] = clock64() - t_start;
       }
     }
   } else {
@@ -233,16 +280,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint32_t acc_phase = 0;
     const float* nbias = p.e.nbias ? p.e.nbias + (p.e.nb_t ? (long long)(*p.e.nb_t) * p.e.nb_ts : 0) : nullptr;
     bool ok = true;
+    long long w_tf = 0;
+    const long long t_start = p.dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
       const int n = mt / tpi, r = mt - n * tpi;
       const int y = (r / p.tiles_x) * kRows + (row >> 3);
       const int xb = (r % p.tiles_x) * (8 * MT) + (row & 7);
-      ok = mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 4);
+      ok = timed_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 4, p.dbg, w_tf);
       if (!ok) break;
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * (MT * BN) + ((uint32_t)(quarter * 32) << 16);
-      if constexpr (nC >= 1) {
+      if (p.variant & 1) {
+      } else if constexpr (nC >= 1) {
         const uint32_t stage = smem_u32(smem_stage + (warp - kFirstEpiWarp) * 4096);
         const int ty0 = (r / p.tiles_x) * kRows, tx0 = (r % p.tiles_x) * (8 * MT);
         // one pre-combined bias vector per image: the bias-folded noise embedding if present, else the conv bias
@@ -283,6 +333,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
       if (++acc == 2) acc = 0, acc_phase ^= 1;
     }
+    if (p.dbg && warp == kFirstEpiWarp && lane == 0) p.dbg[blockIdx.x * 8 + 6] = w_tf, p.dbg[blockIdx.x * 8 + 7] = clock64() - t_start;
   }
 
   tc_fence_before();
@@ -307,7 +358,7 @@ void pick_shape(const ConvOp& op, int* MT, int* BN) {
   }
 }
 
-template <int MT, int BN>
+template <int MT, int BN, int NT>
 int launch(const ConvOp& op, cudaStream_t stream) {
   using C = HCfg<MT, BN>;
   HaloP p;
@@ -321,10 +372,12 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   p.rchunks1 = op.rsrc[1].C / kBK;
   fill_epilogue(&p.e, op);
   p.err = host().err_flag;
-  p.ntaps = 9, p.tw = 3, p.dy0 = p.dx0 = 0, p.kb0 = 0, p.oscale = 1, p.oy = p.ox = 0, p.slot_base = 0;
+  p.dbg = host().halo_dbg;
+  p.variant = host().variant;
+  p.dy0 = p.dx0 = 0, p.kb0 = 0, p.oscale = 1, p.oy = p.ox = 0, p.slot_base = 0;
   if (op.up_parity >= 0) {
     const int py = op.up_parity >> 1, px = op.up_parity & 1;
-    p.ntaps = 4, p.tw = 2, p.dy0 = py, p.dx0 = px, p.kb0 = op.up_parity * 4 * (p.chunks0 + p.chunks1);
+    p.dy0 = py, p.dx0 = px, p.kb0 = op.up_parity * 4 * (p.chunks0 + p.chunks1);
     p.oscale = 2, p.oy = py, p.ox = px;
     p.slot_base = op.up_parity * (p.tiles_x * p.tiles_y * (BN / 64 >= 2 ? 4 : 8));
   }
@@ -347,18 +400,22 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   const double flops = op.up_parity >= 0 ? 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * 9 * (op.src[0].C + op.src[1].C)
                                          : 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * K;
   ProfScope prof(PROF_CONV_TC, flops, stream, tag);
-  conv_halo_kernel<MT, BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmR0, tmR1, tmB, p);
+  conv_halo_kernel<MT, BN, NT><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmR0, tmR1, tmB, p);
   return after_launch("conv_halo_kernel");
 }
 
 }  // namespace
 
 int conv_halo_init() {
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 128>::kSmemBytes));
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 16>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 128, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 128>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 128>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 16, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 16>::kSmemBytes));
   return HSIDM_OK;
 }
+
+void conv_halo_set_timing(long long* device_counters) { tc::host().halo_dbg = device_counters; }
 
 int conv_halo_stats_slots(const ConvOp& op) {
   int MT, BN;
@@ -383,9 +440,10 @@ bool conv_halo_supported(const ConvOp& op) {
 int conv_halo(const ConvOp& op, cudaStream_t stream) {
   int MT, BN;
   pick_shape(op, &MT, &BN);
-  if (MT == 2 && BN == 128) return launch<2, 128>(op, stream);
-  if (MT == 4 && BN == 64) return launch<4, 64>(op, stream);
-  if (MT == 4 && BN == 16) return launch<4, 16>(op, stream);
+  const bool sub = op.up_parity >= 0;
+  if (MT == 2 && BN == 128) return sub ? launch<2, 128, 4>(op, stream) : launch<2, 128, 9>(op, stream);
+  if (MT == 4 && BN == 64) return sub ? launch<4, 64, 4>(op, stream) : launch<4, 64, 9>(op, stream);
+  if (MT == 4 && BN == 16 && !sub) return launch<4, 16, 9>(op, stream);
   HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_halo: unsupported shape");
 }
 

@@ -380,9 +380,9 @@ int conv_tc_stats_slots(const ConvOp& op) {
   return tc::pertap_stats_slots(op);
 }
 
-void conv_tc_set_mode(int no_halo, int base_offset_mode) {
+void conv_tc_set_mode(int no_halo, int variant) {
   tc::host().no_halo = no_halo;
-  tc::host().base_offset_mode = base_offset_mode;
+  tc::host().variant = variant;
 }
 
 int conv_tc_bn_rows(int Cout) { return pick_bn(Cout); }

@@ -64,7 +64,8 @@ bool conv_halo_ok(const ConvOp& op);         // the halo kernel (and with it fus
 int conv_tc_stats_slots(const ConvOp& op);  // slots per image the kernel chosen for `op` fills (0 = no fused statistics)
 int conv_tc_init();               // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int conv_tc_bn_rows(int Cout);    // N-tile height; packed bf16 weights are padded to a multiple of it (0 = unsupported)
-void conv_tc_set_mode(int no_halo, int base_offset_mode);  // test knobs
+void conv_tc_set_mode(int no_halo, int variant);  // test knobs
+void conv_halo_set_timing(long long* device_counters);   // developer probe, see hsidm_debug_halo_timing
 int conv_tc_error_flag(int* v);   // barrier-timeout flag of the tensor-core kernel (synchronises; tests only)
 
 // Batched GEMM on CUDA cores: C[b] = alpha * A[b] (MxK, row-major lda) * op(B[b]); B is [N][K] (transB=1)

@@ -436,7 +436,8 @@ struct Host {
   int num_sms = 0;
   int* err_flag = nullptr;
   int no_halo = 0;           // test knob: 1 -> always use the per-tap kernel of conv_tc.cu
-  int base_offset_mode = 0;  // test knob for the halo kernel's A descriptors
+  int variant = 0;           // test knob: kernel-variant selector for A/B runs (0 = default routing)
+  long long* halo_dbg = nullptr;   // developer timing probe of the halo kernel (device buffer, 8 counters per CTA)
 };
 Host& host();
 // NHWC bf16 activation [N,H,W,C] as a 4-D tensor map with box {64, bw, bh, bn} and 128B swizzle (OOB reads are zero).

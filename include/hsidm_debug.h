@@ -25,8 +25,13 @@ HSIDM_API int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const
                           const float* gamma, const float* beta, float eps, int swish, void* out);
 
 /* Kernel-selection knobs for A/B tests: no_halo = 1 forces the per-tap tcgen05 kernel for every 3x3 conv;
- * base_offset_mode selects how the halo kernel fills the UMMA descriptor base-offset field (0 = zero). */
-HSIDM_API int hsidm_debug_conv_mode(int no_halo, int base_offset_mode);
+ * variant selects among alternative halo-kernel configurations (0 = the production routing). */
+HSIDM_API int hsidm_debug_conv_mode(int no_halo, int variant);
+
+/* Developer probe: when device_counters is non-null every halo-kernel launch writes 8 int64 cycle counters per CTA
+ * ([a_empty wait, b_empty wait, tmem_empty wait, a_full wait, b_full wait, MMA-issuer total, tmem_full wait,
+ * epilogue total]); null switches the probe off.  The buffer must hold 8 * (number of SMs) values. */
+HSIDM_API int hsidm_debug_halo_timing(long long* device_counters);
 
 /* Reads and clears the tensor-core kernel's barrier-timeout flag (0 = healthy). */
 HSIDM_API int hsidm_debug_tc_error_flag(int* value);
