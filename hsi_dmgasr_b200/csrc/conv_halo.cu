@@ -40,7 +40,8 @@ struct HaloP {
   int m_tiles, n_tiles;
   int chunks0, chunks1;   // 64-channel chunks of source 0 / 1
   int rchunks0, rchunks1; // 64-channel chunks of the shortcut sources (centre tap only; K columns after the 3x3 part)
-  int dy0, dx0;           // halo offset of tap (0,0): 0,0 for 3x3 (NT = 9); (py,px) for the 2x2 sub-pixel form (NT = 4)
+  int dy0, dx0;           // halo offset of tap (0,0): 0,0 for 3x3 (NT = 9); (py,px) for the 2x2 sub-pixel form (NT = 4);
+                          // 1,1 for a 1x1 conv (NT = 1, the centre tap)
   int kb0;                // first 64-wide k-block of this launch's weight columns (parity * 4 * chunks)
   int oscale, oy, ox;     // output pixel of source-tile pixel (i,j) = (oscale*i + oy, oscale*j + ox)
   int slot_base;          // first statistics slot of this launch
@@ -67,7 +68,7 @@ struct HCfg {
   static constexpr int kAStage = (kABox + 1023) / 1024 * 1024;             // keep every stage 1024-B aligned
   static constexpr int kBStage = BN * 128;
   static constexpr int kStageBytes = kEpiWarps * 4096;                     // epilogue staging, 4 KB per epilogue warp
-  static constexpr int kBStagesRaw = (232448 - 1536 - kStageBytes - kAStages * kAStage) / kBStage;
+  static constexpr int kBStagesRaw = (232448 - 1536 - kEpiWarps * 256 - kStageBytes - kAStages * kAStage) / kBStage;
   // Weight tiles land in groups of kBGroup taps that share ONE full barrier: every barrier wait of the MMA issuer
   // stalls the tensor pipe for ~160 clk (measured, scripts/mma_rate.cu), so it waits once per group, not per tap.
   // Stages are still released (tcgen05.commit, free) and refilled one tap at a time.
@@ -75,7 +76,8 @@ struct HCfg {
   static constexpr int kBGroups = (kBStagesRaw > 9 ? 9 : kBStagesRaw) / kBGroup;
   static constexpr int kBStages = kBGroups * kBGroup;
   static constexpr int kTmemCols = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;
-  static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + kStageBytes + 1024 + 512;
+  static constexpr int kBiasBytes = kEpiWarps * 256;                       // 64 bias floats per epilogue warp
+  static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + kStageBytes + kBiasBytes + 1024 + 512;
   static_assert(kBGroups >= 2, "not enough shared memory for the B ring");
   static_assert(2 * MT * BN <= 512, "accumulators do not fit TMEM");
 };
@@ -84,13 +86,14 @@ template <int MT, int BN, int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
-                 const __grid_constant__ CUtensorMap tmB, const HaloP p) {
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const HaloP p) {
   using C = HCfg<MT, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem + kAStages * C::kAStage;
   uint8_t* smem_stage = smem_b + C::kBStages * C::kBStage;
-  uint8_t* tail = smem_stage + C::kStageBytes;
+  uint8_t* smem_bias = smem_stage + C::kStageBytes;
+  uint8_t* tail = smem_bias + C::kBiasBytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* a_empty = a_full + kAStages;
   uint64_t* b_full = a_empty + kAStages;
@@ -111,6 +114,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (p.rchunks0) tma_prefetch_desc(&tmR0);
     if (p.rchunks1) tma_prefetch_desc(&tmR1);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
     for (int s = 0; s < kAStages; ++s) mbar_init(smem_u32(&a_full[s]), 1), mbar_init(smem_u32(&a_empty[s]), 1);
     for (int s = 0; s < C::kBStages; ++s) mbar_init(smem_u32(&b_empty[s]), 1);
     for (int g = 0; g < C::kBGroups; ++g) mbar_init(smem_u32(&b_full[g]), C::kBGroup);
@@ -287,6 +291,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int n = mt / tpi, r = mt - n * tpi;
       const int y = (r / p.tiles_x) * kRows + (row >> 3);
       const int xb = (r % p.tiles_x) * (8 * MT) + (row & 7);
+      // this warp's share of the tile: one 64-channel chunk `ci` (of BN/64) and sub-tiles s_first, s_first+s_step, ...
+      constexpr bool by_chunk = nC >= 2;
+      const int ci = by_chunk ? half : 0;
+      const int s_first = by_chunk ? 0 : half, s_step = by_chunk ? 1 : 2;
+      const int ty0 = (r / p.tiles_x) * kRows, tx0 = (r % p.tiles_x) * (8 * MT);
+      uint32_t bias_smem = 0;
+      if constexpr (nC >= 1) {
+        // park the tile's 64 bias values (conv bias and/or this image's noise embedding) in shared memory while the
+        // accumulators are still being produced
+        const float* cb = nbias ? nbias + (long long)n * p.e.nbs : p.e.bias;
+        if (cb && !(p.variant & 1)) {
+          bias_smem = smem_u32(smem_bias + (warp - kFirstEpiWarp) * 256);
+          if (lane < 16) {
+            float4 b = __ldg(reinterpret_cast<const float4*>(cb + nt * BN + ci * 64) + lane);
+            if (nbias && p.e.bias) {
+              const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.e.bias + nt * BN + ci * 64) + lane);
+              b.x += b2.x, b.y += b2.y, b.z += b2.z, b.w += b2.w;
+            }
+            sts128(bias_smem + lane * 16, make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
+          }
+          __syncwarp();
+        }
+      }
       ok = timed_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.err, 4, p.dbg, w_tf);
       if (!ok) break;
       tc_fence_after();
@@ -294,27 +321,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (p.variant & 1) {
       } else if constexpr (nC >= 1) {
         const uint32_t stage = smem_u32(smem_stage + (warp - kFirstEpiWarp) * 4096);
-        const int ty0 = (r / p.tiles_x) * kRows, tx0 = (r % p.tiles_x) * (8 * MT);
-        // one pre-combined bias vector per image: the bias-folded noise embedding if present, else the conv bias
-        const float* cb = nbias ? nbias + (long long)n * p.e.nbs : p.e.bias;
-        const float* cb2 = nbias ? p.e.bias : nullptr;
-        // split between the two warps of a quarter: by channel chunk when there are several, else by sub-tile
-        constexpr bool by_chunk = nC >= 2;
-        const int c_first = by_chunk ? half : 0, c_step = by_chunk ? 2 : 1;
-        const int s_first = by_chunk ? 0 : half, s_step = by_chunk ? 1 : 2;
-        // flat pixel index of this warp's first accumulator row in sub-tile 0: 4 image rows per lane quarter
-        const long long m_q = ((long long)n * p.e.H + p.oscale * (ty0 + quarter * 4) + p.oy) * p.e.W + p.oscale * tx0 + p.ox;
+        const int co0 = nt * BN + ci * 64;
+        // residual layers: this lane's element of the tile in the residual tensor (same lattice as the output)
         const long long xstep = (long long)p.oscale * p.e.Cout, pitch = (long long)p.oscale * p.e.W * p.e.Cout;
-#pragma unroll 1
-        for (int ci = c_first; ci < nC; ci += c_step) {
-          float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-          for (int s = s_first; s < MT; s += s_step)
-            epilogue_halo64(p.e, cb, cb2, taddr + s * BN + ci * 64, lane, nt * BN + ci * 64, stage, m_q + 8 * s * p.oscale, xstep,
-                            pitch, st);
-          if (p.e.stats)
-            stats_store(p.e, n, p.slot_base + r * (by_chunk ? 4 : 8) + quarter + (by_chunk ? 0 : 4 * half), nt * BN + ci * 64, lane, st);
+        const bf16* resid_lane = nullptr;
+        if (p.e.resid) {
+          const long long m_q = ((long long)n * p.e.H + p.oscale * (ty0 + quarter * 4) + p.oy) * p.e.W + p.oscale * tx0 + p.ox;
+          resid_lane = p.e.resid + m_q * p.e.Cout + (lane >> 3) * xstep + co0 + (lane & 7) * 8;
         }
+        float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int s = s_first; s < MT; s += s_step)
+          epilogue_tma64(p.e, &tmO, bias_smem, taddr + s * BN + ci * 64, lane, stage, co0, tx0 + 8 * s, ty0 + quarter * 4, n,
+                         resid_lane ? resid_lane + 8 * s * xstep : nullptr, pitch, 4 * xstep, st);
+        if (p.e.stats)
+          stats_store(p.e, n, p.slot_base + r * (by_chunk ? 4 : 8) + quarter + (by_chunk ? 0 : 4 * half), co0, lane, st);
       } else {
 #pragma unroll 1
         for (int s = half; s < MT; s += 2) {
@@ -333,6 +354,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
       if (++acc == 2) acc = 0, acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all();   // the staging tiles must outlive the stores reading them
     if (p.dbg && warp == kFirstEpiWarp && lane == 0) p.dbg[blockIdx.x * 8 + 6] = w_tf, p.dbg[blockIdx.x * 8 + 7] = clock64() - t_start;
   }
 
@@ -347,13 +369,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 // (MT, BN) for an op, or MT = 0 when the halo kernel does not apply.
 void pick_shape(const ConvOp& op, int* MT, int* BN) {
   *MT = 0, *BN = 0;
-  if (op.ksize != 3 || op.stride != 1 || op.up) return;
+  if (op.stride != 1 || op.up) return;
+  // 1x1 convs with a short K (one or two 64-channel chunks) are per-tile-overhead bound in the per-tap kernel; here
+  // they run as the centre tap alone over 4x larger tiles.  Longer-K 1x1 convs stay with the per-tap kernel, whose
+  // halo-free A tiles and BN = 256 serve them better.
+  if (op.ksize == 1 && (op.src[0].C + op.src[1].C > 2 * kBK || op.rsrc[0].C || op.up_parity >= 0)) return;
+  if (op.ksize != 3 && op.ksize != 1) return;
   if (op.Hin % kRows) return;
   if (op.Cout % 128 == 0 && op.Win % 16 == 0) {
     *MT = 2, *BN = 128;
   } else if (op.Cout % 64 == 0 && op.Win % 32 == 0) {
     *MT = 4, *BN = 64;
-  } else if (op.Cout <= 16 && op.Win % 32 == 0) {
+  } else if (op.Cout <= 16 && op.Win % 32 == 0 && op.ksize == 3) {
     *MT = 4, *BN = 16;
   }
 }
@@ -374,7 +401,7 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   p.err = host().err_flag;
   p.dbg = host().halo_dbg;
   p.variant = host().variant;
-  p.dy0 = p.dx0 = 0, p.kb0 = 0, p.oscale = 1, p.oy = p.ox = 0, p.slot_base = 0;
+  p.dy0 = p.dx0 = NT == 1 ? 1 : 0, p.kb0 = 0, p.oscale = 1, p.oy = p.ox = 0, p.slot_base = 0;
   if (op.up_parity >= 0) {
     const int py = op.up_parity >> 1, px = op.up_parity & 1;
     p.dy0 = py, p.dx0 = px, p.kb0 = op.up_parity * 4 * (p.chunks0 + p.chunks1);
@@ -392,6 +419,8 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   if (p.rchunks1) HSIDM_TRY(encode_act_map(&tmR1, op.rsrc[1].p, op.N, op.Hin, op.Win, op.rsrc[1].C, C::kPW, kHaloRows, 1));
   const int K = op.K();
   HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, BN));
+  CUtensorMap tmO = tmB;   // the BN = 16 instantiation (fp32 NCHW output) stores from registers and never reads it
+  if (BN % 64 == 0) HSIDM_TRY(encode_out_map(&tmO, op.out, op.N, op.Hout, op.Wout, op.Cout, p.oscale, p.oy, p.ox));
   const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
   char tag[96];
   snprintf(tag, sizeof(tag), "halo MT%d BN%d cin%d+%d cout%d %dx%d n%d%s%s%s%s", MT, BN, op.src[0].C, op.src[1].C, op.Cout, op.Hin, op.Win, op.N,
@@ -400,7 +429,7 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   const double flops = op.up_parity >= 0 ? 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * 9 * (op.src[0].C + op.src[1].C)
                                          : 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * K;
   ProfScope prof(PROF_CONV_TC, flops, stream, tag);
-  conv_halo_kernel<MT, BN, NT><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmR0, tmR1, tmB, p);
+  conv_halo_kernel<MT, BN, NT><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmR0, tmR1, tmB, tmO, p);
   return after_launch("conv_halo_kernel");
 }
 
@@ -411,6 +440,8 @@ int conv_halo_init() {
   HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 128>::kSmemBytes));
   HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
   HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 128>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
   HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 16, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 16>::kSmemBytes));
   return HSIDM_OK;
 }
@@ -440,10 +471,10 @@ bool conv_halo_supported(const ConvOp& op) {
 int conv_halo(const ConvOp& op, cudaStream_t stream) {
   int MT, BN;
   pick_shape(op, &MT, &BN);
-  const bool sub = op.up_parity >= 0;
-  if (MT == 2 && BN == 128) return sub ? launch<2, 128, 4>(op, stream) : launch<2, 128, 9>(op, stream);
-  if (MT == 4 && BN == 64) return sub ? launch<4, 64, 4>(op, stream) : launch<4, 64, 9>(op, stream);
-  if (MT == 4 && BN == 16 && !sub) return launch<4, 16, 9>(op, stream);
+  const bool sub = op.up_parity >= 0, one = op.ksize == 1;
+  if (MT == 2 && BN == 128) return one ? launch<2, 128, 1>(op, stream) : sub ? launch<2, 128, 4>(op, stream) : launch<2, 128, 9>(op, stream);
+  if (MT == 4 && BN == 64) return one ? launch<4, 64, 1>(op, stream) : sub ? launch<4, 64, 4>(op, stream) : launch<4, 64, 9>(op, stream);
+  if (MT == 4 && BN == 16 && !sub && !one) return launch<4, 16, 9>(op, stream);
   HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_halo: unsupported shape");
 }
 

@@ -46,7 +46,12 @@ struct Cfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  // Stages fill in groups of kGroup that share one full barrier: each barrier wait of the MMA issuer idles the tensor
+  // pipe for ~160 clk (scripts/mma_rate.cu), so it waits once per group; stages are still freed one by one.
+  static constexpr int kGroup = 2;
+  static constexpr int kGroups = ((kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes)) / kGroup;
+  static constexpr int kStages = kGroups * kGroup;
+  static_assert(kGroups >= 2, "pipeline too shallow");
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;
   static constexpr int kEpiBytes = BN % 64 == 0 ? kEpiWarps * 4096 : 0;   // staging for the coalesced epilogue
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -75,10 +80,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tma_prefetch_desc(&tmA0);
     if (p.chunks1) tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
-    }
+    for (int s = 0; s < C::kStages; ++s) mbar_init(smem_u32(&empty_bar[s]), 1);
+    for (int g = 0; g < C::kGroups; ++g) mbar_init(smem_u32(&full_bar[g]), C::kGroup);
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
       mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);   // one arrive per epilogue warp
@@ -94,7 +97,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      int stage = 0;
+      int stage = 0, grp = 0, gcnt = 0;
       uint32_t phase = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
@@ -115,7 +118,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int ch = 0; ch < p.chunks0 + p.chunks1; ++ch, ++kb) {
             ok = mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
             if (!ok) break;
-            const uint32_t fb = smem_u32(&full_bar[stage]);
+            const uint32_t fb = smem_u32(&full_bar[grp]);
             const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
             mbar_expect_tx(fb, C::kStageBytes);
             if (ch < p.chunks0)
@@ -124,16 +127,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               tma_load_4d(sa, &tmA1, fb, (ch - p.chunks0) * kBK, x0 + dx, y0 + dy, n0);
             tma_load_2d(sa + C::kABytes, &tmB, fb, kb * kBK, nt * BN);
             if (++stage == C::kStages) stage = 0, phase ^= 1;
+            if (++gcnt == C::kGroup) gcnt = 0, grp = grp + 1 == C::kGroups ? 0 : grp + 1;
           }
         }
       }
+      // the issuer waits for whole groups: complete the last, partly filled one
+      for (; ok && gcnt != 0 && gcnt < C::kGroup; ++gcnt) mbar_arrive(smem_u32(&full_bar[grp]));
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, grp = 0, gcnt = 0;
+      uint32_t gph = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       bool ok = true;
@@ -143,9 +149,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
-          ok = mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
-          if (!ok) break;
-          tc_fence_after();
+          if (gcnt == 0) {
+            ok = mbar_wait(smem_u32(&full_bar[grp]), gph, p.err, 3);
+            if (!ok) break;
+            tc_fence_after();
+          }
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + C::kABytes);
@@ -153,7 +161,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int k = 0; k < kBK / 16; ++k)  // +32 bytes (encoded +2) per K=16 slice inside the swizzle line
             umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
           umma_commit(smem_u32(&empty_bar[stage]));
-          if (++stage == C::kStages) stage = 0, phase ^= 1;
+          if (++stage == C::kStages) stage = 0;
+          if (++gcnt == C::kGroup) {
+            gcnt = 0;
+            if (++grp == C::kGroups) grp = 0, gph ^= 1;
+          }
         }
         umma_commit(smem_u32(&tfull_bar[acc]));
         if (++acc == 2) acc = 0, acc_phase ^= 1;
@@ -324,6 +336,18 @@ int encode_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int 
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: %d", N, H, W, C, (int)r);
+  return HSIDM_OK;
+}
+
+int encode_out_map(CUtensorMap* map, void* base, int N, int H, int W, int C, int scale, int oy, int ox) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(W / scale), (cuuint64_t)(H / scale), (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)scale * C * 2, (cuuint64_t)scale * W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBK, 8, 4, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  void* origin = static_cast<bf16*>(base) + ((long long)oy * W + ox) * C;
+  CUresult r = host().encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, origin, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled(output %dx%dx%dx%d) failed: %d", N, H, W, C, (int)r);
   return HSIDM_OK;
 }
 

@@ -30,7 +30,11 @@ struct GCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  // as in conv_tc.cu: kGroup stages share one full barrier so the MMA issuer waits (and idles the pipe) half as often
+  static constexpr int kGroup = 2;
+  static constexpr int kGroups = ((kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes)) / kGroup;
+  static constexpr int kStages = kGroups * kGroup;
+  static_assert(kGroups >= 2, "pipeline too shallow");
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kEpiBytes = 4 * 4096;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 256;
@@ -65,7 +69,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < C::kStages; ++s) mbar_init(smem_u32(&full_bar[s]), 1), mbar_init(smem_u32(&empty_bar[s]), 1);
+    for (int s = 0; s < C::kStages; ++s) mbar_init(smem_u32(&empty_bar[s]), 1);
+    for (int g = 0; g < C::kGroups; ++g) mbar_init(smem_u32(&full_bar[g]), C::kGroup);
     for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&tfull_bar[s]), 1), mbar_init(smem_u32(&tempty_bar[s]), 4);
     fence_barrier_init();
   }
@@ -77,7 +82,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
+      int stage = 0, grp = 0, gcnt = 0;
       uint32_t phase = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
@@ -86,20 +91,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < kblocks; ++kb) {
           ok = mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 11);
           if (!ok) break;
-          const uint32_t fb = smem_u32(&full_bar[stage]);
+          const uint32_t fb = smem_u32(&full_bar[grp]);
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           mbar_expect_tx(fb, C::kStageBytes);
           tma_load_3d(sa, &tmA, fb, kb * kBK, mt * kBM, p.a_batched ? b : 0);
           tma_load_3d(sa + C::kABytes, &tmB, fb, kb * kBK, nt * BN, p.b_batched ? b : 0);
           if (++stage == C::kStages) stage = 0, phase ^= 1;
+          if (++gcnt == C::kGroup) gcnt = 0, grp = grp + 1 == C::kGroups ? 0 : grp + 1;
         }
       }
+      for (; ok && gcnt != 0 && gcnt < C::kGroup; ++gcnt) mbar_arrive(smem_u32(&full_bar[grp]));   // complete the last group
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      int stage = 0, acc = 0, grp = 0, gcnt = 0;
+      uint32_t gph = 0, acc_phase = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         ok = mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 12);
@@ -107,15 +114,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
-          ok = mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 13);
-          if (!ok) break;
-          tc_fence_after();
+          if (gcnt == 0) {
+            ok = mbar_wait(smem_u32(&full_bar[grp]), gph, p.err, 13);
+            if (!ok) break;
+            tc_fence_after();
+          }
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + C::kABytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
           umma_commit(smem_u32(&empty_bar[stage]));
-          if (++stage == C::kStages) stage = 0, phase ^= 1;
+          if (++stage == C::kStages) stage = 0;
+          if (++gcnt == C::kGroup) {
+            gcnt = 0;
+            if (++grp == C::kGroups) grp = 0, gph ^= 1;
+          }
         }
         umma_commit(smem_u32(&tfull_bar[acc]));
         if (++acc == 2) acc = 0, acc_phase ^= 1;

@@ -420,6 +420,108 @@ static __device__ __forceinline__ void epilogue_halo64(const EpiP& p, const floa
   __syncwarp();
 }
 
+// ---- TMA store of a staged tile ----
+static __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+static __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+static __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+static __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Epilogue of the halo kernel for 64 output channels of one warp's 32 accumulator rows (4 image rows x 8 pixels):
+// TMEM -> registers -> +bias (64 floats the warp parked in shared memory at `bias_smem`, 0 = none) -> act/scale ->
+// +residual -> bf16 rows in the 128B-swizzled staging tile -> column statistics -> ONE TMA store of the tile
+// (box {64 ch, 8 px, 4 rows, 1 image} of the output lattice map, coordinates c0..c3).  Compared with epilogue_halo64
+// the write-back costs one instruction instead of 8 LDS + 8 STG with 64-bit address arithmetic, and the bias lives in
+// shared memory instead of 64 registers: the warp stays below the spill limit and issues ~1/3 fewer instructions.
+static __device__ __forceinline__ void epilogue_tma64(const EpiP& p, const CUtensorMap* tmO, uint32_t bias_smem, uint32_t taddr,
+                                                      int lane, uint32_t stage, int c0, int c1, int c2, int c3,
+                                                      const bf16* __restrict__ resid_lane, long long pitch, long long odd_off,
+                                                      float4& st) {
+  if (lane == 0) tma_store_wait_read();   // the previous store out of `stage` must have read it
+  __syncwarp();
+  // phase 1 (residual layers only): residual tile -> staging, coalesced; resid_lane already points at this lane's
+  // (row sub, 16-byte chunk) element of the tile
+  const int sub = lane >> 3, chunk = lane & 7;
+  if (resid_lane) {
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(resid_lane + (i >> 1) * pitch + (i & 1) * odd_off));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r7 = (4 * (i & 1) + sub) & 7;
+      sts128(stage + (uint32_t)((4 * i + sub) * 128 + ((chunk ^ r7) << 4)), v[i]);
+    }
+    __syncwarp();
+  }
+  // phase 2: own row in registers
+  {
+    uint32_t acc[4][16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tmem_ld16(taddr + q * 16, acc[q]);
+    tmem_ld_wait();
+    const uint32_t my_row = stage + (uint32_t)(lane * 128);
+    const int l7 = lane & 7;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {   // 8 channels per 16-byte chunk
+      float2 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        v[j] = make_float2(__uint_as_float(acc[c >> 1][(c & 1) * 8 + 2 * j]), __uint_as_float(acc[c >> 1][(c & 1) * 8 + 2 * j + 1]));
+      if (bias_smem) {
+        const uint4 b0 = lds128(bias_smem + c * 32), b1 = lds128(bias_smem + c * 32 + 16);   // broadcast reads
+        v[0] = __fadd2_rn(v[0], make_float2(__uint_as_float(b0.x), __uint_as_float(b0.y)));
+        v[1] = __fadd2_rn(v[1], make_float2(__uint_as_float(b0.z), __uint_as_float(b0.w)));
+        v[2] = __fadd2_rn(v[2], make_float2(__uint_as_float(b1.x), __uint_as_float(b1.y)));
+        v[3] = __fadd2_rn(v[3], make_float2(__uint_as_float(b1.z), __uint_as_float(b1.w)));
+      }
+      if (p.act == ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j].x = v[j].x > 0.f ? v[j].x : 0.01f * v[j].x, v[j].y = v[j].y > 0.f ? v[j].y : 0.01f * v[j].y;
+      }
+      if (p.scale != 1.0f) {
+        const float2 sc = make_float2(p.scale, p.scale);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __fmul2_rn(v[j], sc);
+      }
+      const uint32_t slot = my_row + (uint32_t)((c ^ l7) << 4);
+      if (resid_lane) {
+        const uint4 rv = lds128(slot);
+        v[0] = __fadd2_rn(v[0], bf16x2_to_f2(rv.x));
+        v[1] = __fadd2_rn(v[1], bf16x2_to_f2(rv.y));
+        v[2] = __fadd2_rn(v[2], bf16x2_to_f2(rv.z));
+        v[3] = __fadd2_rn(v[3], bf16x2_to_f2(rv.w));
+      }
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[j].x, v[j].y);
+      sts128(slot, o);
+    }
+    fence_proxy_async_smem();   // the rows just written are read by the TMA unit (async proxy)
+    __syncwarp();
+  }
+  if (lane == 0) tma_store_4d(tmO, stage, c0, c1, c2, c3);
+  // column sums of the stored values (lane -> channel pair 2*lane, 2*lane+1); conflict-free word reads
+  if (p.stats) {
+    const int cw = lane >> 2, ww = lane & 3;
+    uint32_t base[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) base[k] = stage + (uint32_t)(((cw ^ k) << 4) + ww * 4);
+    float2 s = make_float2(st.x, st.y), q = make_float2(st.z, st.w);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const float2 a = bf16x2_to_f2(lds32(base[r & 7] + r * 128));
+      s = __fadd2_rn(s, a);
+      q = __ffma2_rn(a, a, q);
+    }
+    st = make_float4(s.x, s.y, q.x, q.y);
+  }
+}
+
 // Publishes one warp's accumulated statistics for 64 channels into its slot.
 static __device__ __forceinline__ void stats_store(const EpiP& p, int n, int slot, int co0, int lane, const float4& st) {
   if (n < p.N_img)
@@ -442,6 +544,9 @@ struct Host {
 Host& host();
 // NHWC bf16 activation [N,H,W,C] as a 4-D tensor map with box {64, bw, bh, bn} and 128B swizzle (OOB reads are zero).
 int encode_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bw, int bh, int bn);
+// Store map of an NHWC bf16 output [N,H,W,C] restricted to the pixel lattice (scale*i + oy, scale*j + ox): a 4-D tensor
+// {C, W/scale, H/scale, N} with box {64, 8, 4, 1} (one epilogue warp's tile) and 128B swizzle.
+int encode_out_map(CUtensorMap* map, void* base, int N, int H, int W, int C, int scale, int oy, int ox);
 // K-major bf16 weights [rows][K] with box {64, bn_rows}.
 int encode_weight_map(CUtensorMap* map, const void* base, int K, int rows, int bn_rows);
 void fill_epilogue(EpiP* e, const ConvOp& op);
