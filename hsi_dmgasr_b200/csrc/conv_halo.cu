@@ -30,7 +30,9 @@ using namespace tc;
 
 constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter
 constexpr int kFirstEpiWarp = 3;    // warp 0: A (halo) producer, warp 1: B (weights) producer, warp 2: MMA issuer
-constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
+constexpr int kXformWarps = 4;      // warps 11..14: GroupNorm(+Swish) of the halo tile in place, when the op asks for it
+constexpr int kFirstXformWarp = kFirstEpiWarp + kEpiWarps;
+constexpr int kThreads = 32 * (kFirstXformWarp + kXformWarps);
 constexpr int kRows = 16;          // output rows per tile
 constexpr int kHaloRows = kRows + 2;
 constexpr int kAStages = 2;
@@ -45,6 +47,9 @@ struct HaloP {
   int kb0;                // first 64-wide k-block of this launch's weight columns (parity * 4 * chunks)
   int oscale, oy, ox;     // output pixel of source-tile pixel (i,j) = (oscale*i + oy, oscale*j + ox)
   int slot_base;          // first statistics slot of this launch
+  int Hin, Win;           // source image size (the fused GroupNorm must leave the zero padding at zero)
+  const float* gn_ab;     // fused input GroupNorm: per-image per-channel (A, B), [N][chunks*64][2]; null = none
+  int gn_swish;
   EpiP e;
   int* err;
   int variant;            // developer experiments (timing only, results invalid): 1 skip epilogue, 2 skip B loads, 4 skip A loads
@@ -96,7 +101,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint8_t* tail = smem_bias + C::kBiasBytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* a_empty = a_full + kAStages;
-  uint64_t* b_full = a_empty + kAStages;
+  uint64_t* a_ready = a_empty + kAStages;   // halo tile normalised in place (fused GroupNorm only)
+  uint64_t* b_full = a_ready + kAStages;
   uint64_t* b_empty = b_full + C::kBStages;
   uint64_t* tfull_bar = b_empty + C::kBStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -115,7 +121,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (p.rchunks1) tma_prefetch_desc(&tmR1);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
-    for (int s = 0; s < kAStages; ++s) mbar_init(smem_u32(&a_full[s]), 1), mbar_init(smem_u32(&a_empty[s]), 1);
+    for (int s = 0; s < kAStages; ++s)
+      mbar_init(smem_u32(&a_full[s]), 1), mbar_init(smem_u32(&a_empty[s]), 1), mbar_init(smem_u32(&a_ready[s]), kXformWarps);
     for (int s = 0; s < C::kBStages; ++s) mbar_init(smem_u32(&b_empty[s]), 1);
     for (int g = 0; g < C::kBGroups; ++g) mbar_init(smem_u32(&b_full[g]), C::kBGroup);
     for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&tfull_bar[s]), 1), mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
@@ -203,6 +210,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t b_lo = smem_u32(smem_b) >> 4;
       int as = 0, bs = 0, acc = 0, grp = 0, gcnt = 0;
       uint32_t aph = 0, gph = 0, acc_phase = 0;
+      uint32_t rph = 0;   // parity bit per halo stage of a_ready, which completes only on normalised (non-shortcut) uses
       bool ok = true;
       long long w_te = 0, w_af = 0, w_bf = 0;
       const long long t_start = p.dbg ? clock64() : 0;
@@ -212,7 +220,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (MT * BN);
         for (int ch = 0; ch < chunks && ok; ++ch) {
-          ok = timed_wait(smem_u32(&a_full[as]), aph, p.err, 3, p.dbg, w_af);
+          if (p.gn_ab) {
+            ok = timed_wait(smem_u32(&a_ready[as]), (rph >> as) & 1u, p.err, 8, p.dbg, w_af);
+            rph ^= 1u << as;
+          } else {
+            ok = timed_wait(smem_u32(&a_full[as]), aph, p.err, 3, p.dbg, w_af);
+          }
           if (!ok) break;
           const uint64_t adesc0 = desc_hi | (uint64_t)((smem_u32(smem + as * C::kAStage) + tap0) >> 4);
 #pragma unroll
@@ -272,6 +285,74 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (p.dbg) {
         p.dbg[blockIdx.x * 8 + 2] = w_te, p.dbg[blockIdx.x * 8 + 3] = w_af, p.dbg[blockIdx.x * 8 + 4] = w_bf;
         p.dbg[blockIdx.x * 8 + 5] = clock64() - t_start;
+      }
+    }
+  } else if (warp >= kFirstXformWarp) {
+    // =============================== fused GroupNorm(+Swish) of the halo tiles ===============================
+    // y = act(x*A[n,c] + B[n,c]) in place on every in-image pixel of the tile TMA just delivered; pixels outside the
+    // image keep the zeros TMA filled in (the conv pads the NORMALISED tensor).  Thread -> one 16-byte chunk (8
+    // channels, so 16 affine coefficients in registers) of rows tid/8, tid/8 + 16, ...; a row's logical chunk j sits
+    // at physical chunk j ^ (row & 7) (128B swizzle).  Same arithmetic as gn_apply (norm.cu), so fused and unfused
+    // paths agree bit for bit.
+    if (p.gn_ab) {
+      const int tid = threadIdx.x - 32 * kFirstXformWarp;
+      const int j8 = tid & 7, row0 = tid >> 3;
+      constexpr int kRowsTot = kHaloRows * C::kPW;
+      constexpr int kRowStep = 32 * kXformWarps / 8;
+      const int ctot = chunks * kBK;
+      int as = 0;
+      uint32_t aph = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles;
+        const int n = mt / tpi, r = mt - n * tpi;
+        const int y0 = (r / p.tiles_x) * kRows - 1, x0 = (r % p.tiles_x) * (8 * MT) - 1;   // image coordinates of halo (0,0)
+        for (int ch = 0; ch < chunks && ok; ++ch) {
+          // coefficients of this thread's 8 channels (issued before the wait: independent of the tile data)
+          const float4* abp = reinterpret_cast<const float4*>(p.gn_ab + ((long long)n * ctot + ch * kBK + j8 * 8) * 2);
+          float4 ab[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ab[q] = __ldg(abp + q);
+          ok = mbar_wait(smem_u32(&a_full[as]), aph, p.err, 7);
+          if (!ok) break;
+          const uint32_t base = smem_u32(smem + as * C::kAStage);
+          int hy = 0, hx = row0;   // row0 < 16 <= kPW
+#pragma unroll 2
+          for (int row = row0; row < kRowsTot; row += kRowStep) {
+            if ((unsigned)(y0 + hy) < (unsigned)p.Hin && (unsigned)(x0 + hx) < (unsigned)p.Win) {
+              const uint32_t addr = base + (uint32_t)(row * 128 + ((j8 ^ (row & 7)) << 4));
+              uint4 v = lds128(addr);
+              uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = bf16x2_to_f2(w[q]);
+                float y0f = fmaf(f.x, ab[q].x, ab[q].y), y1f = fmaf(f.y, ab[q].z, ab[q].w);
+                if (p.gn_swish) {
+                  float t0, t1;
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * y0f));
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * y1f));
+                  y0f = y0f * fmaf(0.5f, t0, 0.5f), y1f = y1f * fmaf(0.5f, t1, 0.5f);
+                }
+                const __nv_bfloat162 h = __floats2bfloat162_rn(y0f, y1f);
+                w[q] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              sts128(addr, v);
+            }
+            hx += kRowStep;
+            if (hx >= C::kPW) hx -= C::kPW, ++hy;
+          }
+          fence_proxy_async_smem();   // the MMA reads these rows through the async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&a_ready[as]));
+          if (++as == kAStages) as = 0, aph ^= 1;
+        }
+        // Shortcut tiles pass through un-normalised, but their barrier phases must still be observed one by one: a
+        // waiter that skipped them could run a whole ring lap ahead, where the parity of an old phase aliases the
+        // one it means to wait for.
+        for (int rc = 0; rc < rchunks && ok; ++rc) {
+          ok = mbar_wait(smem_u32(&a_full[as]), aph, p.err, 7);
+          if (++as == kAStages) as = 0, aph ^= 1;
+        }
       }
     }
   } else {
@@ -400,6 +481,7 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   fill_epilogue(&p.e, op);
   p.err = host().err_flag;
   p.dbg = host().halo_dbg;
+  p.Hin = op.Hin, p.Win = op.Win, p.gn_ab = op.gn_ab, p.gn_swish = op.gn_swish;
   p.variant = host().variant;
   p.dy0 = p.dx0 = NT == 1 ? 1 : 0, p.kb0 = 0, p.oscale = 1, p.oy = p.ox = 0, p.slot_base = 0;
   if (op.up_parity >= 0) {
@@ -422,9 +504,9 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   CUtensorMap tmO = tmB;   // the BN = 16 instantiation (fp32 NCHW output) stores from registers and never reads it
   if (BN % 64 == 0) HSIDM_TRY(encode_out_map(&tmO, op.out, op.N, op.Hout, op.Wout, op.Cout, p.oscale, p.oy, p.ox));
   const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
-  char tag[96];
-  snprintf(tag, sizeof(tag), "halo MT%d BN%d cin%d+%d cout%d %dx%d n%d%s%s%s%s", MT, BN, op.src[0].C, op.src[1].C, op.Cout, op.Hin, op.Win, op.N,
-           op.resid ? " +res" : "", op.nbias ? " +nb" : "", op.stats_out ? " +st" : "", op.up_parity >= 0 ? " up2x" : "");
+  char tag[112];
+  snprintf(tag, sizeof(tag), "halo MT%d BN%d cin%d+%d cout%d %dx%d n%d%s%s%s%s%s", MT, BN, op.src[0].C, op.src[1].C, op.Cout, op.Hin, op.Win, op.N,
+           op.resid ? " +res" : "", op.nbias ? " +nb" : "", op.stats_out ? " +st" : "", op.up_parity >= 0 ? " up2x" : "", op.gn_ab ? " +gn" : "");
   // algorithmic FLOPs: for the sub-pixel form, the share of the reference's 3x3 conv over the upsampled tensor
   const double flops = op.up_parity >= 0 ? 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * 9 * (op.src[0].C + op.src[1].C)
                                          : 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * K;

@@ -409,6 +409,8 @@ void conv_tc_set_mode(int no_halo, int variant) {
   tc::host().variant = variant;
 }
 
+int conv_tc_variant() { return tc::host().variant; }
+
 int conv_tc_bn_rows(int Cout) { return pick_bn(Cout); }
 
 bool conv_tc_supported(const ConvOp& op, int prec) {
@@ -434,8 +436,8 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: op (Cin %d+%d, Cout %d, k%d s%d, %dx%d) does not fit the tensor-core kernel",
                op.src[0].C, op.src[1].C, op.Cout, op.ksize, op.stride, op.Hin, op.Win);
   if (!host().no_halo && conv_halo_supported(op)) return conv_halo(op, stream);
-  if (op.rsrc[0].C || op.rsrc[1].C || op.up_parity >= 0)
-    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: fused shortcut sources / sub-pixel upsampling need the halo kernel, which does not take this shape");
+  if (op.rsrc[0].C || op.rsrc[1].C || op.up_parity >= 0 || op.gn_ab)
+    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: fused shortcut sources / sub-pixel upsampling / fused input GroupNorm need the halo kernel, which does not take this shape");
   TcP p;
   tile_geometry(op.Hin, op.Win, &p.bw, &p.bh, &p.bn);
   const int BN = pick_bn(op.Cout);

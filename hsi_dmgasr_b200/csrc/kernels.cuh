@@ -48,6 +48,12 @@ struct ConvOp {
   // conv_tc_stats_slots(op) (tensor-core kernels only)
   float* stats_out = nullptr;
   int stats_slots = 0;
+  // optional GroupNorm(+Swish) of the INPUT fused into the load path (halo tensor-core kernel only): src[] hold the
+  // un-normalised tensors and gn_ab the per-image per-channel affine [N][C0+C1][2] = (A, B) from gn_finalize, so that
+  // the conv sees act(x*A + B) with zero padding applied AFTER the activation, as in GroupNorm -> Swish -> Conv2d.
+  // The shortcut sources rsrc[] are never normalised.
+  const float* gn_ab = nullptr;
+  int gn_swish = 0;
   int K() const {
     if (up_parity >= 0) return 16 * (src[0].C + src[1].C);
     return ksize * ksize * (src[0].C + src[1].C) + rsrc[0].C + rsrc[1].C;
@@ -65,6 +71,7 @@ int conv_tc_stats_slots(const ConvOp& op);  // slots per image the kernel chosen
 int conv_tc_init();               // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int conv_tc_bn_rows(int Cout);    // N-tile height; packed bf16 weights are padded to a multiple of it (0 = unsupported)
 void conv_tc_set_mode(int no_halo, int variant);  // test knobs
+int conv_tc_variant();                             // current variant bits (8 = no fused input GroupNorm)
 void conv_halo_set_timing(long long* device_counters);   // developer probe, see hsidm_debug_halo_timing
 int conv_tc_error_flag(int* v);   // barrier-timeout flag of the tensor-core kernel (synchronises; tests only)
 
@@ -113,8 +120,10 @@ int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int 
              unsigned* tickets, float* stats, int prec, cudaStream_t stream);
 // Statistics from the per-slot partial sums the producing convolutions left behind (no pass over the tensors).
 // part0/part1: [N][slots][C][2] (sum, sumsq) for the two concatenated sources.
+// gamma/beta/ab optional: when given, also writes the per-channel affine ab[n][c] = (A, B) with GN(x) = x*A + B.
 int gn_finalize(const float* part0, int slots0, int C0, const float* part1, int slots1, int C1, int N, int HW, int groups,
-                float eps, float* stats, cudaStream_t stream);
+                float eps, float* stats, cudaStream_t stream, const float* gamma = nullptr, const float* beta = nullptr,
+                float* ab = nullptr);
 int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const float* stats,
              const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream);
 

@@ -288,6 +288,13 @@ void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps) {
   const int prec = ex.prec;
   ConvOp g;
   const Route route = plan_conv(ex, op, w, &g);
+  if (op.gn_ab && route != R_TC) {   // only the halo tensor-core kernel normalises its input on the fly
+    if (ex.status == HSIDM_OK) {
+      set_last_error("run_conv: fused input GroupNorm requested for an op the halo kernel does not take");
+      ex.status = HSIDM_UNSUPPORTED_CFG;
+    }
+    return;
+  }
   if (route == R_TC) {
     ex.run([&] { return conv_tc(op, st); });
   } else if (route == R_DOWN) {

@@ -265,7 +265,8 @@ int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int 
 // grid = N; thread -> (slot lane, channel pair), float4 loads = (sum, sumsq) of two channels; fixed-order folds only.
 __global__ void __launch_bounds__(1024)
 gn_finalize_kernel(const float* __restrict__ part0, int slots0, int C0, const float* __restrict__ part1, int slots1, int C1,
-                   int groups, int lanes, double cnt, float eps, float* __restrict__ stats) {
+                   int groups, int lanes, double cnt, float eps, float* __restrict__ stats, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ ab) {
   extern __shared__ float4 fsm4[];   // [lanes][C/2], then reused as float[2][C]
   const int C = C0 + C1, n = blockIdx.x, tid = threadIdx.x;
   const int pairs = C >> 1;
@@ -319,10 +320,19 @@ gn_finalize_kernel(const float* __restrict__ part0, int slots0, int C0, const fl
     stats[((long long)n * groups + g) * 2] = (float)mean;
     stats[((long long)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
   }
+  if (ab) {   // per-channel affine, the same expressions gn_apply evaluates
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      const float mean = stats[((long long)n * groups + g) * 2], rstd = stats[((long long)n * groups + g) * 2 + 1];
+      const float A = rstd * __ldg(gamma + c);
+      *reinterpret_cast<float2*>(ab + ((long long)n * C + c) * 2) = make_float2(A, __ldg(beta + c) - mean * A);
+    }
+  }
 }
 
 int gn_finalize(const float* part0, int slots0, int C0, const float* part1, int slots1, int C1, int N, int HW, int groups,
-                float eps, float* stats, cudaStream_t stream) {
+                float eps, float* stats, cudaStream_t stream, const float* gamma, const float* beta, float* ab) {
   const int C = C0 + C1;
   if (C0 % 64 || C1 % 64 || C % groups || C > 2048)
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "gn_finalize: channel counts %d+%d must be multiples of 64 and of the group count", C0, C1);
@@ -332,7 +342,7 @@ int gn_finalize(const float* part0, int slots0, int C0, const float* part1, int 
   const size_t smem = std::max<size_t>(sizeof(float4) * lanes * pairs, sizeof(float) * 2 * C);
   ProfScope prof(PROF_GN_STATS, 8.0 * N * ((double)slots0 * C0 + (double)slots1 * C1), stream, "finalize");
   gn_finalize_kernel<<<N, threads, smem, stream>>>(part0, slots0, C0, part1, slots1, C1, groups, lanes,
-                                                   (double)(C / groups) * HW, eps, stats);
+                                                   (double)(C / groups) * HW, eps, stats, gamma, beta, ab);
   return after_launch("gn_finalize_kernel");
 }
 

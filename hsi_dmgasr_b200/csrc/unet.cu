@@ -348,23 +348,63 @@ void attention(hsidm_ctx* c, const ResW& r, const Act& x, Act& out) {
   ex.release(av);
 }
 
+// conv(w) over GroupNorm(+Swish)(cat(x, skip)) -> out; `fill` sets the op's epilogue fields (noise bias, residual,
+// shortcut sources).  When the halo tensor-core kernel takes the op and both inputs carry the partial sums of their
+// producers, the normalisation is fused into the conv's load path (the conv reads the raw tensors and applies the
+// per-image per-channel affine + Swish to each halo tile in shared memory): the normalised tensor is never written or
+// re-read.  Otherwise it goes through gn_act's normalised copy.
+template <typename Fill>
+void gn_conv(hsidm_ctx* c, const Act& x, const Act* skip, int gw, int gb, bool swish, Act& out, const ConvW& w, Fill&& fill) {
+  Exec& ex = c->ex;
+  const int C1 = skip ? skip->C : 0;
+  static const bool no_fuse = std::getenv("HSIDM_NO_GNFUSE") != nullptr;   // A/B switch for profiling runs
+  bool fuse = !no_fuse && !(conv_tc_variant() & 8) && ex.prec == HSIDM_BF16 && x.stats && (!skip || skip->stats) && x.C % 64 == 0 && C1 % 64 == 0;
+  if (fuse) {
+    ConvOp probe = conv_op_nhwc(x, skip, out);
+    fill(probe);
+    probe.w_bf16 = w.w_bf16, probe.Cout = w.Cout, probe.ksize = w.ks;
+    static const float kDummy = 0.f;
+    probe.gn_ab = &kDummy;
+    fuse = probe.w_bf16 && conv_tc_supported(probe, ex.prec) && conv_halo_ok(probe);
+  }
+  if (!fuse) {
+    Act a = gn_act(c, x, skip, gw, gb, swish);
+    ConvOp op = conv_op_nhwc(a, nullptr, out);
+    fill(op);
+    run_conv(ex, op, w, c->ps);
+    ex.release(a);
+    return;
+  }
+  const int groups = c->cfg.norm_groups, C = x.C + C1;
+  float* stats = static_cast<float*>(ex.alloc_raw(sizeof(float) * 2 * x.N * groups));
+  float* ab = static_cast<float*>(ex.alloc_raw(sizeof(float) * 2 * (int64_t)x.N * C));
+  const float* s1 = skip ? skip->stats : nullptr;
+  const int sl1 = skip ? skip->slots : 0;
+  ex.run([&] {
+    return gn_finalize(x.stats, x.slots, x.C, s1, sl1, C1, x.N, x.H * x.W, groups, kGnEps, stats, ex.stream, c->ps.dev(gw),
+                       c->ps.dev(gb), ab);
+  });
+  ConvOp op = conv_op_nhwc(x, skip, out);
+  fill(op);
+  op.gn_ab = ab, op.gn_swish = swish ? 1 : 0;
+  run_conv(ex, op, w, c->ps);
+  ex.release_raw(ab);
+  ex.release_raw(stats);
+}
+
 // ResnetBlocWithAttn.forward (unet.py:105-111, 155-159) on cat(x, skip), written into `out`.  Inputs are not released.
 void res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const NoiseRef& nz, Act& out) {
   Exec& ex = c->ex;
   const int C1 = skip ? skip->C : 0;
-  Act a1 = gn_act(c, x, skip, r.gn1_w, r.gn1_b, true);
   Act h = conv_out(c, r.c1, x.N, x.H, x.W, r.cin, 0);
   {
-    ConvOp op = conv_op_nhwc(a1, nullptr, h);
-    op.nbias = nz.base + r.noise_off, op.nbias_stride = nz.n_stride;
-    op.nbias_t = nz.t_dev, op.nbias_t_stride = nz.t_stride;
     ConvW w1 = r.c1;
     w1.pb = -1;   // conv1's bias is folded into the noise-embedding vector (see hsidm_unet_commit)
-    run_conv(ex, op, w1, c->ps);
+    gn_conv(c, x, skip, r.gn1_w, r.gn1_b, true, h, w1, [&](ConvOp& op) {
+      op.nbias = nz.base + r.noise_off, op.nbias_stride = nz.n_stride;
+      op.nbias_t = nz.t_dev, op.nbias_t_stride = nz.t_stride;
+    });
   }
-  ex.release(a1);
-  Act a2 = gn_act(c, h, nullptr, r.gn2_w, r.gn2_b, true);
-  ex.release(h);
   // with attention the block output is an intermediate; otherwise conv2 writes straight into `out`
   Act mid;
   if (r.attn) mid = conv_out(c, r.c2, x.N, x.H, x.W, r.cout, 0);
@@ -372,18 +412,14 @@ void res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const
   // Shortcut: folded into conv2 as extra K columns on the halo tensor-core kernel (res_conv always; the identity only
   // for the narrow layers whose epilogue, not the MMA pipe, is the bottleneck); otherwise a 1x1 conv / epilogue add.
   bool fused = false;
+  ConvW wf;
   if (ex.prec == HSIDM_BF16 && r.fused.w && (r.has_res || r.cout <= 128)) {
-    ConvOp op = conv_op_nhwc(a2, nullptr, y);
-    op.rsrc[0].p = x.p, op.rsrc[0].C = x.C;
-    if (skip) op.rsrc[1].p = skip->p, op.rsrc[1].C = skip->C;
-    ConvW wf;
+    ConvOp probe = conv_op_nhwc(h, nullptr, y);
+    probe.rsrc[0].p = x.p, probe.rsrc[0].C = x.C;
+    if (skip) probe.rsrc[1].p = skip->p, probe.rsrc[1].C = skip->C;
     wf.Cin = r.cout, wf.Cout = r.cout, wf.ks = 3, wf.w_bf16 = r.fused.w, wf.bias_override = r.fused.bias;
-    ConvOp probe = op;
     probe.w_bf16 = wf.w_bf16, probe.Cout = wf.Cout;
-    if (conv_tc_supported(probe, ex.prec) && conv_halo_ok(probe)) {
-      run_conv(ex, op, wf, c->ps);
-      fused = true;
-    }
+    fused = conv_tc_supported(probe, ex.prec) && conv_halo_ok(probe);
   }
   Act shortcut;
   const void* resid = x.p;
@@ -392,13 +428,16 @@ void res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const
     run_conv(ex, conv_op_nhwc(x, skip, shortcut), r.rc, c->ps);
     resid = shortcut.p;
   }
-  if (!fused) {
-    ConvOp op = conv_op_nhwc(a2, nullptr, y);
-    op.resid = resid;
-    run_conv(ex, op, r.c2, c->ps);
-  }
+  gn_conv(c, h, nullptr, r.gn2_w, r.gn2_b, true, y, fused ? wf : r.c2, [&](ConvOp& op) {
+    if (fused) {
+      op.rsrc[0].p = x.p, op.rsrc[0].C = x.C;
+      if (skip) op.rsrc[1].p = skip->p, op.rsrc[1].C = skip->C;
+    } else {
+      op.resid = resid;
+    }
+  });
   if (!fused && r.has_res) ex.release(shortcut);
-  ex.release(a2);
+  ex.release(h);
   if (r.attn) {
     attention(c, r, mid, out);
     ex.release(mid);
@@ -554,14 +593,15 @@ void unet_forward_pass(hsidm_ctx* c, const float* x0, int c0, const float* x1, i
       }
       if (last_stage) {
         // final_conv = GroupNorm -> Swish -> conv to out_channel, fp32 NCHW (unet.py:236, 263)
-        Act a = gn_act(c, xs, nullptr, c->fin_gn_w, c->fin_gn_b, true);
+        Act dst;   // the network output is not an arena tensor: only the shape fields matter here
+        dst.N = cnt, dst.H = xs.H, dst.W = xs.W, dst.C = out_ch;
+        float* eps_out = eps ? eps + (int64_t)n0 * out_ch * xs.H * xs.W : nullptr;
+        gn_conv(c, xs, nullptr, c->fin_gn_w, c->fin_gn_b, true, dst, c->fin_conv, [&](ConvOp& op) {
+          op.N = cnt;
+          op.out = eps_out, op.out_layout = L_NCHW_F32;
+          op.stats_out = nullptr, op.stats_slots = 0;
+        });
         if (xs_owned) ex.release(xs);
-        ConvOp op;
-        op.src[0].p = a.p, op.src[0].C = a.C;
-        op.N = cnt, op.Hin = a.H, op.Win = a.W, op.Hout = a.H, op.Wout = a.W;
-        op.out = eps ? eps + (int64_t)n0 * out_ch * a.H * a.W : nullptr, op.out_layout = L_NCHW_F32;
-        run_conv(ex, op, c->fin_conv, c->ps);
-        ex.release(a);
       }
     }
     for (auto& s : skips) ex.release(s);

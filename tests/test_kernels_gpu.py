@@ -105,6 +105,11 @@ TC_CASES += [
     (2, 64, 0, 32, 32, 64, 3),        # halo kernel <4,64>, one tile per image
     (3, 64, 64, 16, 32, 128, 3),      # halo kernel <2,128>, two sources, two tiles per row
     (1, 192, 0, 48, 64, 64, 3),       # three chunks, H = 3 tiles
+    # more tiles than SMs: every CTA walks several tiles, so all barrier rings wrap (persistent-loop phases)
+    (10, 64, 0, 128, 128, 64, 3),     # <4,64>: 320 tiles
+    (24, 128, 64, 64, 64, 128, 3),    # <2,128>: 384 tiles, 3 chunks (odd ring occupancy per tile)
+    (40, 64, 0, 32, 32, 64, 1),       # centre-tap form of a short-K 1x1: 160 tiles
+    (40, 256, 0, 16, 16, 512, 1),     # per-tap kernel, 80 x 2 tiles, 4 k-blocks
 ]
 
 

@@ -67,3 +67,28 @@ def test_weights_follow_parameter_updates():
         net.final_conv["block"]["3"].bias.add_(1.0)
     b = net(x, lv)
     assert torch.allclose(b - a, torch.ones_like(a), atol=1e-5)
+
+
+@pytest.mark.parametrize("tag,hw,n", [("full32", 128, 2), ("full32", 64, 3), ("full32", 128, 12)])
+def test_fused_input_groupnorm_matches_normalised_copy(tag, hw, n):
+    """bf16 mode normalises each conv's input inside the conv's load path (halo kernel); the result must equal the
+    two-kernel form (GroupNorm-apply writes a normalised copy, the conv reads it) bit for bit: same arithmetic, same
+    bf16 rounding point, zero padding applied after the activation in both.  The 12-image case has more tiles than SMs
+    at the 128x128 and 64x64 levels, so the persistent kernels' barrier rings wrap."""
+    from hsi_dmgasr_b200 import _lib
+    lib = _lib.load()
+    cfg, seed, *_ = UNET_CASES[tag]
+    x = torch.from_numpy(np.random.default_rng(77).standard_normal((n, 6, hw, hw), dtype=np.float32)).cuda()
+    lv = torch.linspace(0.2, 0.9, n).view(n, 1).cuda()
+    outs = []
+    try:
+        for variant in (8, 0):
+            lib.hsidm_debug_conv_mode(0, variant)
+            net = build(cfg, seed, "bf16")
+            with torch.no_grad():
+                outs.append(net(x, lv).clone())
+            del net
+    finally:
+        lib.hsidm_debug_conv_mode(0, 0)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]), f"max |diff| {float((outs[0] - outs[1]).abs().max()):.3e}"
