@@ -35,7 +35,6 @@ constexpr int kFirstXformWarp = kFirstEpiWarp + kEpiWarps;
 constexpr int kThreads = 32 * (kFirstXformWarp + kXformWarps);
 constexpr int kRows = 16;          // output rows per tile
 constexpr int kHaloRows = kRows + 2;
-constexpr int kAStages = 2;
 
 struct HaloP {
   int tiles_x, tiles_y;   // tiles per image
@@ -69,6 +68,9 @@ static __device__ __forceinline__ bool timed_wait(uint32_t bar, uint32_t parity,
 template <int MT, int BN>
 struct HCfg {
   static constexpr int kPW = 8 * MT + 2;                                   // halo row pitch in pixels
+  // Halo stages: a tile's load (+ in-place GroupNorm) must hide behind the MMAs of the stages before it; with the short
+  // shortcut chunks in the ring two stages leave it exposed, so the narrow tiles take three (the wide ones do not fit).
+  static constexpr int kAStages = MT <= 2 ? 3 : 2;
   static constexpr int kABox = kHaloRows * kPW * 128;                      // bytes one TMA box writes
   static constexpr int kAStage = (kABox + 1023) / 1024 * 1024;             // keep every stage 1024-B aligned
   static constexpr int kBStage = BN * 128;
@@ -95,14 +97,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   using C = HCfg<MT, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_b = smem + kAStages * C::kAStage;
+  uint8_t* smem_b = smem + C::kAStages * C::kAStage;
   uint8_t* smem_stage = smem_b + C::kBStages * C::kBStage;
   uint8_t* smem_bias = smem_stage + C::kStageBytes;
   uint8_t* tail = smem_bias + C::kBiasBytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* a_empty = a_full + kAStages;
-  uint64_t* a_ready = a_empty + kAStages;   // halo tile normalised in place (fused GroupNorm only)
-  uint64_t* b_full = a_ready + kAStages;
+  uint64_t* a_empty = a_full + C::kAStages;
+  uint64_t* a_ready = a_empty + C::kAStages;   // halo tile normalised in place (fused GroupNorm only)
+  uint64_t* b_full = a_ready + C::kAStages;
   uint64_t* b_empty = b_full + C::kBStages;
   uint64_t* tfull_bar = b_empty + C::kBStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -121,7 +123,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (p.rchunks1) tma_prefetch_desc(&tmR1);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
-    for (int s = 0; s < kAStages; ++s)
+    for (int s = 0; s < C::kAStages; ++s)
       mbar_init(smem_u32(&a_full[s]), 1), mbar_init(smem_u32(&a_empty[s]), 1), mbar_init(smem_u32(&a_ready[s]), kXformWarps);
     for (int s = 0; s < C::kBStages; ++s) mbar_init(smem_u32(&b_empty[s]), 1);
     for (int g = 0; g < C::kBGroups; ++g) mbar_init(smem_u32(&b_full[g]), C::kBGroup);
@@ -150,7 +152,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (!ok) break;
           const uint32_t fb = smem_u32(&a_full[as]);
           const uint32_t dst = smem_u32(smem + as * C::kAStage);
-          if (p.variant & 4) { mbar_arrive(fb); if (++as == kAStages) as = 0, aph ^= 1; continue; }
+          if (p.variant & 4) { mbar_arrive(fb); if (++as == C::kAStages) as = 0, aph ^= 1; continue; }
           mbar_expect_tx(fb, C::kABox);
           if (ch < p.chunks0)
             tma_load_4d(dst, &tmA0, fb, ch * kBK, x0 - 1, y0 - 1, n);
@@ -160,7 +162,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_load_4d(dst, &tmR0, fb, (ch - chunks) * kBK, x0 - 1, y0 - 1, n);
           else
             tma_load_4d(dst, &tmR1, fb, (ch - chunks - p.rchunks0) * kBK, x0 - 1, y0 - 1, n);
-          if (++as == kAStages) as = 0, aph ^= 1;
+          if (++as == C::kAStages) as = 0, aph ^= 1;
         }
       }
       if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = w_ae;
@@ -210,7 +212,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t b_lo = smem_u32(smem_b) >> 4;
       int as = 0, bs = 0, acc = 0, grp = 0, gcnt = 0;
       uint32_t aph = 0, gph = 0, acc_phase = 0;
-      uint32_t rph = 0;   // parity bit per halo stage of a_ready, which completes only on normalised (non-shortcut) uses
       bool ok = true;
       long long w_te = 0, w_af = 0, w_bf = 0;
       const long long t_start = p.dbg ? clock64() : 0;
@@ -220,12 +221,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (MT * BN);
         for (int ch = 0; ch < chunks && ok; ++ch) {
-          if (p.gn_ab) {
-            ok = timed_wait(smem_u32(&a_ready[as]), (rph >> as) & 1u, p.err, 8, p.dbg, w_af);
-            rph ^= 1u << as;
-          } else {
-            ok = timed_wait(smem_u32(&a_full[as]), aph, p.err, 3, p.dbg, w_af);
-          }
+          ok = timed_wait(smem_u32(p.gn_ab ? &a_ready[as] : &a_full[as]), aph, p.err, 3, p.dbg, w_af);
           if (!ok) break;
           const uint64_t adesc0 = desc_hi | (uint64_t)((smem_u32(smem + as * C::kAStage) + tap0) >> 4);
 #pragma unroll
@@ -252,10 +248,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
           }
           umma_commit(smem_u32(&a_empty[as]));
-          if (++as == kAStages) as = 0, aph ^= 1;
+          if (++as == C::kAStages) as = 0, aph ^= 1;
         }
         for (int rc = 0; rc < rchunks && ok; ++rc) {   // shortcut: centre tap of the un-normalised block input
-          ok = timed_wait(smem_u32(&a_full[as]), aph, p.err, 3, p.dbg, w_af);
+          ok = timed_wait(smem_u32(p.gn_ab ? &a_ready[as] : &a_full[as]), aph, p.err, 3, p.dbg, w_af);
           if (!ok) break;
           if (gcnt == 0) {
             ok = timed_wait(smem_u32(&b_full[grp]), gph, p.err, 6, p.dbg, w_bf);
@@ -277,7 +273,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (++grp == C::kBGroups) grp = 0, gph ^= 1;
           }
           umma_commit(smem_u32(&a_empty[as]));
-          if (++as == kAStages) as = 0, aph ^= 1;
+          if (++as == C::kAStages) as = 0, aph ^= 1;
         }
         umma_commit(smem_u32(&tfull_bar[acc]));
         if (++acc == 2) acc = 0, acc_phase ^= 1;
@@ -344,14 +340,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           fence_proxy_async_smem();   // the MMA reads these rows through the async proxy
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&a_ready[as]));
-          if (++as == kAStages) as = 0, aph ^= 1;
+          if (++as == C::kAStages) as = 0, aph ^= 1;
         }
-        // Shortcut tiles pass through un-normalised, but their barrier phases must still be observed one by one: a
-        // waiter that skipped them could run a whole ring lap ahead, where the parity of an old phase aliases the
-        // one it means to wait for.
+        // Shortcut tiles pass through un-normalised, but every use of a stage is still acknowledged through a_ready:
+        // the issuer then cannot hand a stage back to the producer before all four warps have seen its phase, so no
+        // waiter can fall a ring lap behind (where the parity of an old phase would alias the one it waits for).
         for (int rc = 0; rc < rchunks && ok; ++rc) {
           ok = mbar_wait(smem_u32(&a_full[as]), aph, p.err, 7);
-          if (++as == kAStages) as = 0, aph ^= 1;
+          if (!ok) break;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&a_ready[as]));
+          if (++as == C::kAStages) as = 0, aph ^= 1;
         }
       }
     }

@@ -409,11 +409,13 @@ void res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const
   Act mid;
   if (r.attn) mid = conv_out(c, r.c2, x.N, x.H, x.W, r.cout, 0);
   Act& y = r.attn ? mid : out;
-  // Shortcut: folded into conv2 as extra K columns on the halo tensor-core kernel (res_conv always; the identity only
-  // for the narrow layers whose epilogue, not the MMA pipe, is the bottleneck); otherwise a 1x1 conv / epilogue add.
+  // Shortcut: res_conv is folded into conv2 as extra K columns on the halo tensor-core kernel; the identity shortcut is
+  // the epilogue's residual add (folding it too - HSIDM_FUSE_ID_MAX=<max Cout> - measured no faster since the epilogue
+  // stores through TMA: 19.5 vs 19.1 ms per step); without the halo kernel: a 1x1 conv / epilogue add.
   bool fused = false;
   ConvW wf;
-  if (ex.prec == HSIDM_BF16 && r.fused.w && (r.has_res || r.cout <= 128)) {
+  static const int fuse_id_max = std::getenv("HSIDM_FUSE_ID_MAX") ? atoi(std::getenv("HSIDM_FUSE_ID_MAX")) : 0;
+  if (ex.prec == HSIDM_BF16 && r.fused.w && (r.has_res || r.cout <= fuse_id_max)) {
     ConvOp probe = conv_op_nhwc(h, nullptr, y);
     probe.rsrc[0].p = x.p, probe.rsrc[0].C = x.C;
     if (skip) probe.rsrc[1].p = skip->p, probe.rsrc[1].C = skip->C;
