@@ -458,8 +458,12 @@ void pick_shape(const ConvOp& op, int* MT, int* BN) {
   if (op.Hin % kRows) return;
   if (op.Cout % 128 == 0 && op.Win % 16 == 0) {
     *MT = 2, *BN = 128;
-  } else if (op.Cout % 64 == 0 && op.Win % 32 == 0) {
+  } else if (op.Cout % 64 == 0 && op.Win % 32 == 0 && !(host().variant & 16)) {
     *MT = 4, *BN = 64;
+  } else if (op.Cout % 64 == 0 && op.Win % 16 == 0) {
+    // narrow tile with three halo stages: also the test knob (variant bit 16) for the 32-multiple widths, where it
+    // measured 10-30 % slower than <4,64> (half the weight-tile reuse, twice the per-tile overhead)
+    *MT = 2, *BN = 64;
   } else if (op.Cout <= 16 && op.Win % 32 == 0 && op.ksize == 3) {
     *MT = 4, *BN = 16;
   }
@@ -523,6 +527,9 @@ int conv_halo_init() {
   HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
   HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 128>::kSmemBytes));
   HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 64, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 64>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 64>::kSmemBytes));
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 64>::kSmemBytes));
   HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 16, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 16>::kSmemBytes));
   return HSIDM_OK;
 }
@@ -554,6 +561,7 @@ int conv_halo(const ConvOp& op, cudaStream_t stream) {
   pick_shape(op, &MT, &BN);
   const bool sub = op.up_parity >= 0, one = op.ksize == 1;
   if (MT == 2 && BN == 128) return one ? launch<2, 128, 1>(op, stream) : sub ? launch<2, 128, 4>(op, stream) : launch<2, 128, 9>(op, stream);
+  if (MT == 2 && BN == 64) return one ? launch<2, 64, 1>(op, stream) : sub ? launch<2, 64, 4>(op, stream) : launch<2, 64, 9>(op, stream);
   if (MT == 4 && BN == 64) return one ? launch<4, 64, 1>(op, stream) : sub ? launch<4, 64, 4>(op, stream) : launch<4, 64, 9>(op, stream);
   if (MT == 4 && BN == 16 && !sub && !one) return launch<4, 16, 9>(op, stream);
   HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_halo: unsupported shape");
