@@ -263,7 +263,7 @@ int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int 
 }
 
 // grid = N; thread -> (slot lane, channel pair), float4 loads = (sum, sumsq) of two channels; fixed-order folds only.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 2)   // two blocks per SM: a 176-image batch is one wave, not two
 gn_finalize_kernel(const float* __restrict__ part0, int slots0, int C0, const float* __restrict__ part1, int slots1, int C1,
                    int groups, int lanes, double cnt, float eps, float* __restrict__ stats, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ ab) {
