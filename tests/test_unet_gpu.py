@@ -92,3 +92,25 @@ def test_fused_input_groupnorm_matches_normalised_copy(tag, hw, n):
         lib.hsidm_debug_conv_mode(0, 0)
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1]), f"max |diff| {float((outs[0] - outs[1]).abs().max()):.3e}"
+
+
+def test_c4_shape_512_bf16_tracks_fp32():
+    """BASELINE config C4: the 64_512 UNet (mults 1-2-4-8-16, one res block, 16 groups, mid attention at 32x32 = 1024
+    tokens) on a 512x512 latent.  The CPU oracle needs minutes at this size, so the check is internal: the tensor-core
+    bf16 path (halo kernel with 512 tiles per image at the top level, fused GroupNorm, sub-pixel upsampling, batched
+    tensor-core attention at S = 1024) must track this library's fp32 CUDA-core path, which the golden vectors pin at
+    64x64 (wide64), within the bf16 gate."""
+    cfg, seed, *_ = UNET_CASES["wide64"]
+    x = torch.from_numpy(np.random.default_rng(5).standard_normal((1, 6, 512, 512), dtype=np.float32)).cuda()
+    lv = torch.tensor([[0.37]], dtype=torch.float32).cuda()
+    outs = {}
+    for precision in ("fp32", "bf16"):
+        net = build(cfg, seed, precision)
+        with torch.no_grad():
+            outs[precision] = net(x, lv).clone()
+        del net
+        torch.cuda.empty_cache()
+    err = rel_l2(outs["bf16"], outs["fp32"])
+    print(f"C4 512x512: bf16 vs fp32 rel-L2 {err:.3e}")
+    assert torch.isfinite(outs["bf16"]).all() and outs["bf16"].shape == (1, 3, 512, 512)
+    assert err < TOL["bf16"]
