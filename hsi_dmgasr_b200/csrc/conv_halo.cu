@@ -65,7 +65,7 @@ static __device__ __forceinline__ bool timed_wait(uint32_t bar, uint32_t parity,
   return ok;
 }
 
-template <int MT, int BN>
+template <int MT, int BN, bool PAIR = false>
 struct HCfg {
   static constexpr int kPW = 8 * MT + 2;                                   // halo row pitch in pixels
   // Halo stages: a tile's load (+ in-place GroupNorm) must hide behind the MMAs of the stages before it; with the short
@@ -73,9 +73,10 @@ struct HCfg {
   static constexpr int kAStages = MT <= 2 ? 3 : 2;
   static constexpr int kABox = kHaloRows * kPW * 128;                      // bytes one TMA box writes
   static constexpr int kAStage = (kABox + 1023) / 1024 * 1024;             // keep every stage 1024-B aligned
-  static constexpr int kBStage = BN * 128;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;                         // weight rows this CTA holds (a pair splits them)
+  static constexpr int kBStage = kBRows * 128;
   static constexpr int kStageBytes = kEpiWarps * 4096;                     // epilogue staging, 4 KB per epilogue warp
-  static constexpr int kBStagesRaw = (232448 - 1536 - kEpiWarps * 256 - kStageBytes - kAStages * kAStage) / kBStage;
+  static constexpr int kBStagesRaw = (232448 - 1536 - kEpiWarps * 512 - kStageBytes - kAStages * kAStage) / kBStage;
   // Weight tiles land in groups of kBGroup taps that share ONE full barrier: every barrier wait of the MMA issuer
   // stalls the tensor pipe for ~160 clk (measured, scripts/mma_rate.cu), so it waits once per group, not per tap.
   // Stages are still released (tcgen05.commit, free) and refilled one tap at a time.
@@ -83,18 +84,18 @@ struct HCfg {
   static constexpr int kBGroups = (kBStagesRaw > 9 ? 9 : kBStagesRaw) / kBGroup;
   static constexpr int kBStages = kBGroups * kBGroup;
   static constexpr int kTmemCols = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;
-  static constexpr int kBiasBytes = kEpiWarps * 256;                       // 64 bias floats per epilogue warp
+  static constexpr int kBiasBytes = kEpiWarps * 512;                       // 2 x 64 bias floats per epilogue warp
   static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + kStageBytes + kBiasBytes + 1024 + 512;
   static_assert(kBGroups >= 2, "not enough shared memory for the B ring");
   static_assert(2 * MT * BN <= 512, "accumulators do not fit TMEM");
 };
 
-template <int MT, int BN, int NT>
+template <int MT, int BN, int NT, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const HaloP p) {
-  using C = HCfg<MT, BN>;
+  using C = HCfg<MT, BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem + C::kAStages * C::kAStage;
@@ -111,7 +112,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // CTA pair (PAIR): the two CTAs of a cluster work on two adjacent pixel tiles (m-tiles 2q, 2q+1) of the SAME channel
+  // tile; each holds its own halo tiles and half of the weight rows, and the leader (rank 0) issues M = 256
+  // cta_group::2 MMAs over both.  Per MMA a CTA then reads its A slice plus HALF a B slice from shared memory.
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int total_tiles = PAIR ? (p.m_tiles / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto m_tile_of = [&](int tile) { return PAIR ? 2 * (tile / p.n_tiles) + (int)rank : tile / p.n_tiles; };
   const int chunks = p.chunks0 + p.chunks1;
   const int rchunks = p.rchunks0 + p.rchunks1;
   const int tpi = p.tiles_x * p.tiles_y;
@@ -124,15 +132,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
     for (int s = 0; s < C::kAStages; ++s)
-      mbar_init(smem_u32(&a_full[s]), 1), mbar_init(smem_u32(&a_empty[s]), 1), mbar_init(smem_u32(&a_ready[s]), kXformWarps);
+      mbar_init(smem_u32(&a_full[s]), 1), mbar_init(smem_u32(&a_empty[s]), 1),
+          mbar_init(smem_u32(&a_ready[s]), PAIR ? 2 * kXformWarps : kXformWarps);   // a pair's leader hears both CTAs
     for (int s = 0; s < C::kBStages; ++s) mbar_init(smem_u32(&b_empty[s]), 1);
     for (int g = 0; g < C::kBGroups; ++g) mbar_init(smem_u32(&b_full[g]), C::kBGroup);
-    for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&tfull_bar[s]), 1), mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
+    for (int s = 0; s < 2; ++s)
+      mbar_init(smem_u32(&tfull_bar[s]), 1), mbar_init(smem_u32(&tempty_bar[s]), PAIR ? 2 * kEpiWarps : kEpiWarps);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_pair(smem_u32(tmem_slot), C::kTmemCols);
+    else tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -143,8 +157,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t aph = 0;
       bool ok = true;
       long long w_ae = 0;
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
+      for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
+        const int mt = m_tile_of(tile);
         const int n = mt / tpi, r = mt - n * tpi;
         const int y0 = (r / p.tiles_x) * kRows, x0 = (r % p.tiles_x) * (8 * MT);
         for (int ch = 0; ch < chunks + rchunks; ++ch) {
@@ -179,7 +193,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         ok = timed_wait(smem_u32(&b_empty[bs]), bph ^ 1, p.err, 5, p.dbg, w_be);
         if (!ok) return;
         const uint32_t bb = smem_u32(&b_full[grp]);
-        if (p.variant & 2) {
+        if constexpr (PAIR) {
+          // each CTA fetches its half of the weight rows; both halves complete on the LEADER's group barrier, which
+          // the leader arms for the bytes of both
+          if (rank == 0) mbar_expect_tx(bb, 2 * C::kBStage);
+          tma_load_2d_pair(smem_u32(smem_b + bs * C::kBStage), &tmB, mapa_cluster(bb, 0), kb * kBK, nt * BN + (int)rank * C::kBRows);
+        } else if (p.variant & 2) {
           mbar_arrive(bb);
         } else {
           mbar_expect_tx(bb, C::kBStage);
@@ -188,14 +207,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (++bs == C::kBStages) bs = 0, bph ^= 1;
         if (++gcnt == C::kBGroup) gcnt = 0, grp = grp + 1 == C::kBGroups ? 0 : grp + 1;
       };
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
         const int nt = tile % p.n_tiles;
         for (int ch = 0; ch < chunks && ok; ++ch)
           for (int tap = 0; tap < NT && ok; ++tap) load_b(p.kb0 + tap * chunks + ch, nt);
         for (int rc = 0; rc < rchunks && ok; ++rc) load_b(p.kb0 + NT * chunks + rc, nt);   // shortcut columns follow the 3x3 ones
       }
       // the issuer waits for whole groups: complete the last, partly filled one
-      for (; ok && gcnt != 0 && gcnt < C::kBGroup; ++gcnt) mbar_arrive(smem_u32(&b_full[grp]));
+      for (; ok && rank == 0 && gcnt != 0 && gcnt < C::kBGroup; ++gcnt) mbar_arrive(smem_u32(&b_full[grp]));
       if (p.dbg) p.dbg[blockIdx.x * 8 + 1] = w_be;
     }
   } else if (warp == 2) {
@@ -203,9 +222,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // The tensor pipe only stays busy while tcgen05.mma instructions arrive back to back: whatever else this thread
     // does between two of them (a barrier wait, address arithmetic) shows up as idle pipe time.  Hence: taps unrolled
     // with compile-time operand offsets, one weight-group wait per kBGroup taps, commits (free) per tap.
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       constexpr int TW = NT == 9 ? 3 : 2;
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kBM : kBM, BN);
+      // one MMA / one completion signal, in the single-CTA or the pair form
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t acc_flag) {
+        if constexpr (PAIR) umma_f16_pair(d, a, b, idesc, acc_flag);
+        else umma_f16(d, a, b, idesc, acc_flag);
+      };
+      auto commit = [](uint32_t bar) {
+        if constexpr (PAIR) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
       constexpr uint64_t desc_hi = (uint64_t)((C::kPW * 128) >> 4) << 32 | (1ull << 46) | (2ull << 61) | (1ull << 16);
       constexpr uint64_t bdesc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
       const uint32_t tap0 = (uint32_t)((p.dy0 * C::kPW + p.dx0) * 128);   // halo offset of tap (0,0)
@@ -215,13 +243,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       bool ok = true;
       long long w_te = 0, w_af = 0, w_bf = 0;
       const long long t_start = p.dbg ? clock64() : 0;
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
         ok = timed_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 2, p.dbg, w_te);
         if (!ok) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (MT * BN);
         for (int ch = 0; ch < chunks && ok; ++ch) {
-          ok = timed_wait(smem_u32(p.gn_ab ? &a_ready[as] : &a_full[as]), aph, p.err, 3, p.dbg, w_af);
+          ok = timed_wait(smem_u32((PAIR || p.gn_ab) ? &a_ready[as] : &a_full[as]), aph, p.err, 3, p.dbg, w_af);
           if (!ok) break;
           const uint64_t adesc0 = desc_hi | (uint64_t)((smem_u32(smem + as * C::kAStage) + tap0) >> 4);
 #pragma unroll
@@ -237,21 +265,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             for (int s = 0; s < MT; ++s) {
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k)
-                umma_f16(d_tmem + s * BN, adesc0 + (uint64_t)((kTapOff + s * 1024) / 16 + 2 * k), bdesc + 2 * k, idesc,
-                         (tap | k) ? 1u : (ch ? 1u : 0u));
+                mma(d_tmem + s * BN, adesc0 + (uint64_t)((kTapOff + s * 1024) / 16 + 2 * k), bdesc + 2 * k,
+                    (tap | k) ? 1u : (ch ? 1u : 0u));
             }
-            umma_commit(smem_u32(&b_empty[bs]));
+            commit(smem_u32(&b_empty[bs]));
             if (++bs == C::kBStages) bs = 0;
             if (++gcnt == C::kBGroup) {
               gcnt = 0;
               if (++grp == C::kBGroups) grp = 0, gph ^= 1;
             }
           }
-          umma_commit(smem_u32(&a_empty[as]));
+          commit(smem_u32(&a_empty[as]));
           if (++as == C::kAStages) as = 0, aph ^= 1;
         }
         for (int rc = 0; rc < rchunks && ok; ++rc) {   // shortcut: centre tap of the un-normalised block input
-          ok = timed_wait(smem_u32(p.gn_ab ? &a_ready[as] : &a_full[as]), aph, p.err, 3, p.dbg, w_af);
+          ok = timed_wait(smem_u32((PAIR || p.gn_ab) ? &a_ready[as] : &a_full[as]), aph, p.err, 3, p.dbg, w_af);
           if (!ok) break;
           if (gcnt == 0) {
             ok = timed_wait(smem_u32(&b_full[grp]), gph, p.err, 6, p.dbg, w_bf);
@@ -264,18 +292,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int s = 0; s < MT; ++s) {
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
-              umma_f16(d_tmem + s * BN, adesc0 + (uint64_t)(s * 1024 / 16 + 2 * k), bdesc + 2 * k, idesc, 1u);
+              mma(d_tmem + s * BN, adesc0 + (uint64_t)(s * 1024 / 16 + 2 * k), bdesc + 2 * k, 1u);
           }
-          umma_commit(smem_u32(&b_empty[bs]));
+          commit(smem_u32(&b_empty[bs]));
           if (++bs == C::kBStages) bs = 0;
           if (++gcnt == C::kBGroup) {
             gcnt = 0;
             if (++grp == C::kBGroups) grp = 0, gph ^= 1;
           }
-          umma_commit(smem_u32(&a_empty[as]));
+          commit(smem_u32(&a_empty[as]));
           if (++as == C::kAStages) as = 0, aph ^= 1;
         }
-        umma_commit(smem_u32(&tfull_bar[acc]));
+        commit(smem_u32(&tfull_bar[acc]));
         if (++acc == 2) acc = 0, acc_phase ^= 1;
       }
       if (p.dbg) {
@@ -290,8 +318,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // channels, so 16 affine coefficients in registers) of rows tid/8, tid/8 + 16, ...; a row's logical chunk j sits
     // at physical chunk j ^ (row & 7) (128B swizzle).  Same arithmetic as gn_apply (norm.cu), so fused and unfused
     // paths agree bit for bit.
-    if (p.gn_ab) {
+    if (PAIR || p.gn_ab) {   // a pair always routes halo readiness through these warps (the leader hears both CTAs)
       const int tid = threadIdx.x - 32 * kFirstXformWarp;
+      // a_ready of the CTA whose issuer consumes the stage: this CTA's own, or the pair leader's
+      auto ready_arrive = [&](int stage) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_cluster(smem_u32(&a_ready[stage]), 0));
+        else mbar_arrive(smem_u32(&a_ready[stage]));
+      };
       const int j8 = tid & 7, row0 = tid >> 3;
       constexpr int kRowsTot = kHaloRows * C::kPW;
       constexpr int kRowStep = 32 * kXformWarps / 8;
@@ -299,20 +332,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       int as = 0;
       uint32_t aph = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
+      for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
+        const int mt = m_tile_of(tile);
         const int n = mt / tpi, r = mt - n * tpi;
         const int y0 = (r / p.tiles_x) * kRows - 1, x0 = (r % p.tiles_x) * (8 * MT) - 1;   // image coordinates of halo (0,0)
         for (int ch = 0; ch < chunks && ok; ++ch) {
           // coefficients of this thread's 8 channels (issued before the wait: independent of the tile data)
-          const float4* abp = reinterpret_cast<const float4*>(p.gn_ab + ((long long)n * ctot + ch * kBK + j8 * 8) * 2);
           float4 ab[4];
+          if (p.gn_ab) {
+            const float4* abp = reinterpret_cast<const float4*>(p.gn_ab + ((long long)n * ctot + ch * kBK + j8 * 8) * 2);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) ab[q] = __ldg(abp + q);
+            for (int q = 0; q < 4; ++q) ab[q] = __ldg(abp + q);
+          }
           ok = mbar_wait(smem_u32(&a_full[as]), aph, p.err, 7);
           if (!ok) break;
+          if (!p.gn_ab) {   // pair without a fused GroupNorm: relay only
+            __syncwarp();
+            if (lane == 0) ready_arrive(as);
+            if (++as == C::kAStages) as = 0, aph ^= 1;
+            continue;
+          }
           const uint32_t base = smem_u32(smem + as * C::kAStage);
-          int hy = 0, hx = row0;   // row0 < 16 <= kPW
+          int hy = row0 / C::kPW, hx = row0 % C::kPW;   // halo coordinates of this thread's current row
 #pragma unroll 2
           for (int row = row0; row < kRowsTot; row += kRowStep) {
             if ((unsigned)(y0 + hy) < (unsigned)p.Hin && (unsigned)(x0 + hx) < (unsigned)p.Win) {
@@ -334,12 +375,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               }
               sts128(addr, v);
             }
-            hx += kRowStep;
+            hx += kRowStep % C::kPW, hy += kRowStep / C::kPW;
             if (hx >= C::kPW) hx -= C::kPW, ++hy;
           }
           fence_proxy_async_smem();   // the MMA reads these rows through the async proxy
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&a_ready[as]));
+          if (lane == 0) ready_arrive(as);
           if (++as == C::kAStages) as = 0, aph ^= 1;
         }
         // Shortcut tiles pass through un-normalised, but every use of a stage is still acknowledged through a_ready:
@@ -349,7 +390,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           ok = mbar_wait(smem_u32(&a_full[as]), aph, p.err, 7);
           if (!ok) break;
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&a_ready[as]));
+          if (lane == 0) ready_arrive(as);
           if (++as == C::kAStages) as = 0, aph ^= 1;
         }
       }
@@ -366,30 +407,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     bool ok = true;
     long long w_tf = 0;
     const long long t_start = p.dbg ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+    for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
+      const int mt = m_tile_of(tile), nt = tile % p.n_tiles;
       const int n = mt / tpi, r = mt - n * tpi;
       const int y = (r / p.tiles_x) * kRows + (row >> 3);
       const int xb = (r % p.tiles_x) * (8 * MT) + (row & 7);
-      // this warp's share of the tile: one 64-channel chunk `ci` (of BN/64) and sub-tiles s_first, s_first+s_step, ...
+      // this warp's share of the tile: with several 64-channel chunks (BN >= 128) the two warps of a lane quarter take
+      // alternate chunks ci = half, half + 2, ... of every sub-tile; with one chunk they take alternate sub-tiles
       constexpr bool by_chunk = nC >= 2;
-      const int ci = by_chunk ? half : 0;
+      const int c_first = by_chunk ? half : 0, c_step = by_chunk ? 2 : 1;
       const int s_first = by_chunk ? 0 : half, s_step = by_chunk ? 1 : 2;
       const int ty0 = (r / p.tiles_x) * kRows, tx0 = (r % p.tiles_x) * (8 * MT);
-      uint32_t bias_smem = 0;
+      const uint32_t bias_base = smem_u32(smem_bias + (warp - kFirstEpiWarp) * 512);
+      bool have_bias = false;
       if constexpr (nC >= 1) {
-        // park the tile's 64 bias values (conv bias and/or this image's noise embedding) in shared memory while the
-        // accumulators are still being produced
+        // park the bias values of this warp's chunks (conv bias and/or this image's noise embedding) in shared memory
+        // while the accumulators are still being produced
         const float* cb = nbias ? nbias + (long long)n * p.e.nbs : p.e.bias;
         if (cb && !(p.variant & 1)) {
-          bias_smem = smem_u32(smem_bias + (warp - kFirstEpiWarp) * 256);
-          if (lane < 16) {
-            float4 b = __ldg(reinterpret_cast<const float4*>(cb + nt * BN + ci * 64) + lane);
+          have_bias = true;
+          const int k = lane >> 4;   // lanes 0-15 park the first chunk, 16-31 the second (if the warp has one)
+          const int ci = c_first + k * c_step;
+          if (ci < nC) {
+            float4 b = __ldg(reinterpret_cast<const float4*>(cb + nt * BN + ci * 64) + (lane & 15));
             if (nbias && p.e.bias) {
-              const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.e.bias + nt * BN + ci * 64) + lane);
+              const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.e.bias + nt * BN + ci * 64) + (lane & 15));
               b.x += b2.x, b.y += b2.y, b.z += b2.z, b.w += b2.w;
             }
-            sts128(bias_smem + lane * 16, make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
+            sts128(bias_base + k * 256 + (lane & 15) * 16,
+                   make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
           }
           __syncwarp();
         }
@@ -400,22 +446,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t taddr = tmem_base + acc * (MT * BN) + ((uint32_t)(quarter * 32) << 16);
       if (p.variant & 1) {
       } else if constexpr (nC >= 1) {
+        static_assert(nC <= 4, "an epilogue warp parks the bias of at most two chunks");
         const uint32_t stage = smem_u32(smem_stage + (warp - kFirstEpiWarp) * 4096);
-        const int co0 = nt * BN + ci * 64;
-        // residual layers: this lane's element of the tile in the residual tensor (same lattice as the output)
         const long long xstep = (long long)p.oscale * p.e.Cout, pitch = (long long)p.oscale * p.e.W * p.e.Cout;
-        const bf16* resid_lane = nullptr;
-        if (p.e.resid) {
-          const long long m_q = ((long long)n * p.e.H + p.oscale * (ty0 + quarter * 4) + p.oy) * p.e.W + p.oscale * tx0 + p.ox;
-          resid_lane = p.e.resid + m_q * p.e.Cout + (lane >> 3) * xstep + co0 + (lane & 7) * 8;
-        }
-        float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-        for (int s = s_first; s < MT; s += s_step)
-          epilogue_tma64(p.e, &tmO, bias_smem, taddr + s * BN + ci * 64, lane, stage, co0, tx0 + 8 * s, ty0 + quarter * 4, n,
-                         resid_lane ? resid_lane + 8 * s * xstep : nullptr, pitch, 4 * xstep, st);
-        if (p.e.stats)
-          stats_store(p.e, n, p.slot_base + r * (by_chunk ? 4 : 8) + quarter + (by_chunk ? 0 : 4 * half), co0, lane, st);
+        for (int ci = c_first, k = 0; ci < nC; ci += c_step, ++k) {
+          const int co0 = nt * BN + ci * 64;
+          // residual layers: this lane's element of the tile in the residual tensor (same lattice as the output)
+          const bf16* resid_lane = nullptr;
+          if (p.e.resid) {
+            const long long m_q = ((long long)n * p.e.H + p.oscale * (ty0 + quarter * 4) + p.oy) * p.e.W + p.oscale * tx0 + p.ox;
+            resid_lane = p.e.resid + m_q * p.e.Cout + (lane >> 3) * xstep + co0 + (lane & 7) * 8;
+          }
+          float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+          for (int s = s_first; s < MT; s += s_step)
+            epilogue_tma64(p.e, &tmO, have_bias ? bias_base + k * 256 : 0u, taddr + s * BN + ci * 64, lane, stage, co0, tx0 + 8 * s,
+                           ty0 + quarter * 4, n, resid_lane ? resid_lane + 8 * s * xstep : nullptr, pitch, 4 * xstep, st);
+          if (p.e.stats)
+            stats_store(p.e, n, p.slot_base + r * (by_chunk ? 4 : 8) + quarter + (by_chunk ? 0 : 4 * half), co0, lane, st);
+        }
       } else {
 #pragma unroll 1
         for (int s = half; s < MT; s += 2) {
@@ -431,7 +481,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (lane == 0) {   // the issuer (of the pair's leader) may overwrite this accumulator buffer
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(smem_u32(&tempty_bar[acc]));
+      }
       if (++acc == 2) acc = 0, acc_phase ^= 1;
     }
     if (lane == 0) tma_store_wait_all();   // the staging tiles must outlive the stores reading them
@@ -440,15 +493,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // neither CTA may leave while the other can still signal it or read its smem
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
-// (MT, BN) for an op, or MT = 0 when the halo kernel does not apply.
-void pick_shape(const ConvOp& op, int* MT, int* BN) {
-  *MT = 0, *BN = 0;
+// (MT, BN) for an op, or MT = 0 when the halo kernel does not apply; *pair = run it on CTA pairs (cta_group::2).
+void pick_shape(const ConvOp& op, int* MT, int* BN, bool* pair) {
+  *MT = 0, *BN = 0, *pair = false;
   if (op.stride != 1 || op.up) return;
   // 1x1 convs with a short K (one or two 64-channel chunks) are per-tile-overhead bound in the per-tap kernel; here
   // they run as the centre tap alone over 4x larger tiles.  Longer-K 1x1 convs stay with the per-tap kernel, whose
@@ -456,10 +511,21 @@ void pick_shape(const ConvOp& op, int* MT, int* BN) {
   if (op.ksize == 1 && (op.src[0].C + op.src[1].C > 2 * kBK || op.rsrc[0].C || op.up_parity >= 0)) return;
   if (op.ksize != 3 && op.ksize != 1) return;
   if (op.Hin % kRows) return;
-  if (op.Cout % 128 == 0 && op.Win % 16 == 0) {
-    *MT = 2, *BN = 128;
-  } else if (op.Cout % 64 == 0 && op.Win % 32 == 0 && !(host().variant & 16)) {
-    *MT = 4, *BN = 64;
+  // CTA pairs need an even number of pixel tiles (the two CTAs take tiles 2q and 2q+1).  Only the N = 256 pair tile is
+  // on by default: its MMAs run at the tensor pipe's full rate (128 clk) where the single-CTA N = 128 tile is capped at
+  // ~90 clk per 128x128x16 by shared-memory operand bandwidth (deep layers 1.13 -> 1.35 PFLOP/s).  The N = 128 and
+  // N = 64 pair tiles gain 12 % / 28 % in the MMA micro-benchmark but measured 15-25 % SLOWER end to end (the pair
+  // advances at the pace of its slower CTA on every chunk); variant bits 64 / 128 switch them on for A/B runs, bit 32
+  // switches the N = 256 pair off.
+  const int var = host().variant ^ (64 | 128);
+  auto even_tiles = [&](int mt) { return (((long long)op.N * (op.Hin / kRows) * (op.Win / (8 * mt))) & 1) == 0; };
+  const bool pair_ok = op.ksize == 3 && host().pairs_ok;
+  if (op.Cout % 256 == 0 && op.Win % 8 == 0 && pair_ok && !(var & 32) && even_tiles(1)) {
+    *MT = 1, *BN = 256, *pair = true;   // N = 256 is the only shape whose MMAs run at the tensor pipe's full rate
+  } else if (op.Cout % 128 == 0 && op.Win % 16 == 0) {
+    *MT = 2, *BN = 128, *pair = pair_ok && !(var & 64) && even_tiles(2);
+  } else if (op.Cout % 64 == 0 && op.Win % 32 == 0 && !(var & 16)) {
+    *MT = 4, *BN = 64, *pair = pair_ok && !(var & 128) && even_tiles(4);
   } else if (op.Cout % 64 == 0 && op.Win % 16 == 0) {
     // narrow tile with three halo stages: also the test knob (variant bit 16) for the 32-multiple widths, where it
     // measured 10-30 % slower than <4,64> (half the weight-tile reuse, twice the per-tile overhead)
@@ -469,9 +535,9 @@ void pick_shape(const ConvOp& op, int* MT, int* BN) {
   }
 }
 
-template <int MT, int BN, int NT>
+template <int MT, int BN, int NT, bool PAIR>
 int launch(const ConvOp& op, cudaStream_t stream) {
-  using C = HCfg<MT, BN>;
+  using C = HCfg<MT, BN, PAIR>;
   HaloP p;
   p.tiles_x = op.Win / (8 * MT);
   p.tiles_y = op.Hin / kRows;
@@ -485,7 +551,7 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   p.err = host().err_flag;
   p.dbg = host().halo_dbg;
   p.Hin = op.Hin, p.Win = op.Win, p.gn_ab = op.gn_ab, p.gn_swish = op.gn_swish;
-  p.variant = host().variant;
+  p.variant = host().variant & 7;
   p.dy0 = p.dx0 = NT == 1 ? 1 : 0, p.kb0 = 0, p.oscale = 1, p.oy = p.ox = 0, p.slot_base = 0;
   if (op.up_parity >= 0) {
     const int py = op.up_parity >> 1, px = op.up_parity & 1;
@@ -503,34 +569,59 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   if (p.rchunks0) HSIDM_TRY(encode_act_map(&tmR0, op.rsrc[0].p, op.N, op.Hin, op.Win, op.rsrc[0].C, C::kPW, kHaloRows, 1));
   if (p.rchunks1) HSIDM_TRY(encode_act_map(&tmR1, op.rsrc[1].p, op.N, op.Hin, op.Win, op.rsrc[1].C, C::kPW, kHaloRows, 1));
   const int K = op.K();
-  HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, BN));
+  HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, C::kBRows));
   CUtensorMap tmO = tmB;   // the BN = 16 instantiation (fp32 NCHW output) stores from registers and never reads it
   if (BN % 64 == 0) HSIDM_TRY(encode_out_map(&tmO, op.out, op.N, op.Hout, op.Wout, op.Cout, p.oscale, p.oy, p.ox));
-  const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
-  char tag[112];
-  snprintf(tag, sizeof(tag), "halo MT%d BN%d cin%d+%d cout%d %dx%d n%d%s%s%s%s%s", MT, BN, op.src[0].C, op.src[1].C, op.Cout, op.Hin, op.Win, op.N,
-           op.resid ? " +res" : "", op.nbias ? " +nb" : "", op.stats_out ? " +st" : "", op.up_parity >= 0 ? " up2x" : "", op.gn_ab ? " +gn" : "");
+  char tag[120];
+  snprintf(tag, sizeof(tag), "halo%s MT%d BN%d cin%d+%d cout%d %dx%d n%d%s%s%s%s%s", PAIR ? "2" : "", MT, BN, op.src[0].C, op.src[1].C, op.Cout,
+           op.Hin, op.Win, op.N, op.resid ? " +res" : "", op.nbias ? " +nb" : "", op.stats_out ? " +st" : "", op.up_parity >= 0 ? " up2x" : "",
+           op.gn_ab ? " +gn" : "");
   // algorithmic FLOPs: for the sub-pixel form, the share of the reference's 3x3 conv over the upsampled tensor
   const double flops = op.up_parity >= 0 ? 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * 9 * (op.src[0].C + op.src[1].C)
                                          : 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * K;
   ProfScope prof(PROF_CONV_TC, flops, stream, tag);
-  conv_halo_kernel<MT, BN, NT><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmR0, tmR1, tmB, tmO, p);
+  if constexpr (PAIR) {
+    // one cluster of two CTAs per pair of adjacent pixel tiles; an even grid of at most one CTA per SM
+    const int pairs = std::min((p.m_tiles / 2) * p.n_tiles, host().num_sms / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = C::kSmemBytes, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    HSIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<MT, BN, NT, true>, tmA0, tmA1, tmR0, tmR1, tmB, tmO, p));
+  } else {
+    const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
+    conv_halo_kernel<MT, BN, NT, false><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmR0, tmR1, tmB, tmO, p);
+  }
   return after_launch("conv_halo_kernel");
+}
+
+template <int MT, int BN, int NT, bool PAIR>
+int set_smem() {
+  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<MT, BN, NT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<MT, BN, PAIR>::kSmemBytes));
+  return HSIDM_OK;
 }
 
 }  // namespace
 
 int conv_halo_init() {
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 128, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 128>::kSmemBytes));
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 128>::kSmemBytes));
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 128>::kSmemBytes));
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 64>::kSmemBytes));
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 64, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 64>::kSmemBytes));
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 64>::kSmemBytes));
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<2, 64>::kSmemBytes));
-  HSIDM_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, 16, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<4, 16>::kSmemBytes));
+  HSIDM_TRY((set_smem<2, 128, 9, false>()));
+  HSIDM_TRY((set_smem<2, 128, 4, false>()));
+  HSIDM_TRY((set_smem<2, 128, 1, false>()));
+  HSIDM_TRY((set_smem<4, 64, 9, false>()));
+  HSIDM_TRY((set_smem<4, 64, 4, false>()));
+  HSIDM_TRY((set_smem<4, 64, 1, false>()));
+  HSIDM_TRY((set_smem<2, 64, 9, false>()));
+  HSIDM_TRY((set_smem<2, 64, 4, false>()));
+  HSIDM_TRY((set_smem<2, 64, 1, false>()));
+  HSIDM_TRY((set_smem<4, 16, 9, false>()));
+  HSIDM_TRY((set_smem<1, 256, 9, true>()));
+  HSIDM_TRY((set_smem<1, 256, 4, true>()));
+  HSIDM_TRY((set_smem<2, 128, 9, true>()));
+  HSIDM_TRY((set_smem<2, 128, 4, true>()));
+  HSIDM_TRY((set_smem<4, 64, 9, true>()));
+  HSIDM_TRY((set_smem<4, 64, 4, true>()));
   return HSIDM_OK;
 }
 
@@ -538,7 +629,8 @@ void conv_halo_set_timing(long long* device_counters) { tc::host().halo_dbg = de
 
 int conv_halo_stats_slots(const ConvOp& op) {
   int MT, BN;
-  pick_shape(op, &MT, &BN);
+  bool pair;
+  pick_shape(op, &MT, &BN, &pair);
   if (MT == 0 || BN % 64 || op.out_layout != L_NHWC) return 0;
   const int tpi = (op.Win / (8 * MT)) * (op.Hin / kRows);
   return tpi * (BN / 64 >= 2 ? 4 : 8) * (op.up_parity >= 0 ? 4 : 1);
@@ -547,7 +639,8 @@ int conv_halo_stats_slots(const ConvOp& op) {
 // Assumes conv_tc_supported(op) already holds (bf16 NHWC sources with 64-multiple channels, Cout fits an N tile).
 bool conv_halo_supported(const ConvOp& op) {
   int MT, BN;
-  pick_shape(op, &MT, &BN);
+  bool pair;
+  pick_shape(op, &MT, &BN, &pair);
   if (MT == 0) return false;
   for (int i = 0; i < 2; ++i)
     if (op.rsrc[i].C && (op.rsrc[i].C % kBK || op.rsrc[i].layout != L_NHWC)) return false;
@@ -558,12 +651,22 @@ bool conv_halo_supported(const ConvOp& op) {
 
 int conv_halo(const ConvOp& op, cudaStream_t stream) {
   int MT, BN;
-  pick_shape(op, &MT, &BN);
+  bool pair;
+  pick_shape(op, &MT, &BN, &pair);
   const bool sub = op.up_parity >= 0, one = op.ksize == 1;
-  if (MT == 2 && BN == 128) return one ? launch<2, 128, 1>(op, stream) : sub ? launch<2, 128, 4>(op, stream) : launch<2, 128, 9>(op, stream);
-  if (MT == 2 && BN == 64) return one ? launch<2, 64, 1>(op, stream) : sub ? launch<2, 64, 4>(op, stream) : launch<2, 64, 9>(op, stream);
-  if (MT == 4 && BN == 64) return one ? launch<4, 64, 1>(op, stream) : sub ? launch<4, 64, 4>(op, stream) : launch<4, 64, 9>(op, stream);
-  if (MT == 4 && BN == 16 && !sub && !one) return launch<4, 16, 9>(op, stream);
+  if (pair) {
+    if (MT == 1 && BN == 256) return sub ? launch<1, 256, 4, true>(op, stream) : launch<1, 256, 9, true>(op, stream);
+    if (MT == 2 && BN == 128) return sub ? launch<2, 128, 4, true>(op, stream) : launch<2, 128, 9, true>(op, stream);
+    if (MT == 4 && BN == 64) return sub ? launch<4, 64, 4, true>(op, stream) : launch<4, 64, 9, true>(op, stream);
+  } else {
+    if (MT == 2 && BN == 128)
+      return one ? launch<2, 128, 1, false>(op, stream) : sub ? launch<2, 128, 4, false>(op, stream) : launch<2, 128, 9, false>(op, stream);
+    if (MT == 2 && BN == 64)
+      return one ? launch<2, 64, 1, false>(op, stream) : sub ? launch<2, 64, 4, false>(op, stream) : launch<2, 64, 9, false>(op, stream);
+    if (MT == 4 && BN == 64)
+      return one ? launch<4, 64, 1, false>(op, stream) : sub ? launch<4, 64, 4, false>(op, stream) : launch<4, 64, 9, false>(op, stream);
+    if (MT == 4 && BN == 16 && !sub && !one) return launch<4, 16, 9, false>(op, stream);
+  }
   HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_halo: unsupported shape");
 }
 

@@ -391,7 +391,8 @@ int pick_bn(int Cout) {
 int conv_tc_init() {
   std::call_once(g_once, [] {
     g_init_status = do_init();
-    if (std::getenv("HSIDM_NO_HALO")) tc::host().no_halo = 1;   // A/B switch for profiling runs
+    if (std::getenv("HSIDM_NO_HALO")) tc::host().no_halo = 1;   // A/B switches for profiling runs
+    if (std::getenv("HSIDM_NO_PAIRS")) tc::host().pairs_ok = 0;
   });
   return g_init_status;
 }

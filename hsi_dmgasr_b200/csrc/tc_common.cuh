@@ -108,6 +108,54 @@ static __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[1
 }
 static __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pair (cta_group::2): two CTAs of a cluster issue one M = 256 MMA over both halves ----
+static __device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+static __device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+static __device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+static __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+static __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+static __device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+static __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far arrives on the barrier at this offset in BOTH CTAs of the pair
+static __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// 2-D TMA load into THIS CTA's shared memory whose bytes complete on a barrier of the pair's leader (cluster address)
+static __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row groups are 1024 B apart (SBO), LBO unused (=1),
 // descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
 static __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -539,6 +587,7 @@ struct Host {
   int* err_flag = nullptr;
   int no_halo = 0;           // test knob: 1 -> always use the per-tap kernel of conv_tc.cu
   int variant = 0;           // test knob: kernel-variant selector for A/B runs (0 = default routing)
+  int pairs_ok = 1;          // HSIDM_NO_PAIRS=1 (or a device without cluster launch) keeps every conv on single CTAs
   long long* halo_dbg = nullptr;   // developer timing probe of the halo kernel (device buffer, 8 counters per CTA)
 };
 Host& host();

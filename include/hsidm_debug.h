@@ -27,7 +27,8 @@ HSIDM_API int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const
 /* Kernel-selection knobs for A/B tests: no_halo = 1 forces the per-tap tcgen05 kernel for every 3x3 conv;
  * variant is a bit mask of developer switches (0 = the production routing): 1, 2, 4 = timing experiments that skip the
  * epilogue / weight loads / halo loads (results invalid); 8 = GroupNorm through a normalised copy instead of fused into
- * the consuming convolution's load path; 16 = 64-output-channel convs on the narrow <2,64> halo tile instead of <4,64>. */
+ * the consuming convolution's load path; 16 = 64-output-channel convs on the narrow <2,64> halo tile instead of <4,64>;
+ * 32 = no CTA-pair (cta_group::2) tile for Cout % 256 == 0; 64 / 128 = CTA-pair tiles also for the 128- / 64-channel tiles. */
 HSIDM_API int hsidm_debug_conv_mode(int no_halo, int variant);
 
 /* Developer probe: when device_counters is non-null every halo-kernel launch writes 8 int64 cycle counters per CTA
