@@ -75,6 +75,8 @@ SIGNATURES = {
                                      _P, _P, C.c_int]),
     "hsidm_debug_groupnorm": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
                                         C.c_float, C.c_int, _P]),
+    "hsidm_bicubic_upsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hsidm_quality_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hsidm_debug_conv_mode": (C.c_int, [C.c_int, C.c_int]),
     "hsidm_debug_halo_timing": (C.c_int, [C.c_void_p]),
     "hsidm_debug_tc_error_flag": (C.c_int, [C.POINTER(C.c_int)]),

@@ -1,5 +1,7 @@
 // Library-level C ABI entry points and the test hooks of include/hsidm_debug.h.
 #include "../../include/hsidm_debug.h"
+#include <algorithm>
+
 #include "net.cuh"
 
 using namespace hsidm;
@@ -100,6 +102,30 @@ int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const void* x1,
     set_last_error("kernel failed: %s", cudaGetErrorString(e));
     s = HSIDM_CUDA_ERROR;
   }
+  return s;
+}
+
+int hsidm_bicubic_upsample(const float* lr, float* sr, int N, int C, int h, int w, int scale, int clamp01, hsidm_stream stream) {
+  if (!lr || !sr) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_bicubic_upsample: null argument");
+  if (N <= 0 || C <= 0) HSIDM_FAIL(HSIDM_BAD_SHAPE, "hsidm_bicubic_upsample: bad batch %d x %d", N, C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // (image, band) planes go along gridDim.y: at most 65535 per launch
+  const long long planes = (long long)N * C;
+  for (long long p0 = 0; p0 < planes; p0 += 65535) {
+    const int cnt = (int)std::min<long long>(65535, planes - p0);
+    HSIDM_TRY(bicubic_upsample(lr + p0 * h * w, sr + p0 * (long long)h * scale * w * scale, cnt, h, w, scale, clamp01, st));
+  }
+  return HSIDM_OK;
+}
+
+int hsidm_quality_metrics(const float* truth, const float* pred, int N, int C, int H, int W, float* out, hsidm_stream stream) {
+  if (!truth || !pred || !out) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_quality_metrics: null argument");
+  if (H <= 0 || W <= 0) HSIDM_FAIL(HSIDM_BAD_SHAPE, "hsidm_quality_metrics: bad image size %dx%d", H, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* scratch = nullptr;
+  HSIDM_CUDA(cudaMallocAsync(&scratch, (size_t)quality_metrics_scratch_bytes(N, C, H * W), st));
+  const int s = quality_metrics(truth, pred, N, C, H * W, 1.0f, scratch, out, st);
+  HSIDM_CUDA(cudaFreeAsync(scratch, st));
   return s;
 }
 

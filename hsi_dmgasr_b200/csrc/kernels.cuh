@@ -128,6 +128,12 @@ int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int 
              const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream);
 
 int upsample2x(const void* x, void* out, int N, int H, int W, int C, int prec, cudaStream_t stream);
+
+// prepost.cu : bicubic pre-upsampling of NCHW fp32 planes and the per-cube MPSNR / SAM metrics
+int bicubic_upsample(const float* src, float* dst, int planes, int h, int w, int scale, int clamp01, cudaStream_t stream);
+int64_t quality_metrics_scratch_bytes(int N, int C, int HW);
+int quality_metrics(const float* truth, const float* pred, int N, int C, int HW, float data_range, void* scratch, float* out,
+                    cudaStream_t stream);
 // 3x3/pad-1 im2col of up to two NCHW fp32 sources with 9*(C0+C1) <= 64 into [N,H,W,64] bf16 rows (k = tap*(C0+C1) + c,
 // zero padded): lets the first UNet conv (6 -> 64) run as a K = 64 tensor-core GEMM.
 int im2col_small(const float* x0, int C0, const float* x1, int C1, void* out, int N, int H, int W, cudaStream_t stream);

@@ -55,6 +55,13 @@ class SRPipeline:
         return (y, lat) if return_latents else y
 
     @torch.no_grad()
+    def super_resolve_lr(self, lr: torch.Tensor, scale: int = 4, **kw):
+        """From the LOW-RESOLUTION cubes [B,C,h,w] on the GPU: the dataset code's bicubic x`scale` pre-upsampling and clamp
+        (sr_gae.py:72, HStest.py:59-60) run on the device (prepost.bicubic_upsample), then `super_resolve`."""
+        from . import prepost
+        return self.super_resolve(prepost.bicubic_upsample(lr, scale, clamp01=True), **kw)
+
+    @torch.no_grad()
     def super_resolve_host(self, sr_host: torch.Tensor, device: torch.device, **kw) -> torch.Tensor:
         """End-to-end call with HOST buffers: pinned H2D of the cubes, the pipeline, D2H of the result."""
         if sr_host.is_cuda:

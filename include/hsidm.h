@@ -169,6 +169,20 @@ HSIDM_API int hsidm_gae_encode(hsidm_gae* gae, const float* x, float* z, int B, 
  * through the residual trunk. clamp01 != 0 additionally applies the driver's clamp to [0,1] (sr_gae.py:474-475). */
 HSIDM_API int hsidm_gae_decode(hsidm_gae* gae, const float* z, float* y, int B, int H, int W, int clamp01, hsidm_stream stream);
 
+/* ---- the steps either side of the path ------------------------------------------------------------ */
+
+/* Bicubic x`scale` pre-upsampling of the low-resolution cube, NCHW fp32 on the device: replaces
+ * torch.nn.functional.interpolate(img_LR, scale_factor=4, mode='bicubic') (sr_gae.py:72, :118).  PyTorch's convention:
+ * align_corners=False, A = -0.75, border indices clamped.  lr [N,C,h,w] -> sr [N,C,h*scale,w*scale]; clamp01 != 0 also
+ * applies the dataset's clamp to [0,1] (HStest.py:59-60). */
+HSIDM_API int hsidm_bicubic_upsample(const float* lr, float* sr, int N, int C, int h, int w, int scale, int clamp01, hsidm_stream stream);
+
+/* Per-cube validation metrics on the device, after the driver's clamp of both cubes to [0,1] (sr_gae.py:474-475):
+ * out[n] = (MPSNR in dB with data_range 1 - eval_hsi.py:110-121, SAM in degrees - eval_hsi.py:47-65).
+ * truth / pred: [N,C,H,W] fp32 device pointers; out: [N][2] fp32 device pointer.  Deterministic (fixed-order folds in
+ * float64); allocates its scratch with cudaMallocAsync on `stream`. */
+HSIDM_API int hsidm_quality_metrics(const float* truth, const float* pred, int N, int C, int H, int W, float* out, hsidm_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -360,3 +360,22 @@ def sam_deg(x_true: np.ndarray, x_pred: np.ndarray) -> float:
     # the reference lets arccos produce nan for |cos|>1 by rounding; clip only by 1 ulp to stay defined
     ang = np.arccos(np.clip(cos, -1.0, 1.0))
     return float(ang.sum() / ok.sum() * 180.0 / np.pi)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the steps either side of the path
+def bicubic_pre_upsample(lr: torch.Tensor, scale: int = 4) -> torch.Tensor:
+    """The dataset code's pre-upsampling, verbatim call (sr_gae.py:72, :118): torch bicubic, align_corners=False."""
+    return torch.nn.functional.interpolate(lr, scale_factor=scale, mode="bicubic")
+
+
+def cube_metrics(truth: torch.Tensor, pred: torch.Tensor):
+    """Per-cube (MPSNR, SAM) of NCHW batches the way the validation loop computes them: clamp to [0,1], HWC, then
+    compare_mpsnr / compare_sam (sr_gae.py:474-475, eval_hsi.py:110-121, :47-65)."""
+    out = []
+    for t, p in zip(truth, pred):
+        th = t.clamp(0, 1).permute(1, 2, 0).numpy()
+        ph = p.clamp(0, 1).permute(1, 2, 0).numpy()
+        out.append((mpsnr(th, ph), sam_deg(th, ph)))
+    return out
+
