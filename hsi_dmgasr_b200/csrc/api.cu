@@ -41,6 +41,7 @@ int hsidm_debug_conv2d(int backend, int precision, const void* src0, int c0, con
   if (precision == HSIDM_BF16) HSIDM_TRY(conv_tc_init());
   int s = pack_conv(ps, w, precision == HSIDM_BF16);
   if (s == HSIDM_OK && up && precision == HSIDM_BF16) s = pack_conv_up(ps, w);
+  if (s == HSIDM_OK && stride == 2 && precision == HSIDM_BF16) s = pack_conv_s2(ps, w);
   if (s != HSIDM_OK) {
     free_conv(w);
     return s;

@@ -126,9 +126,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
-    if (p.chunks1) tma_prefetch_desc(&tmA1);
-    if (p.rchunks0) tma_prefetch_desc(&tmR0);
-    if (p.rchunks1) tma_prefetch_desc(&tmR1);
+    if (p.chunks1 || NT == 0) tma_prefetch_desc(&tmA1);
+    if (p.rchunks0 || NT == 0) tma_prefetch_desc(&tmR0);
+    if (p.rchunks1 || NT == 0) tma_prefetch_desc(&tmR1);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
     for (int s = 0; s < C::kAStages; ++s)
@@ -168,7 +168,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const uint32_t dst = smem_u32(smem + as * C::kAStage);
           if (p.variant & 4) { mbar_arrive(fb); if (++as == C::kAStages) as = 0, aph ^= 1; continue; }
           mbar_expect_tx(fb, C::kABox);
-          if (ch < p.chunks0)
+          if constexpr (NT == 0) {
+            // stride-2 form: chunk = (phase, channel block); the four maps are the phase lattices (1,1) (1,0) (0,1) (0,0)
+            const int cpp = chunks >> 2, ph = ch / cpp;
+            const CUtensorMap* map = ph == 0 ? &tmA0 : ph == 1 ? &tmA1 : ph == 2 ? &tmR0 : &tmR1;
+            tma_load_4d(dst, map, fb, (ch - ph * cpp) * kBK, x0 - 1, y0 - 1, n);
+          } else if (ch < p.chunks0)
             tma_load_4d(dst, &tmA0, fb, ch * kBK, x0 - 1, y0 - 1, n);
           else if (ch < chunks)
             tma_load_4d(dst, &tmA1, fb, (ch - p.chunks0) * kBK, x0 - 1, y0 - 1, n);
@@ -209,6 +214,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       };
       for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
         const int nt = tile % p.n_tiles;
+        if constexpr (NT == 0) {   // stride-2 form: weights are packed in consumption order, 9 k-blocks per channel block
+          for (int kb = 0; kb < 9 * (chunks >> 2) && ok; ++kb) load_b(kb, nt);
+        }
         for (int ch = 0; ch < chunks && ok; ++ch)
           for (int tap = 0; tap < NT && ok; ++tap) load_b(p.kb0 + tap * chunks + ch, nt);
         for (int rc = 0; rc < rchunks && ok; ++rc) load_b(p.kb0 + NT * chunks + rc, nt);   // shortcut columns follow the 3x3 ones
@@ -252,21 +260,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           ok = timed_wait(smem_u32((PAIR || p.gn_ab) ? &a_ready[as] : &a_full[as]), aph, p.err, 3, p.dbg, w_af);
           if (!ok) break;
           const uint64_t adesc0 = desc_hi | (uint64_t)((smem_u32(smem + as * C::kAStage) + tap0) >> 4);
-#pragma unroll
-          for (int tap = 0; tap < NT; ++tap) {
+          // one tap: (group barrier) -> MT*4 MMAs from the halo tile at byte offset `off` -> release the weight stage
+          auto tap_body = [&](int off, bool first) {
             if (gcnt == 0) {
               ok = timed_wait(smem_u32(&b_full[grp]), gph, p.err, 6, p.dbg, w_bf);
-              if (!ok) break;
+              if (!ok) return;
               tc_fence_after();
             }
             const uint64_t bdesc = bdesc_hi | (uint64_t)(b_lo + bs * (C::kBStage >> 4));
-            const int kTapOff = ((tap / TW) * C::kPW + tap % TW) * 128;   // halo coordinates of this tap (constant once unrolled)
 #pragma unroll
             for (int s = 0; s < MT; ++s) {
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k)
-                mma(d_tmem + s * BN, adesc0 + (uint64_t)((kTapOff + s * 1024) / 16 + 2 * k), bdesc + 2 * k,
-                    (tap | k) ? 1u : (ch ? 1u : 0u));
+                mma(d_tmem + s * BN, adesc0 + (uint64_t)((off + s * 1024) / 16 + 2 * k), bdesc + 2 * k, (first && k == 0) ? 0u : 1u);
             }
             commit(smem_u32(&b_empty[bs]));
             if (++bs == C::kBStages) bs = 0;
@@ -274,6 +280,32 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               gcnt = 0;
               if (++grp == C::kBGroups) grp = 0, gph ^= 1;
             }
+          };
+          if constexpr (NT == 0) {
+            // stride-2 3x3 conv over the four phase lattices of the input: phase (py,px) serves the taps whose source
+            // row/column has that parity, at lattice offsets -1 / 0 (halo coordinates 0 / 1)
+            constexpr int R = C::kPW * 128, X = 128;
+            const int ph = ch / (chunks >> 2);
+            if (ph == 0) {          // (1,1): taps (ky,kx) in {0,2}x{0,2}
+              tap_body(0, ch == 0);
+              if (ok) tap_body(X, false);
+              if (ok) tap_body(R, false);
+              if (ok) tap_body(R + X, false);
+            } else if (ph == 1) {   // (1,0): ky in {0,2}, kx = 1
+              tap_body(X, false);
+              if (ok) tap_body(R + X, false);
+            } else if (ph == 2) {   // (0,1): ky = 1, kx in {0,2}
+              tap_body(R, false);
+              if (ok) tap_body(R + X, false);
+            } else {                // (0,0): the centre tap
+              tap_body(R + X, false);
+            }
+            if (!ok) break;
+          }
+#pragma unroll
+          for (int tap = 0; tap < NT; ++tap) {
+            tap_body(((tap / TW) * C::kPW + tap % TW) * 128, tap == 0 && ch == 0);   // halo offset: constant once unrolled
+            if (!ok) break;
           }
           commit(smem_u32(&a_empty[as]));
           if (++as == C::kAStages) as = 0, aph ^= 1;
@@ -519,7 +551,8 @@ void pick_shape(const ConvOp& op, int* MT, int* BN, bool* pair) {
   // switches the N = 256 pair off.
   const int var = host().variant ^ (64 | 128);
   auto even_tiles = [&](int mt) { return (((long long)op.N * (op.Hin / kRows) * (op.Win / (8 * mt))) & 1) == 0; };
-  const bool pair_ok = op.ksize == 3 && host().pairs_ok;
+  const bool pair_ok = op.ksize == 3 && !op.s2 && host().pairs_ok;
+  if (op.s2 && (op.ksize != 3 || op.src[1].C || op.rsrc[0].C || op.up_parity >= 0 || op.gn_ab)) return;
   if (op.Cout % 256 == 0 && op.Win % 8 == 0 && pair_ok && !(var & 32) && even_tiles(1)) {
     *MT = 1, *BN = 256, *pair = true;   // N = 256 is the only shape whose MMAs run at the tensor pipe's full rate
   } else if (op.Cout % 128 == 0 && op.Win % 16 == 0) {
@@ -530,7 +563,7 @@ void pick_shape(const ConvOp& op, int* MT, int* BN, bool* pair) {
     // narrow tile with three halo stages: also the test knob (variant bit 16) for the 32-multiple widths, where it
     // measured 10-30 % slower than <4,64> (half the weight-tile reuse, twice the per-tile overhead)
     *MT = 2, *BN = 64;
-  } else if (op.Cout <= 16 && op.Win % 32 == 0 && op.ksize == 3) {
+  } else if (op.Cout <= 16 && op.Win % 32 == 0 && op.ksize == 3 && !op.s2) {
     *MT = 4, *BN = 16;
   }
 }
@@ -560,12 +593,24 @@ int launch(const ConvOp& op, cudaStream_t stream) {
     p.slot_base = op.up_parity * (p.tiles_x * p.tiles_y * (BN / 64 >= 2 ? 4 : 8));
   }
   CUtensorMap tmA0, tmA1, tmB;
+  if (NT == 0) {
+    // stride-2 form: every 64-channel block is visited once per phase lattice; the four maps are the phases
+    // (1,1) (1,0) (0,1) (0,0) of the full-resolution source
+    p.chunks0 = 4 * (op.src[0].C / kBK);
+    HSIDM_TRY(encode_phase_map(&tmA0, op.src[0].p, op.N, 2 * op.Hin, 2 * op.Win, op.src[0].C, 1, 1, C::kPW, kHaloRows));
+    HSIDM_TRY(encode_phase_map(&tmA1, op.src[0].p, op.N, 2 * op.Hin, 2 * op.Win, op.src[0].C, 1, 0, C::kPW, kHaloRows));
+  } else
   HSIDM_TRY(encode_act_map(&tmA0, op.src[0].p, op.N, op.Hin, op.Win, op.src[0].C, C::kPW, kHaloRows, 1));
-  if (p.chunks1)
+  if (NT == 0) {
+  } else if (p.chunks1)
     HSIDM_TRY(encode_act_map(&tmA1, op.src[1].p, op.N, op.Hin, op.Win, op.src[1].C, C::kPW, kHaloRows, 1));
   else
     tmA1 = tmA0;
   CUtensorMap tmR0 = tmA0, tmR1 = tmA0;
+  if (NT == 0) {
+    HSIDM_TRY(encode_phase_map(&tmR0, op.src[0].p, op.N, 2 * op.Hin, 2 * op.Win, op.src[0].C, 0, 1, C::kPW, kHaloRows));
+    HSIDM_TRY(encode_phase_map(&tmR1, op.src[0].p, op.N, 2 * op.Hin, 2 * op.Win, op.src[0].C, 0, 0, C::kPW, kHaloRows));
+  }
   if (p.rchunks0) HSIDM_TRY(encode_act_map(&tmR0, op.rsrc[0].p, op.N, op.Hin, op.Win, op.rsrc[0].C, C::kPW, kHaloRows, 1));
   if (p.rchunks1) HSIDM_TRY(encode_act_map(&tmR1, op.rsrc[1].p, op.N, op.Hin, op.Win, op.rsrc[1].C, C::kPW, kHaloRows, 1));
   const int K = op.K();
@@ -574,7 +619,7 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   if (BN % 64 == 0) HSIDM_TRY(encode_out_map(&tmO, op.out, op.N, op.Hout, op.Wout, op.Cout, p.oscale, p.oy, p.ox));
   char tag[120];
   snprintf(tag, sizeof(tag), "halo%s MT%d BN%d cin%d+%d cout%d %dx%d n%d%s%s%s%s%s", PAIR ? "2" : "", MT, BN, op.src[0].C, op.src[1].C, op.Cout,
-           op.Hin, op.Win, op.N, op.resid ? " +res" : "", op.nbias ? " +nb" : "", op.stats_out ? " +st" : "", op.up_parity >= 0 ? " up2x" : "",
+           op.Hin, op.Win, op.N, op.resid ? " +res" : "", op.nbias ? " +nb" : "", op.stats_out ? " +st" : "", op.up_parity >= 0 ? " up2x" : op.s2 ? " s2" : "",
            op.gn_ab ? " +gn" : "");
   // algorithmic FLOPs: for the sub-pixel form, the share of the reference's 3x3 conv over the upsampled tensor
   const double flops = op.up_parity >= 0 ? 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * 9 * (op.src[0].C + op.src[1].C)
@@ -616,6 +661,9 @@ int conv_halo_init() {
   HSIDM_TRY((set_smem<2, 64, 4, false>()));
   HSIDM_TRY((set_smem<2, 64, 1, false>()));
   HSIDM_TRY((set_smem<4, 16, 9, false>()));
+  HSIDM_TRY((set_smem<2, 128, 0, false>()));
+  HSIDM_TRY((set_smem<4, 64, 0, false>()));
+  HSIDM_TRY((set_smem<2, 64, 0, false>()));
   HSIDM_TRY((set_smem<1, 256, 9, true>()));
   HSIDM_TRY((set_smem<1, 256, 4, true>()));
   HSIDM_TRY((set_smem<2, 128, 9, true>()));
@@ -658,6 +706,10 @@ int conv_halo(const ConvOp& op, cudaStream_t stream) {
     if (MT == 1 && BN == 256) return sub ? launch<1, 256, 4, true>(op, stream) : launch<1, 256, 9, true>(op, stream);
     if (MT == 2 && BN == 128) return sub ? launch<2, 128, 4, true>(op, stream) : launch<2, 128, 9, true>(op, stream);
     if (MT == 4 && BN == 64) return sub ? launch<4, 64, 4, true>(op, stream) : launch<4, 64, 9, true>(op, stream);
+  } else if (op.s2) {
+    if (MT == 2 && BN == 128) return launch<2, 128, 0, false>(op, stream);
+    if (MT == 4 && BN == 64) return launch<4, 64, 0, false>(op, stream);
+    if (MT == 2 && BN == 64) return launch<2, 64, 0, false>(op, stream);
   } else {
     if (MT == 2 && BN == 128)
       return one ? launch<2, 128, 1, false>(op, stream) : sub ? launch<2, 128, 4, false>(op, stream) : launch<2, 128, 9, false>(op, stream);

@@ -339,6 +339,19 @@ int encode_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int 
   return HSIDM_OK;
 }
 
+int encode_phase_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int py, int px, int bw, int bh) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(W / 2), (cuuint64_t)(H / 2), (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)2 * C * 2, (cuuint64_t)2 * W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const void* origin = static_cast<const bf16*>(base) + ((long long)py * W + px) * C;
+  CUresult r = host().encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(origin), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled(phase %d,%d of %dx%dx%dx%d) failed: %d", py, px, N, H, W, C, (int)r);
+  return HSIDM_OK;
+}
+
 int encode_out_map(CUtensorMap* map, void* base, int N, int H, int W, int C, int scale, int oy, int ox) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(W / scale), (cuuint64_t)(H / scale), (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)scale * C * 2, (cuuint64_t)scale * W * C * 2, (cuuint64_t)H * W * C * 2};
@@ -437,7 +450,7 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: op (Cin %d+%d, Cout %d, k%d s%d, %dx%d) does not fit the tensor-core kernel",
                op.src[0].C, op.src[1].C, op.Cout, op.ksize, op.stride, op.Hin, op.Win);
   if (!host().no_halo && conv_halo_supported(op)) return conv_halo(op, stream);
-  if (op.rsrc[0].C || op.rsrc[1].C || op.up_parity >= 0 || op.gn_ab)
+  if (op.rsrc[0].C || op.rsrc[1].C || op.up_parity >= 0 || op.gn_ab || op.s2)
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: fused shortcut sources / sub-pixel upsampling / fused input GroupNorm need the halo kernel, which does not take this shape");
   TcP p;
   tile_geometry(op.Hin, op.Win, &p.bw, &p.bh, &p.bn);

@@ -29,6 +29,9 @@ struct ConvOp {
   // (2i+py, 2j+px) as a 2x2-tap conv over the LOW-RES source with pre-summed weights (w_bf16 = [Cout][4 parities][4 taps][C]);
   // Hin/Win are the source size, Hout/Wout twice that.  2.25x fewer FLOPs and no upsampled tensor.
   int up_parity = -1;
+  // 1: stride-2 3x3 conv in its phase-lattice form (halo tensor-core kernel): src[0] is the FULL-RESOLUTION tensor
+  // [N, 2*Hin, 2*Win, C], Hin/Win = Hout/Wout are the output size, w_bf16 = ConvW::w_s2.  No im2col buffer.
+  int s2 = 0;
   int ksize = 3, stride = 1;    // padding = ksize/2
   int Hout = 0, Wout = 0, Cout = 0;
   const float* w_f32 = nullptr;  // [K][Cout], k = tap*(C0+C1) + c

@@ -124,6 +124,30 @@ __global__ void pack_up_kernel(const float* __restrict__ w, int Cout, int Cin, b
   }
 }
 
+// Stride-2 halo form: k-blocks in the order the kernel consumes them - for phase (py,px) in (1,1) (1,0) (0,1) (0,0), for
+// each 64-channel block, for each tap of that phase (lattice offsets in row-major order):
+//   phase parity 1 -> kernel rows/cols {0, 2} (offsets -1, 0), parity 0 -> {1} (offset 0).
+__global__ void pack_s2_kernel(const float* __restrict__ w, int Cout, int Cin, bf16* __restrict__ o) {
+  const int cpp = Cin / 64;
+  const int64_t K = 9LL * Cin, total = (int64_t)Cout * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i / K);
+    int kb = (int)((i % K) / 64);
+    const int c64 = (int)(i % 64);
+    // locate (phase, channel block, tap) of k-block kb: phases hold 4, 2, 2, 1 taps per channel block
+    const int per_phase[4] = {4, 2, 2, 1};
+    int ph = 0;
+    while (kb >= per_phase[ph] * cpp) kb -= per_phase[ph] * cpp, ++ph;
+    const int cb = kb / per_phase[ph], t = kb % per_phase[ph];
+    const int py = ph < 2 ? 1 : 0, px = (ph == 0 || ph == 2) ? 1 : 0;
+    const int ny = py ? 2 : 1, nx = px ? 2 : 1;        // taps along y / x for this phase
+    const int ty = t / nx, tx = t % nx;
+    const int ky = py ? 2 * ty : 1, kx = px ? 2 * tx : 1;
+    (void)ny;
+    o[i] = __float2bfloat16_rn(w[((int64_t)co * Cin + cb * 64 + c64) * 9 + ky * 3 + kx]);
+  }
+}
+
 // w[co][ci][tap] -> col[co*64 + tap*Cin + ci], zero padded to 64 columns
 __global__ void pack_col_kernel(const float* __restrict__ w, int Cout, int Cin, bf16* __restrict__ o) {
   const int total = Cout * 64;
@@ -144,7 +168,20 @@ void free_conv(ConvW& c) {
   if (c.w_bf16) cudaFree(c.w_bf16);
   if (c.w_col) cudaFree(c.w_col);
   if (c.w_up) cudaFree(c.w_up);
-  c.w_f32 = nullptr, c.w_bf16 = nullptr, c.w_col = nullptr, c.w_up = nullptr, c.packed_bytes = 0;
+  if (c.w_s2) cudaFree(c.w_s2);
+  c.w_f32 = nullptr, c.w_bf16 = nullptr, c.w_col = nullptr, c.w_up = nullptr, c.w_s2 = nullptr, c.packed_bytes = 0;
+}
+
+int pack_conv_s2(const ParamStore& ps, ConvW& c) {
+  const int bn = conv_tc_bn_rows(c.Cout);
+  if (c.ks != 3 || bn <= 0 || c.Cin % 64 || c.Cout % 64) return HSIDM_OK;
+  const int64_t rows = round_up(c.Cout, bn), K = 9LL * c.Cin;
+  if (c.w_s2) cudaFree(c.w_s2);
+  HSIDM_CUDA(cudaMalloc(&c.w_s2, sizeof(bf16) * rows * K));
+  HSIDM_CUDA(cudaMemset(c.w_s2, 0, sizeof(bf16) * rows * K));
+  c.packed_bytes += sizeof(bf16) * rows * K;
+  pack_s2_kernel<<<(unsigned)std::min<int64_t>(ceil_div(c.Cout * K, 256), 4096), 256>>>(ps.dev(c.pw), c.Cout, c.Cin, c.w_s2);
+  return after_launch("pack_s2_kernel");
 }
 
 int pack_conv_up(const ParamStore& ps, ConvW& c) {
@@ -233,7 +270,7 @@ int pack_fused(const ParamStore& ps, const ConvW& c2, const ConvW* rc, FusedW& f
 
 // ---- dispatcher -----------------------------------------------------------------------------------------------
 namespace {
-enum Route { R_TC, R_DOWN, R_UP, R_UP_SUBPIX, R_COL, R_SIMT };
+enum Route { R_TC, R_DOWN, R_DOWN_HALO, R_UP, R_UP_SUBPIX, R_COL, R_SIMT };
 
 // Decides how `op` runs and, for the lowered routes, fills `g` with the tensor-core op (its source pointer is patched
 // once the temporary exists).
@@ -254,7 +291,14 @@ Route plan_conv(const Exec& ex, const ConvOp& op, const ConvW& w, ConvOp* g) {
   if (conv_tc_supported(op, prec)) return R_TC;
   const bool nhwc1 = op.src[0].layout == L_NHWC && op.src[1].C == 0 && op.src[0].C % 64 == 0;
   if (nhwc1 && op.stride == 2 && op.ksize == 3 && !op.up && op.Hin % 2 == 0 && op.Win % 2 == 0) {
-    // Downsample (unet.py:68-74): gather the 9 taps once, then a 1x1 tensor-core GEMM with K = 9*C.
+    // Downsample (unet.py:68-74), preferred: the halo kernel over the four phase lattices of the input (no im2col)
+    static const bool no_s2 = std::getenv("HSIDM_NO_S2HALO") != nullptr;   // A/B switch for profiling runs
+    if (w.w_s2 && !no_s2) {
+      g->Hin = op.Hout, g->Win = op.Wout, g->stride = 1, g->s2 = 1, g->w_bf16 = w.w_s2;
+      if (conv_tc_supported(*g, prec) && conv_halo_ok(*g)) return R_DOWN_HALO;
+      *g = op;
+    }
+    // else: gather the 9 taps once, then a 1x1 tensor-core GEMM with K = 9*C.
     g->src[0].C = 9 * op.src[0].C;
     g->Hin = op.Hout, g->Win = op.Wout, g->stride = 1, g->ksize = 1;
     if (conv_tc_supported(*g, prec)) return R_DOWN;
@@ -297,6 +341,8 @@ void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps) {
   }
   if (route == R_TC) {
     ex.run([&] { return conv_tc(op, st); });
+  } else if (route == R_DOWN_HALO) {
+    ex.run([&] { return conv_tc(g, st); });
   } else if (route == R_DOWN) {
     const int C = op.src[0].C;
     Act col = ex.alloc_act(op.N, op.Hout, op.Wout, 9 * C);

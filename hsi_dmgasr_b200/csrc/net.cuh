@@ -47,6 +47,7 @@ struct ConvW {
   float* w_f32 = nullptr;  // [k*k*Cin][Cout]
   bf16* w_bf16 = nullptr;  // [rows >= Cout][k*k*Cin], zero padded rows
   bf16* w_up = nullptr;    // [rows >= Cout][4 parities][4 taps][Cin]: pre-summed weights of (nearest-2x upsample -> 3x3 conv)
+  bf16* w_s2 = nullptr;    // [rows >= Cout][9*Cin] in the consumption order of the stride-2 (phase lattice) halo form
   bf16* w_col = nullptr;   // [rows >= Cout][64]: the same weights for the im2col route of tiny-Cin 3x3 convs (9*Cin <= 64)
   int64_t packed_bytes = 0;
   const float* bias_override = nullptr;  // used instead of the parameter bias when set (fused weights)
@@ -67,6 +68,7 @@ void free_fused(FusedW& f);
 ConvW make_conv(ParamStore& ps, const std::string& prefix, int Cin, int Cout, int ks, bool bias = true);
 // (Re)packs w_f32 always and w_bf16 when `bf16_too`. Idempotent; frees previous packs.
 int pack_conv(const ParamStore& ps, ConvW& c, bool bf16_too);
+int pack_conv_s2(const ParamStore& ps, ConvW& c);   // extra pack for Downsample convs (stride-2 halo form), after pack_conv
 int pack_conv_up(const ParamStore& ps, ConvW& c);   // extra pack for Upsample convs (sub-pixel form), after pack_conv
 void free_conv(ConvW& c);
 

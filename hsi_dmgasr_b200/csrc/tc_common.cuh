@@ -593,6 +593,9 @@ struct Host {
 Host& host();
 // NHWC bf16 activation [N,H,W,C] as a 4-D tensor map with box {64, bw, bh, bn} and 128B swizzle (OOB reads are zero).
 int encode_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int bw, int bh, int bn);
+// Load map of the phase lattice (2i + py, 2j + px) of an NHWC bf16 tensor [N,H,W,C] (H, W even): a 4-D tensor
+// {C, W/2, H/2, N} with box {64, bw, bh, 1}; used by the stride-2 form of the halo kernel.
+int encode_phase_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int py, int px, int bw, int bh);
 // Store map of an NHWC bf16 output [N,H,W,C] restricted to the pixel lattice (scale*i + oy, scale*j + ox): a 4-D tensor
 // {C, W/scale, H/scale, N} with box {64, 8, 4, 1} (one epilogue warp's tile) and 128B swizzle.
 int encode_out_map(CUtensorMap* map, void* base, int N, int H, int W, int C, int scale, int oy, int ox);

@@ -764,6 +764,14 @@ int hsidm_unet_commit(hsidm_ctx* c) {
   });
   HSIDM_TRY(status);
   if (c->cfg.precision == HSIDM_BF16)
+    for (auto& L : c->downs)
+      if (L.kind == LayerW::DOWN && status == HSIDM_OK) {
+        const int64_t before = L.conv.packed_bytes;
+        status = pack_conv_s2(c->ps, L.conv);
+        c->packed_bytes += L.conv.packed_bytes - before;
+      }
+  HSIDM_TRY(status);
+  if (c->cfg.precision == HSIDM_BF16)
     for (auto& L : c->ups)
       if (L.kind == LayerW::UP && status == HSIDM_OK) {
         const int64_t before = L.conv.packed_bytes;

@@ -169,6 +169,20 @@ def test_upsample_conv_subpixel_form(shape, conv_mode):
     assert rel_l2(got, ref_conv(bf(x), None, bf(wt), b, up=1)) < 8e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64, 64, 64), (3, 128, 32, 64, 128), (20, 256, 32, 32, 256), (1, 64, 128, 128, 64),
+                                   (2, 64, 32, 32, 128)])
+def test_downsample_conv_phase_lattice_form(shape):
+    """Downsample (3x3, stride 2, pad 1) runs on the halo kernel over the four phase lattices of the input (no im2col
+    buffer) whenever the OUTPUT is a multiple of 16 rows; (20, 256, 32, 32) has more tiles than SMs."""
+    n, c, h, w, cout = shape
+    x = randn((n, c, h, w), 61)
+    wt, b = randn((cout, c, 3, 3), 62, scale=(1.0 / (9 * c)) ** 0.5), randn((cout,), 63)
+    got = conv2d(AUTO, "bf16", x, None, wt, b, ksize=3, stride=2)
+    assert tc_flag() == 0
+    want = ref_conv(bf(x), None, bf(wt), b, stride=2)
+    assert got.shape == want.shape and rel_l2(got, want) < 6e-3
+
+
 @pytest.mark.parametrize("kind", ["down", "up"])
 def test_conv_dispatch_lowerings(kind):
     x = randn((2, 128, 16, 16), 41)

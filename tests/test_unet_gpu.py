@@ -7,7 +7,7 @@ import torch
 
 from hsi_dmgasr_b200 import UNet, synth
 from tests.cfgs import UNET_CASES
-from tests.gpu_util import rel_l2
+from tests.gpu_util import rel_l2, tc_flag
 
 pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
@@ -33,9 +33,11 @@ def test_unet_eps_matches_reference(golden, tag, precision):
         eps = net(x, lv)
     want = torch.from_numpy(g[f"{tag}.eps"])
     err = rel_l2(eps, want)
-    print(f"{tag} {precision}: rel-L2 {err:.3e}")
+    flag = tc_flag()
+    print(f"{tag} {precision}: rel-L2 {err:.3e}  barrier-timeout flag {flag}")
+    assert flag == 0, f"a tensor-core kernel hit a barrier timeout (wait code {flag})"
     assert eps.shape == want.shape and torch.isfinite(eps).all()
-    assert err < TOL[precision]
+    assert err < TOL[precision], f"rel-L2 {err:.3e}"
 
 
 def test_unet_state_dict_is_drop_in():
