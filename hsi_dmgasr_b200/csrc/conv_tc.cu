@@ -221,7 +221,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           } else {
             sn = n0, sslot = (mt - n0 * tpi) * 4 + quarter;
           }
-          const float* cb = nbias ? nbias + (long long)sn * p.e.nbs : p.e.bias;
+          // a tile of several small images may reach past the batch: those rows are masked (valid_rows / stats_store),
+          // but their noise-bias row must not be read - it does not exist
+          const float* cb = nbias ? nbias + (long long)min(sn, p.e.N_img - 1) * p.e.nbs : p.e.bias;
           const float* cb2 = nbias ? p.e.bias : nullptr;
           constexpr int nC = BN / 64;
           // the two warps of a quarter alternate over the 64-channel chunks (a single chunk goes to the first warp)

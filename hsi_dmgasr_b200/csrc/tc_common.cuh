@@ -265,7 +265,7 @@ static __device__ __forceinline__ void epilogue_rows64(const EpiP& p, const floa
 #pragma unroll
     for (int q = 0; q < 4; ++q) tmem_ld16(taddr + q * 16, acc[q]);
     tmem_ld_wait();
-    const float* nb = nbias ? nbias + (long long)n * p.nbs + co0 : nullptr;
+    const float* nb = nbias ? nbias + (long long)min(n, p.N_img - 1) * p.nbs + co0 : nullptr;   // rows past the batch are masked, not read
 #pragma unroll
     for (int c = 0; c < 8; ++c) {   // 8 channels per 16-byte chunk
       float v[8];
