@@ -80,9 +80,10 @@ with open("profiles/r1_conv_halo_ncu.md", "w") as f:
                 f"{val(r, col, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'):.1f} | "
                 f"{val(r, col, 'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed'):.1f} | {rd:.1f} | {wr:.1f} | "
                 f"{val(r, col, 'lts__t_sectors_srcunit_tex_op_read.sum'):.3g} | {val(r, col, 'launch__registers_per_thread'):.0f} |\n")
-    f.write(f"\nMean DRAM traffic per launch: {sum(traffic) / len(traffic) / 1e6:.1f} MB (read + write).  Launch 0 here is a 128x128 64-channel layer whose "
-            "operands (369 MB in, 369 MB out) exceed the L2; the mid-network launches move far less from HBM than their operands' size because what "
-            "they read was just written by the preceding conv and still sits in the 126 MB L2 (with the GroupNorm fused there is no kernel in between any more).\n")
+    f.write(f"\nMean DRAM traffic per launch: {sum(traffic) / len(traffic) / 1e6:.1f} MB (read + write).  The 64x64-level launches read tensors larger than the "
+            "126 MB L2 (185-370 MB); the deeper ones move far less from HBM than their operands' size because what they read was just written by the "
+            "preceding conv and still sits in the L2 (with the GroupNorm fused there is no kernel in between any more).  Template arguments: "
+            "<MT, BN, taps (0 = stride-2 phase form), CTA pair>.\n")
     f.write("ncu times are cold (serialised, clocks not boosted): the warm per-MMA rates are in `r1_mma_rate.md`.\n")
 json.dump({"kernel": "conv_halo_kernel", "dram_bytes_per_launch": sum(traffic) / len(traffic), "launches_sampled": len(traffic),
            "source": f"ncu --set full, {tag}: dram__bytes_read.sum + dram__bytes_write.sum"}, open("profiles/r1_traffic.json", "w"), indent=1)
