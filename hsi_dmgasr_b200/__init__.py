@@ -11,7 +11,7 @@ __version__ = "0.1.0"
 def __getattr__(name):  # lazy: importing the package must not need torch.cuda or the shared library
     import importlib
     table = {"UNet": "unet", "GaussianDiffusion": "diffusion", "define_G": "networks", "DDPM": "model",
-             "create_model": "model", "GAE": "gae", "load_gae": "gae", "SRPipeline": "pipeline",
+             "create_model": "model", "GAE": "gae", "load_gae": "gae", "save_gae_state": "gae", "SRPipeline": "pipeline",
              "set_default_precision": "unet"}
     if name in table:
         return getattr(importlib.import_module("." + table[name], __name__), name)

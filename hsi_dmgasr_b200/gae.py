@@ -265,9 +265,32 @@ class _PickleModule:
     UnpicklingError = pickle.UnpicklingError
 
 
+GAE_STATE_FORMAT = "hsidm-gae-state-v1"
+
+
+def save_gae_state(gae: GAE, path: str) -> str:
+    """the GAE as a self-describing ``state_dict`` file (tensors + band-group geometry, no pickled
+    classes), so it loads with ``weights_only=True`` and needs none of the reference's class names in ``__main__``.
+    ``load_gae`` reads it back; the reference's whole-module pickles stay importable (import-only compatibility)."""
+    g = gae.geometry()
+    torch.save({"format": GAE_STATE_FORMAT,
+                "geometry": {"n_colors": g.n_colors, "n_subs": g.n_subs, "n_ovls": g.n_ovls, "n_feats": g.n_feats},
+                "state_dict": {k: v.detach().cpu() for k, v in gae.state_dict().items()}}, path)
+    return path
+
+
 def load_gae(path: str, map_location="cpu", precision: str = "fp32") -> GAE:
-    """Load ``GAE_pretrained/GAE_4_*.pth`` (whole-module pickle, AE.py:637) or a plain ``state_dict`` file."""
-    obj = torch.load(path, map_location=map_location, weights_only=False, pickle_module=_PickleModule)
+    """Load ``GAE_pretrained/GAE_4_*.pth`` (whole-module pickle, AE.py:637), a ``save_gae_state`` file, or a plain
+    ``state_dict`` file."""
+    try:   # tensors-only files first: no unpickling of arbitrary globals
+        obj = torch.load(path, map_location=map_location, weights_only=True)
+    except Exception:
+        obj = torch.load(path, map_location=map_location, weights_only=False, pickle_module=_PickleModule)
+    if isinstance(obj, dict) and obj.get("format") == GAE_STATE_FORMAT:
+        geo = obj["geometry"]
+        gae = GAE(n_subs=geo["n_subs"], n_ovls=geo["n_ovls"], n_colors=geo["n_colors"], n_feats=geo["n_feats"], precision=precision)
+        gae.load_state_dict(obj["state_dict"], strict=True)
+        return gae
     if isinstance(obj, dict):
         sd = obj
         n_subs, n_feats = sd["Encoder.branch.head.weight"].shape[1], sd["Encoder.branch.head.weight"].shape[0]

@@ -98,6 +98,26 @@ def test_group_layouts_from_survey():
     assert set(GAE_PRESETS["Cav"].band_counts()) == {1, 2}
 
 
+def test_gae_state_file_round_trip(tmp_path):
+    """the tensors-only GAE file written by save_gae_state loads with weights_only=True semantics and
+    reproduces geometry, key order and every tensor; a bare state_dict file still loads too."""
+    import torch
+    from hsi_dmgasr_b200 import load_gae, save_gae_state, synth
+    from hsi_dmgasr_b200.gae import GAE
+    geom = GAE_PRESETS["Pav"]
+    gae = GAE(n_subs=geom.n_subs, n_ovls=geom.n_ovls, n_colors=geom.n_colors, n_feats=geom.n_feats)
+    gae.load_state_dict(synth.gae_state_dict(geom, 5))
+    path = save_gae_state(gae, str(tmp_path / "gae_state.pth"))
+    blob = torch.load(path, map_location="cpu", weights_only=True)          # no pickled classes inside
+    assert blob["format"] == "hsidm-gae-state-v1" and blob["geometry"]["n_colors"] == 102
+    back = load_gae(path)
+    assert back.geometry() == geom and list(back.state_dict().keys()) == list(gae.state_dict().keys())
+    assert all(torch.equal(a, b) for a, b in zip(back.state_dict().values(), gae.state_dict().values()))
+    bare = str(tmp_path / "bare_sd.pth")
+    torch.save(gae.state_dict(), bare)
+    assert load_gae(bare).geometry() == geom
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
 def test_reference_gae_pickles_load_through_the_shim():
     from hsi_dmgasr_b200 import load_gae
