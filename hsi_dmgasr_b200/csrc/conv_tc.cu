@@ -60,7 +60,7 @@ struct Cfg {
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const TcP p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const TcP p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -80,6 +80,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tma_prefetch_desc(&tmA0);
     if (p.chunks1) tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
     for (int s = 0; s < C::kStages; ++s) mbar_init(smem_u32(&empty_bar[s]), 1);
     for (int g = 0; g < C::kGroups; ++g) mbar_init(smem_u32(&full_bar[g]), C::kGroup);
     for (int s = 0; s < 2; ++s) {
@@ -233,7 +234,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (co0 >= p.e.Cout) break;
             float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bn <= 4) {
-              epilogue_halo64(p.e, cb, cb2, taddr + ci * 64, lane, co0, stage, m_warp, p.e.Cout, 8LL * p.e.Cout, st, valid_rows);
+              // this lane's (row sub, 16-byte chunk) element of the warp's 32 consecutive pixels in the residual tensor
+              const bf16* resid_lane =
+                  p.e.resid ? p.e.resid + (m_warp + (lane >> 3)) * p.e.Cout + co0 + (lane & 7) * 8 : nullptr;
+              epilogue_tma64<2>(p.e, &tmO, 0u, taddr + ci * 64, lane, stage, co0, (int)m_warp, 0, 0, resid_lane, 8LL * p.e.Cout,
+                                4LL * p.e.Cout, st, cb, cb2, valid_rows);
               if (p.e.stats) stats_store(p.e, sn, sslot, co0, lane, st);
             } else {
               // images smaller than 32 pixels: a warp's rows span several images, so the noise bias is per row
@@ -263,6 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
       if (++acc == 2) acc = 0, acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all();   // the staging tiles must outlive the stores reading them
   }
 
   tc_fence_before();
@@ -338,6 +344,17 @@ int encode_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int 
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: %d", N, H, W, C, (int)r);
+  return HSIDM_OK;
+}
+
+int encode_rows_map(CUtensorMap* map, void* base, long long pixels, int C) {
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)pixels};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, 32};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = host().encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HSIDM_FAIL(HSIDM_CUDA_ERROR, "cuTensorMapEncodeTiled(output rows %lld x %d) failed: %d", pixels, C, (int)r);
   return HSIDM_OK;
 }
 
@@ -479,6 +496,9 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
     tmA1 = tmA0;
   const int K = op.K();
   HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, BN));
+  CUtensorMap tmO = tmB;   // only the NHWC bf16 outputs with 64-multiple channels store through it
+  if (op.out_layout == L_NHWC && op.Cout % 64 == 0)
+    HSIDM_TRY(encode_rows_map(&tmO, op.out, (long long)op.N * op.Hout * op.Wout, op.Cout));
 
   const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
   char tag[96];
@@ -486,10 +506,10 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
            op.Win, op.N);
   ProfScope prof(PROF_CONV_TC, 2.0 * p.M * (double)op.Cout * K, stream, tag);
   switch (BN) {
-    case 16: conv_tc_kernel<16><<<grid, kThreads, Cfg<16>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;
-    case 64: conv_tc_kernel<64><<<grid, kThreads, Cfg<64>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;
-    case 128: conv_tc_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;
-    default: conv_tc_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, p); break;
+    case 16: conv_tc_kernel<16><<<grid, kThreads, Cfg<16>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, tmO, p); break;
+    case 64: conv_tc_kernel<64><<<grid, kThreads, Cfg<64>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, tmO, p); break;
+    case 128: conv_tc_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, tmO, p); break;
+    default: conv_tc_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, tmO, p); break;
   }
   return after_launch("conv_tc_kernel");
 }

@@ -350,124 +350,6 @@ static __device__ __forceinline__ float2 bf16x2_to_f2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
-// Lean epilogue of the halo kernel for 64 output channels [co0, co0+64) of one warp's 32 accumulator rows, which are
-// 4 image rows x 8 pixels starting at flat pixel index m_warp (row pitch W pixels).  Same three phases as
-// epilogue_rows64 (coalesced residual read -> per-row math in registers -> coalesced write, plus column statistics)
-// but with LDS/STS on 32-bit addresses, packed FADD2/FFMA2 arithmetic, one pre-combined bias vector `cb` (conv bias or
-// bias-folded noise embedding) and incremental global addressing: ~1/3 of the instructions, which is what bounds the
-// K = 576 layers at 128x128.
-static __device__ __forceinline__ void epilogue_halo64(const EpiP& p, const float* __restrict__ cb,
-                                                       const float* __restrict__ cb2, uint32_t taddr, int lane, int co0,
-                                                       uint32_t stage, long long m_warp, long long xstep,
-                                                       long long pitch, float4& st, int valid_rows = 32) {
-  // valid_rows: accumulator rows of this warp that map to real pixels (the per-tap kernel's last tile may be partial)
-  // xstep / pitch: elements between horizontally / vertically adjacent tile pixels in the output tensor
-  // (Cout and W*Cout for a plain conv; doubled for the sub-pixel upsampling form)
-  const int sub = lane >> 3, chunk = lane & 7;
-  // element offset of (row 4i+sub, 16-byte chunk `chunk`) relative to pixel m_warp: (i>>1) tile rows + 4*(i&1)+sub pixels
-  const long long lane_off = (long long)sub * xstep + co0 + chunk * 8;
-  const long long odd_off = 4LL * xstep;
-  // phase 1: residual tile -> staging (coalesced)
-  if (p.resid) {
-    const bf16* base = p.resid + m_warp * p.Cout + lane_off;
-    uint4 v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      v[i] = (4 * i + sub) < valid_rows ? __ldg(reinterpret_cast<const uint4*>(base + (i >> 1) * pitch + (i & 1) * odd_off))
-                                        : make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r7 = (4 * (i & 1) + sub) & 7;   // (4i+sub) & 7
-      sts128(stage + (uint32_t)((4 * i + sub) * 128 + ((chunk ^ r7) << 4)), v[i]);
-    }
-    __syncwarp();
-  }
-  // phase 2: own row in registers
-  {
-    uint32_t acc[4][16];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) tmem_ld16(taddr + q * 16, acc[q]);
-    float4 bias[16];
-    if (cb) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) bias[j] = __ldg(reinterpret_cast<const float4*>(cb + co0) + j);
-      if (cb2) {   // conv bias AND noise embedding given separately (not the executor's case, which folds them)
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(cb2 + co0) + j);
-          bias[j].x += b.x, bias[j].y += b.y, bias[j].z += b.z, bias[j].w += b.w;
-        }
-      }
-    }
-    tmem_ld_wait();
-    const uint32_t my_row = stage + (uint32_t)(lane * 128);
-    const int l7 = lane & 7;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {   // 8 channels per 16-byte chunk
-      float2 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        v[j] = make_float2(__uint_as_float(acc[c >> 1][(c & 1) * 8 + 2 * j]), __uint_as_float(acc[c >> 1][(c & 1) * 8 + 2 * j + 1]));
-      if (cb) {
-        v[0] = __fadd2_rn(v[0], make_float2(bias[2 * c].x, bias[2 * c].y));
-        v[1] = __fadd2_rn(v[1], make_float2(bias[2 * c].z, bias[2 * c].w));
-        v[2] = __fadd2_rn(v[2], make_float2(bias[2 * c + 1].x, bias[2 * c + 1].y));
-        v[3] = __fadd2_rn(v[3], make_float2(bias[2 * c + 1].z, bias[2 * c + 1].w));
-      }
-      if (p.act == ACT_LRELU) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j].x = v[j].x > 0.f ? v[j].x : 0.01f * v[j].x, v[j].y = v[j].y > 0.f ? v[j].y : 0.01f * v[j].y;
-      }
-      if (p.scale != 1.0f) {
-        const float2 sc = make_float2(p.scale, p.scale);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = __fmul2_rn(v[j], sc);
-      }
-      const uint32_t slot = my_row + (uint32_t)((c ^ l7) << 4);
-      if (p.resid) {
-        const uint4 rv = lds128(slot);
-        v[0] = __fadd2_rn(v[0], bf16x2_to_f2(rv.x));
-        v[1] = __fadd2_rn(v[1], bf16x2_to_f2(rv.y));
-        v[2] = __fadd2_rn(v[2], bf16x2_to_f2(rv.z));
-        v[3] = __fadd2_rn(v[3], bf16x2_to_f2(rv.w));
-      }
-      uint4 o;
-      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[j].x, v[j].y);
-      if (lane >= valid_rows) o = make_uint4(0, 0, 0, 0);   // keep rows past the batch out of the statistics
-      sts128(slot, o);
-    }
-    __syncwarp();
-  }
-  // phase 2b: column sums of the stored values (lane -> channel pair 2*lane, 2*lane+1); conflict-free word reads
-  if (p.stats) {
-    const int cw = lane >> 2, ww = lane & 3;
-    uint32_t base[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) base[k] = stage + (uint32_t)(((cw ^ k) << 4) + ww * 4);
-    float2 s = make_float2(st.x, st.y), q = make_float2(st.z, st.w);
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      const float2 a = bf16x2_to_f2(lds32(base[r & 7] + r * 128));
-      s = __fadd2_rn(s, a);
-      q = __ffma2_rn(a, a, q);
-    }
-    st = make_float4(s.x, s.y, q.x, q.y);
-  }
-  // phase 3: staging -> global (coalesced)
-  {
-    bf16* base = static_cast<bf16*>(p.out) + m_warp * p.Cout + lane_off;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r7 = (4 * (i & 1) + sub) & 7;
-      const uint4 v = lds128(stage + (uint32_t)((4 * i + sub) * 128 + ((chunk ^ r7) << 4)));
-      if ((4 * i + sub) < valid_rows) *reinterpret_cast<uint4*>(base + (i >> 1) * pitch + (i & 1) * odd_off) = v;
-    }
-  }
-  __syncwarp();
-}
-
 // ---- TMA store of a staged tile ----
 static __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 static __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -476,19 +358,30 @@ static __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+static __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 static __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 static __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// Epilogue of the halo kernel for 64 output channels of one warp's 32 accumulator rows (4 image rows x 8 pixels):
-// TMEM -> registers -> +bias (64 floats the warp parked in shared memory at `bias_smem`, 0 = none) -> act/scale ->
-// +residual -> bf16 rows in the 128B-swizzled staging tile -> column statistics -> ONE TMA store of the tile
-// (box {64 ch, 8 px, 4 rows, 1 image} of the output lattice map, coordinates c0..c3).  Compared with epilogue_halo64
-// the write-back costs one instruction instead of 8 LDS + 8 STG with 64-bit address arithmetic, and the bias lives in
-// shared memory instead of 64 registers: the warp stays below the spill limit and issues ~1/3 fewer instructions.
+// Epilogue of the tensor-core conv kernels for 64 output channels of one warp's 32 accumulator rows:
+// TMEM -> registers -> +bias (64 floats the warp parked in shared memory at `bias_smem`, or read from global `cb` /
+// `cb2` when bias_smem is 0) -> act/scale -> +residual -> bf16 rows in the 128B-swizzled staging tile -> column
+// statistics -> ONE TMA store of the tile: DIMS = 4, box {64 ch, 8 px, 4 rows, 1 image} of the output lattice map
+// (halo kernel: the rows are 4 image rows x 8 pixels); DIMS = 2, box {64 ch, 32 pixels} of the [pixels, channels] view
+// (per-tap kernel: the rows are 32 consecutive pixels; rows past the tensor are clipped by the TMA unit).
+// valid_rows: accumulator rows that map to real pixels; the others are neither read as residual nor counted.
+// Against per-lane stores the write-back costs one instruction instead of 8 LDS + 8 STG with 64-bit address arithmetic,
+// and with the bias in shared memory instead of 64 registers the warp stays below the spill limit.
+template <int DIMS = 4>
 static __device__ __forceinline__ void epilogue_tma64(const EpiP& p, const CUtensorMap* tmO, uint32_t bias_smem, uint32_t taddr,
                                                       int lane, uint32_t stage, int c0, int c1, int c2, int c3,
                                                       const bf16* __restrict__ resid_lane, long long pitch, long long odd_off,
-                                                      float4& st) {
+                                                      float4& st, const float* __restrict__ cb = nullptr,
+                                                      const float* __restrict__ cb2 = nullptr, int valid_rows = 32) {
   if (lane == 0) tma_store_wait_read();   // the previous store out of `stage` must have read it
   __syncwarp();
   // phase 1 (residual layers only): residual tile -> staging, coalesced; resid_lane already points at this lane's
@@ -497,7 +390,9 @@ static __device__ __forceinline__ void epilogue_tma64(const EpiP& p, const CUten
   if (resid_lane) {
     uint4 v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(resid_lane + (i >> 1) * pitch + (i & 1) * odd_off));
+    for (int i = 0; i < 8; ++i)
+      v[i] = (4 * i + sub) < valid_rows ? __ldg(reinterpret_cast<const uint4*>(resid_lane + (i >> 1) * pitch + (i & 1) * odd_off))
+                                        : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r7 = (4 * (i & 1) + sub) & 7;
@@ -525,6 +420,16 @@ static __device__ __forceinline__ void epilogue_tma64(const EpiP& p, const CUten
         v[1] = __fadd2_rn(v[1], make_float2(__uint_as_float(b0.z), __uint_as_float(b0.w)));
         v[2] = __fadd2_rn(v[2], make_float2(__uint_as_float(b1.x), __uint_as_float(b1.y)));
         v[3] = __fadd2_rn(v[3], make_float2(__uint_as_float(b1.z), __uint_as_float(b1.w)));
+      } else if (cb) {   // bias vectors straight from global memory (L1-resident: every lane reads the same 32 bytes)
+        float4 b0 = __ldg(reinterpret_cast<const float4*>(cb + c0) + 2 * c), b1 = __ldg(reinterpret_cast<const float4*>(cb + c0) + 2 * c + 1);
+        if (cb2) {
+          const float4 e0 = __ldg(reinterpret_cast<const float4*>(cb2 + c0) + 2 * c), e1 = __ldg(reinterpret_cast<const float4*>(cb2 + c0) + 2 * c + 1);
+          b0.x += e0.x, b0.y += e0.y, b0.z += e0.z, b0.w += e0.w, b1.x += e1.x, b1.y += e1.y, b1.z += e1.z, b1.w += e1.w;
+        }
+        v[0] = __fadd2_rn(v[0], make_float2(b0.x, b0.y));
+        v[1] = __fadd2_rn(v[1], make_float2(b0.z, b0.w));
+        v[2] = __fadd2_rn(v[2], make_float2(b1.x, b1.y));
+        v[3] = __fadd2_rn(v[3], make_float2(b1.z, b1.w));
       }
       if (p.act == ACT_LRELU) {
 #pragma unroll
@@ -547,12 +452,16 @@ static __device__ __forceinline__ void epilogue_tma64(const EpiP& p, const CUten
       __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[j].x, v[j].y);
+      if (lane >= valid_rows) o = make_uint4(0, 0, 0, 0);   // keep rows past the batch out of the statistics
       sts128(slot, o);
     }
     fence_proxy_async_smem();   // the rows just written are read by the TMA unit (async proxy)
     __syncwarp();
   }
-  if (lane == 0) tma_store_4d(tmO, stage, c0, c1, c2, c3);
+  if (lane == 0) {
+    if constexpr (DIMS == 4) tma_store_4d(tmO, stage, c0, c1, c2, c3);
+    else tma_store_2d(tmO, stage, c0, c1);
+  }
   // column sums of the stored values (lane -> channel pair 2*lane, 2*lane+1); conflict-free word reads
   if (p.stats) {
     const int cw = lane >> 2, ww = lane & 3;
@@ -596,6 +505,8 @@ int encode_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int 
 // Load map of the phase lattice (2i + py, 2j + px) of an NHWC bf16 tensor [N,H,W,C] (H, W even): a 4-D tensor
 // {C, W/2, H/2, N} with box {64, bw, bh, 1}; used by the stride-2 form of the halo kernel.
 int encode_phase_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int py, int px, int bw, int bh);
+// Store map of an NHWC bf16 output seen as [pixels, channels]: 2-D tensor {C, N*H*W}, box {64, 32}, 128B swizzle.
+int encode_rows_map(CUtensorMap* map, void* base, long long pixels, int C);
 // Store map of an NHWC bf16 output [N,H,W,C] restricted to the pixel lattice (scale*i + oy, scale*j + ox): a 4-D tensor
 // {C, W/scale, H/scale, N} with box {64, 8, 4, 1} (one epilogue warp's tile) and 128B swizzle.
 int encode_out_map(CUtensorMap* map, void* base, int N, int H, int W, int C, int scale, int oy, int ox);
