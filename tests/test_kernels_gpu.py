@@ -183,6 +183,28 @@ def test_downsample_conv_phase_lattice_form(shape):
     assert got.shape == want.shape and rel_l2(got, want) < 6e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 256, 32, 32, 256), (4, 512, 16, 16, 512), (6, 256, 32, 32, 512)])
+def test_pair_tile_is_bitwise_single_cta(shape):
+    """Cout % 256 == 0 runs on CTA pairs (cta_group::2, M = 256, N = 256, weights split over the pair); the developer
+    switch 32 keeps the same conv on the single-CTA <2,128> tile.  Same K order per output -> the same bits."""
+    from hsi_dmgasr_b200 import _lib
+    lib = _lib.load()
+    n, c, h, w, cout = shape
+    x = randn((n, c, h, w), 71)
+    wt, b = randn((cout, c, 3, 3), 72, scale=(1.0 / (9 * c)) ** 0.5), randn((cout,), 73)
+    resid = randn((n, cout, h, w), 74)
+    try:
+        outs = []
+        for variant in (0, 32):
+            lib.hsidm_debug_conv_mode(0, variant)
+            outs.append(conv2d(TC, "bf16", x, None, wt, b, ksize=3, resid=resid))
+    finally:
+        lib.hsidm_debug_conv_mode(0, 0)
+    assert tc_flag() == 0
+    assert torch.equal(outs[0], outs[1])
+    assert rel_l2(outs[0], ref_conv(bf(x), None, bf(wt), b, resid=bf(resid))) < 6e-3
+
+
 @pytest.mark.parametrize("kind", ["down", "up"])
 def test_conv_dispatch_lowerings(kind):
     x = randn((2, 128, 16, 16), 41)

@@ -82,18 +82,26 @@ def test_fused_input_groupnorm_matches_normalised_copy(tag, hw, n):
     cfg, seed, *_ = UNET_CASES[tag]
     x = torch.from_numpy(np.random.default_rng(77).standard_normal((n, 6, hw, hw), dtype=np.float32)).cuda()
     lv = torch.linspace(0.2, 0.9, n).view(n, 1).cuda()
-    outs = []
+    outs = {}
     try:
-        for variant in (8, 0):
+        # 0 = production routing; 8 = GroupNorm as a separate pass; 32 = no CTA-pair tiles; 16 = <2,64> instead of <4,64>
+        for variant in (8, 0, 32, 16):
             lib.hsidm_debug_conv_mode(0, variant)
             net = build(cfg, seed, "bf16")
             with torch.no_grad():
-                outs.append(net(x, lv).clone())
+                outs[variant] = net(x, lv).clone()
             del net
     finally:
         lib.hsidm_debug_conv_mode(0, 0)
     assert torch.isfinite(outs[0]).all()
-    assert torch.equal(outs[0], outs[1]), f"max |diff| {float((outs[0] - outs[1]).abs().max()):.3e}"
+    assert torch.equal(outs[8], outs[0]), f"max |diff| {float((outs[8] - outs[0]).abs().max()):.3e}"
+    # Other tile shapes / CTA pairing leave every conv output bit-identical (test_pair_tile_is_bitwise_single_cta) but
+    # regroup the GroupNorm partial sums (one fp32 slot per warp tile): mean/rstd move in their last bits, bf16 roundings
+    # flip, and 50 layers later the outputs differ at the bf16 noise floor (the bf16-vs-fp32 error is 8e-3).
+    for variant, what in ((32, "pair vs single-CTA tiles"), (16, "<2,64> vs <4,64> tiles")):
+        err = rel_l2(outs[variant], outs[0])
+        print(f"{what}: rel-L2 {err:.3e}")
+        assert err < 1.5e-2, f"{what}: rel-L2 {err:.3e}"
 
 
 def test_c4_shape_512_bf16_tracks_fp32():
