@@ -263,11 +263,14 @@ int gn_stats(const void* x0, int C0, const void* x1, int C1, int N, int HW, int 
 }
 
 // grid = N; thread -> (slot lane, channel pair), float4 loads = (sum, sumsq) of two channels; fixed-order folds only.
+// The per-slot partials are short fp32 sums (32 rows); everything above them is folded in float64, so the statistics do
+// not depend on how the producing kernel happened to tile the tensor beyond the last fp32 bit of a 32-row sum, and
+// E[x^2] - mean^2 keeps its digits for channels whose mean dominates their spread.
 __global__ void __launch_bounds__(1024, 2)   // two blocks per SM: a 176-image batch is one wave, not two
 gn_finalize_kernel(const float* __restrict__ part0, int slots0, int C0, const float* __restrict__ part1, int slots1, int C1,
                    int groups, int lanes, double cnt, float eps, float* __restrict__ stats, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ ab) {
-  extern __shared__ float4 fsm4[];   // [lanes][C/2], then reused as float[2][C]
+  extern __shared__ double dsm[];   // [lanes][C/2][4], then reused as double[2][C]
   const int C = C0 + C1, n = blockIdx.x, tid = threadIdx.x;
   const int pairs = C >> 1;
   const int pr = tid % pairs, lane = tid / pairs;
@@ -277,43 +280,43 @@ gn_finalize_kernel(const float* __restrict__ part0, int slots0, int C0, const fl
     const float* base = second ? part1 + ((long long)n * slots1 * C1 + (c - C0)) * 2 : part0 + ((long long)n * slots0 * C0 + c) * 2;
     const int slots = second ? slots1 : slots0;
     const long long stride = (long long)(second ? C1 : C0) * 2;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int sl = lane;
-    for (; sl + 3 * lanes < slots; sl += 4 * lanes) {
+    for (; sl + 3 * lanes < slots; sl += 4 * lanes) {   // four loads in flight, folded in slot order
       const float4 u0 = *reinterpret_cast<const float4*>(base + (long long)sl * stride);
       const float4 u1 = *reinterpret_cast<const float4*>(base + (long long)(sl + lanes) * stride);
       const float4 u2 = *reinterpret_cast<const float4*>(base + (long long)(sl + 2 * lanes) * stride);
       const float4 u3 = *reinterpret_cast<const float4*>(base + (long long)(sl + 3 * lanes) * stride);
-      a0.x += u0.x, a0.y += u0.y, a0.z += u0.z, a0.w += u0.w;
-      a1.x += u1.x, a1.y += u1.y, a1.z += u1.z, a1.w += u1.w;
-      a2.x += u2.x, a2.y += u2.y, a2.z += u2.z, a2.w += u2.w;
-      a3.x += u3.x, a3.y += u3.y, a3.z += u3.z, a3.w += u3.w;
+      a0 += ((double)u0.x + (double)u1.x) + ((double)u2.x + (double)u3.x);
+      a1 += ((double)u0.y + (double)u1.y) + ((double)u2.y + (double)u3.y);
+      a2 += ((double)u0.z + (double)u1.z) + ((double)u2.z + (double)u3.z);
+      a3 += ((double)u0.w + (double)u1.w) + ((double)u2.w + (double)u3.w);
     }
     for (; sl < slots; sl += lanes) {
       const float4 u0 = *reinterpret_cast<const float4*>(base + (long long)sl * stride);
-      a0.x += u0.x, a0.y += u0.y, a0.z += u0.z, a0.w += u0.w;
+      a0 += (double)u0.x, a1 += (double)u0.y, a2 += (double)u0.z, a3 += (double)u0.w;
     }
-    fsm4[lane * pairs + pr] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
-                                          (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+    double* mine = dsm + ((long long)lane * pairs + pr) * 4;
+    mine[0] = a0, mine[1] = a1, mine[2] = a2, mine[3] = a3;
   }
   __syncthreads();
-  float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
   if (tid < pairs)
     for (int l = 0; l < lanes; ++l) {
-      const float4 u = fsm4[l * pairs + tid];
-      tot.x += u.x, tot.y += u.y, tot.z += u.z, tot.w += u.w;
+      const double* u = dsm + ((long long)l * pairs + tid) * 4;
+      t0 += u[0], t1 += u[1], t2 += u[2], t3 += u[3];
     }
   __syncthreads();
-  float* fs = reinterpret_cast<float*>(fsm4);   // [2][C]: sums then sums of squares
+  double* fs = dsm;   // [2][C]: sums then sums of squares
   if (tid < pairs) {
-    fs[2 * tid] = tot.x, fs[2 * tid + 1] = tot.z;
-    fs[C + 2 * tid] = tot.y, fs[C + 2 * tid + 1] = tot.w;
+    fs[2 * tid] = t0, fs[2 * tid + 1] = t2;
+    fs[C + 2 * tid] = t1, fs[C + 2 * tid + 1] = t3;
   }
   __syncthreads();
   const int cpg = C / groups;
   for (int g = tid; g < groups; g += blockDim.x) {
     double a = 0.0, b = 0.0;
-    for (int j = 0; j < cpg; ++j) a += (double)fs[g * cpg + j], b += (double)fs[C + g * cpg + j];
+    for (int j = 0; j < cpg; ++j) a += fs[g * cpg + j], b += fs[C + g * cpg + j];
     const double mean = a / cnt;
     double var = b / cnt - mean * mean;
     var = var < 0.0 ? 0.0 : var;
@@ -339,7 +342,7 @@ int gn_finalize(const float* part0, int slots0, int C0, const float* part1, int 
   const int pairs = C / 2;
   const int lanes = std::max(1, std::min(32, 1024 / pairs));
   const int threads = (int)round_up(lanes * pairs, 32);
-  const size_t smem = std::max<size_t>(sizeof(float4) * lanes * pairs, sizeof(float) * 2 * C);
+  const size_t smem = std::max<size_t>(sizeof(double) * 4 * lanes * pairs, sizeof(double) * 2 * C);
   ProfScope prof(PROF_GN_STATS, 8.0 * N * ((double)slots0 * C0 + (double)slots1 * C1), stream, "finalize");
   gn_finalize_kernel<<<N, threads, smem, stream>>>(part0, slots0, C0, part1, slots1, C1, groups, lanes,
                                                    (double)(C / groups) * HW, eps, stats, gamma, beta, ab);
