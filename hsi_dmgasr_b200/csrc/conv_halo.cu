@@ -14,11 +14,20 @@
 //   * one B tile (BN x 64 weights of one tap) feeds MT*4 MMAs instead of 4.
 // L2->SMEM bytes per MMA cycle drop from ~95 to ~35-40 B/clk/SM.
 // Accumulators: MT x BN fp32 columns per tile, double buffered (2*MT*BN <= 512 TMEM columns).
-// Warp roles: warp 0 TMA producer of the A ring (2 halo buffers), warp 1 TMA producer of the B ring (independent, so the
-// next tile's halo is requested a whole tile ahead instead of queueing behind the weight tiles), warp 2 MMA issuer,
-// warps 3..10 epilogue (two per
-// TMEM lane quarter, splitting the tile's channel halves or sub-tiles).  The epilogue also leaves per-slot (sum, sumsq)
-// of what it stored, so the consumer's GroupNorm never re-reads the tensor for statistics.
+//
+// Forms (template NT): 9 = 3x3 stride 1; 4 = the sub-pixel form of nearest-2x upsampling + 3x3 (a 2x2-tap conv over the
+// low-res source per output parity); 1 = a short-K 1x1 conv (centre tap); 0 = 3x3 stride 2 over the four phase
+// lattices of the input.  Optional per op: GroupNorm(+Swish) of the input applied in place to each halo tile
+// (gn_ab), a 1x1 shortcut over other tensors as extra centre-tap K columns (rsrc), per-slot GroupNorm partial sums
+// of the output (stats).
+//
+// Warp roles (15 warps): 0 = TMA producer of the halo ring (2-3 stages), 1 = TMA producer of the weight ring (stages
+// released per tap, full barriers shared by groups of 2-3 taps: every barrier wait of the issuer idles the tensor pipe
+// for ~160 clk), 2 = MMA issuer (+ TMEM allocation), 3..10 = epilogue (two per TMEM lane quarter: tcgen05.ld -> bias
+// -> act -> residual -> bf16 staging tile -> statistics -> one TMA store), 11..14 = in-place GroupNorm of halo tiles.
+//
+// PAIR = true runs the same pipeline on a cluster of two CTAs (cta_group::2): adjacent pixel tiles, one channel tile,
+// the weight rows split between the CTAs, MMAs (M = 256) issued by the leader and completed on both CTAs' barriers.
 #include <cstdlib>
 
 #include "tc_common.cuh"
