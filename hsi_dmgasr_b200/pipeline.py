@@ -75,6 +75,29 @@ class SRPipeline:
         return out
 
 
+@torch.no_grad()
+def validate(pipeline: SRPipeline, loader, device: torch.device, **kw) -> dict:
+    """The reference's validation loop (sr_gae.py:436-497) over an iterable of ``{'HR': [B,C,H,W], 'SR': [B,C,H,W]}``
+    batches: encode -> sample -> decode -> clamp to [0,1] -> metrics, with the indices the parity gates are stated in
+    (MPSNR, SAM) computed on the device and averaged over cubes like ``sum_dict`` / ``idx`` do.  The GAE is loaded once
+    (the reference re-reads the pickle per cube, sr_gae.py:444); results stay on the device until the final averages."""
+    from . import prepost
+    total = torch.zeros(2, device=device, dtype=torch.float64)
+    count = 0
+    for batch in loader:
+        sr = batch["SR"].to(device, non_blocking=True)
+        hr = batch["HR"].to(device, non_blocking=True)
+        if sr.dim() == 3:
+            sr, hr = sr.unsqueeze(0), hr.unsqueeze(0)
+        y = pipeline.super_resolve(sr.float().contiguous(), clamp=True, **kw)
+        total += prepost.quality_metrics(hr.float().contiguous(), y).double().sum(dim=0)
+        count += sr.shape[0]
+    if count == 0:
+        return {"MPSNR": float("nan"), "SAM": float("nan"), "cubes": 0}
+    mean = (total / count).cpu()
+    return {"MPSNR": float(mean[0]), "SAM": float(mean[1]), "cubes": count}
+
+
 def run_sharded(pipeline: SRPipeline, cubes_host: torch.Tensor, device: torch.device, rank: int, world: int,
                 batch: int, gather: bool = False, **kw) -> Optional[torch.Tensor]:
     """Each rank super-resolves its contiguous slice of `cubes_host` in batches of `batch` cubes.
