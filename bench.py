@@ -283,7 +283,7 @@ def main() -> None:
         _lib.check(lib.hsidm_prof_enable(0))
         tc = shares["conv_tc"]
         achieved = tc["work_per_step"] / (tc["ms_per_step"] * 1e-3) / 1e12 if tc["ms_per_step"] > 0 else 0.0
-        roof = {"kernel": "conv_tc_kernel<BN> (tcgen05/TMEM/TMA implicit-GEMM conv, all instantiations of one step)",
+        roof = {"kernel": "conv_halo_kernel<MT,BN,taps,pair> + conv_tc_kernel<BN> (tcgen05/TMEM/TMA implicit-GEMM convs incl. their fused GroupNorm, all launches of one step)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sustained"], "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)",
                 "traffic": traffic_from_profiles(), "launches_per_step": tc["launches_per_step"],
