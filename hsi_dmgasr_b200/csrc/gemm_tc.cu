@@ -22,6 +22,7 @@ struct GemmP {
   void* C;
   long long ldc, sC;
   int c_f32;
+  int row_softmax;
   int* err;
 };
 
@@ -149,7 +150,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
       const int m = mt * kBM + row;
-      if (p.c_f32) {
+      if (p.row_softmax) {
+        // The tile holds whole rows (n_tiles == 1) and a thread owns one row: three passes over its accumulator row in
+        // tensor memory - max, sum of exp, normalised bf16 probabilities - and the scores are never written anywhere.
+        const float sc = p.alpha * 1.4426950408889634f;   // softmax(alpha*s) = exp2((s - max) * alpha * log2 e) / sum
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum += exp2f((__uint_as_float(v[j]) - mx) * sc);
+        }
+        const float inv = 1.0f / sum;
+        bf16* crow = static_cast<bf16*>(p.C) + b * p.sC + (long long)m * p.ldc;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          uint4 o[2];
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            h[j] = __floats2bfloat162_rn(exp2f((__uint_as_float(v[2 * j]) - mx) * sc) * inv,
+                                         exp2f((__uint_as_float(v[2 * j + 1]) - mx) * sc) * inv);
+          if (m < p.M) {
+            *reinterpret_cast<uint4*>(crow + c0) = o[0];
+            *reinterpret_cast<uint4*>(crow + c0 + 8) = o[1];
+          }
+        }
+      } else if (p.c_f32) {
         float* crow = static_cast<float*>(p.C) + b * p.sC + (long long)m * p.ldc + nt * BN;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -219,13 +260,13 @@ int launch(const GemmTcOp& op, cudaStream_t stream) {
   p.M = op.M, p.N = op.N, p.K = op.K, p.batch = op.batch;
   p.m_tiles = (int)ceil_div(op.M, kBM), p.n_tiles = (int)ceil_div(op.N, BN);
   p.a_batched = op.sA != 0, p.b_batched = op.sB != 0;
-  p.alpha = op.alpha, p.C = op.C, p.ldc = op.ldc, p.sC = op.sC, p.c_f32 = op.c_f32, p.err = host().err_flag;
+  p.alpha = op.alpha, p.C = op.C, p.ldc = op.ldc, p.sC = op.sC, p.c_f32 = op.c_f32, p.row_softmax = op.row_softmax, p.err = host().err_flag;
   CUtensorMap tmA, tmB;
   HSIDM_TRY(encode_3d(&tmA, op.A, op.K, op.M, p.a_batched ? op.batch : 1, op.lda, op.sA, kBM));
   HSIDM_TRY(encode_3d(&tmB, op.B, op.K, op.N, p.b_batched ? op.batch : 1, op.ldb, op.sB, BN));
   const int grid = std::min(p.m_tiles * p.n_tiles * p.batch, host().num_sms);
   char tag[96];
-  snprintf(tag, sizeof(tag), "gemm_tc BN%d m%d n%d k%d b%d", BN, op.M, op.N, op.K, op.batch);
+  snprintf(tag, sizeof(tag), "gemm_tc BN%d m%d n%d k%d b%d%s", BN, op.M, op.N, op.K, op.batch, op.row_softmax ? " +softmax" : "");
   ProfScope prof(PROF_GEMM, 2.0 * op.M * (double)op.N * op.K * op.batch, stream, tag);
   gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
   return after_launch("gemm_tc_kernel");
@@ -244,6 +285,8 @@ bool gemm_tc_supported(const GemmTcOp& op) {
   if (op.K % 8 || op.lda % 8 || op.ldb % 8 || op.sA % 8 || op.sB % 8) return false;   // 16-byte TMA strides
   if (op.N % 64) return false;
   if (!op.c_f32 && (op.ldc % 8 || op.sC % 8)) return false;
+  // row softmax: whole rows in one tile (N is exactly one of the tile widths); the max is taken before scaling by alpha
+  if (op.row_softmax && (op.c_f32 || !(op.N == 64 || op.N == 128 || op.N == 256) || op.alpha <= 0.f)) return false;
   if (op.c_f32 && (op.ldc % 4 || op.sC % 4)) return false;
   return true;
 }

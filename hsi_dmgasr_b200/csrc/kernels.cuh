@@ -102,6 +102,9 @@ struct GemmTcOp {
   int64_t lda = 0, ldb = 0, ldc = 0, sA = 0, sB = 0, sC = 0;
   int c_f32 = 0;
   float alpha = 1.0f;
+  // 1: C = softmax over each row of alpha * A * B^T, written as bf16 (attention probabilities).  Needs the whole row in
+  // one tile: N <= 256, N % 64 == 0, c_f32 == 0.  The scores never leave tensor memory.
+  int row_softmax = 0;
 };
 bool gemm_tc_supported(const GemmTcOp& op);
 int gemm_tc(const GemmTcOp& op, cudaStream_t stream);

@@ -286,21 +286,29 @@ bool attention_tc(hsidm_ctx* c, const ResW& r, const Act& x, Act& out) {
   const bf16* wv = r.qkv.w_bf16 + (int64_t)2 * C * C;   // rows [2C, 3C) of the K-major [3C][C] matrix
   bf16* qkp = static_cast<bf16*>(qk.p);
   bf16* vt = static_cast<bf16*>(ex.alloc_raw(sizeof(bf16) * (int64_t)N * C * S));        // [N][C][S]
-  float* scores = static_cast<float*>(ex.alloc_raw(sizeof(float) * (int64_t)N * S * S));  // [N][S][S]
   GemmTcOp g;
   g.A = wv, g.B = nrm.p, g.C = vt, g.M = C, g.N = S, g.K = C, g.batch = N;
   g.lda = C, g.sA = 0, g.ldb = C, g.sB = (int64_t)S * C, g.ldc = S, g.sC = (int64_t)C * S, g.c_f32 = 0;
   ex.run([&] { return gemm_tc(g, ex.stream); });
+  // probabilities = softmax(q k^T / sqrt(C)) as bf16: with S = 64, 128 or 256 a row is exactly one accumulator tile and the softmax
+  // runs in the GEMM's epilogue; longer sequences go through fp32 scores and the row-softmax kernel
+  bf16* prob = static_cast<bf16*>(ex.alloc_raw(sizeof(bf16) * (int64_t)N * S * S));
   GemmTcOp qkT;
-  qkT.A = qkp, qkT.B = qkp + C, qkT.C = scores, qkT.M = S, qkT.N = S, qkT.K = C, qkT.batch = N;
+  qkT.A = qkp, qkT.B = qkp + C, qkT.M = S, qkT.N = S, qkT.K = C, qkT.batch = N;
   qkT.lda = qkT.ldb = 2 * C, qkT.sA = qkT.sB = (int64_t)S * 2 * C, qkT.ldc = S, qkT.sC = (int64_t)S * S;
-  qkT.c_f32 = 1, qkT.alpha = 1.0f / std::sqrt((float)C);
-  ex.run([&] { return gemm_tc(qkT, ex.stream); });
+  qkT.alpha = 1.0f / std::sqrt((float)C);
+  if (S == 64 || S == 128 || S == 256) {
+    qkT.C = prob, qkT.c_f32 = 0, qkT.row_softmax = 1;
+    ex.run([&] { return gemm_tc(qkT, ex.stream); });
+  } else {
+    float* scores = static_cast<float*>(ex.alloc_raw(sizeof(float) * (int64_t)N * S * S));  // [N][S][S]
+    qkT.C = scores, qkT.c_f32 = 1;
+    ex.run([&] { return gemm_tc(qkT, ex.stream); });
+    ex.run([&] { return softmax_rows_bf16(scores, prob, (int64_t)N * S, S, ex.stream); });
+    ex.release_raw(scores);
+  }
   ex.release(nrm);
   ex.release(qk);
-  bf16* prob = static_cast<bf16*>(ex.alloc_raw(sizeof(bf16) * (int64_t)N * S * S));
-  ex.run([&] { return softmax_rows_bf16(scores, prob, (int64_t)N * S, S, ex.stream); });
-  ex.release_raw(scores);
   Act av = ex.alloc_act(N, x.H, x.W, C);
   GemmTcOp pv;
   pv.A = prob, pv.B = vt, pv.C = av.p, pv.M = S, pv.N = C, pv.K = S, pv.batch = N;
