@@ -108,9 +108,6 @@ __global__ void __launch_bounds__(256) metrics_partial_kernel(const float* __res
 __global__ void metrics_finalize_kernel(const double* __restrict__ part, int C, int HW, int slabs, float data_range,
                                         float* __restrict__ out /*[N][2] = (mpsnr dB, sam degrees)*/) {
   const int n = blockIdx.x;
-  __shared__ double acc[2];
-  if (threadIdx.x == 0) acc[0] = 0.0;
-  __syncthreads();
   // bands in index order by one thread each, folded by thread 0 afterwards through shared memory
   extern __shared__ double band[];   // [C]
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
