@@ -379,3 +379,28 @@ def cube_metrics(truth: torch.Tensor, pred: torch.Tensor):
         out.append((mpsnr(th, ph), sam_deg(th, ph)))
     return out
 
+
+# ----------------------------------------------------------------------------------------------------------------------
+# training step (SURVEY 8f row N2 - the next scope row; pinned by tests/golden/train_step.npz)
+def q_sample(x_start: torch.Tensor, level: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """diffusion.py:213-220: level is the continuous sqrt(alpha_bar) drawn per sample, shape [B,1,1,1]."""
+    return level * x_start + (1 - level ** 2).sqrt() * noise
+
+
+def train_step(sd: SD, cfg: dict, hr: torch.Tensor, sr: torch.Tensor, noise: torch.Tensor, levels: np.ndarray,
+               loss_type: str = "l1"):
+    """One optimisation step's loss and gradients: p_losses (diffusion.py:222-250) with the per-sample noise levels
+    given, then DDPM.optimize_parameters' normalisation loss = sum / (b*c*h*w) (model.py:49-55).  Dropout is the
+    identity (the pinned configuration trains with dropout 0).  Returns (loss_sum, loss, {param: grad})."""
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    lv = torch.as_tensor(np.asarray(levels), dtype=torch.float32).view(-1, 1)   # FloatTensor(...) in the reference
+    x_noisy = q_sample(hr, lv.view(-1, 1, 1, 1), noise)
+    with torch.enable_grad():
+        eps = unet_forward(params, cfg, torch.cat([sr, x_noisy], dim=1), lv)
+        diff = noise - eps
+        loss_sum = diff.abs().sum() if loss_type == "l1" else (diff ** 2).sum()
+        b, c, h, w = hr.shape
+        loss = loss_sum / int(b * c * h * w)
+        loss.backward()
+    return float(loss_sum.detach()), float(loss.detach()), {k: v.grad for k, v in params.items()}
+

@@ -113,3 +113,27 @@ def test_end_to_end_cube_and_metrics(golden, tag):
     true = hr[0].permute(1, 2, 0).numpy()
     assert abs(O.sam_deg(true, pred) - float(g["sam"])) < 1e-3          # reference compare_sam (python loop)
     assert abs(O.mpsnr(true, pred) - float(g["mpsnr"])) < 1e-4
+
+
+@pytest.mark.parametrize("loss_type", ["l1", "l2"])
+def test_train_step_matches_reference(golden, loss_type):
+    """SURVEY 8f row N2 (next scope row): loss and gradients of one training step of the unmodified reference
+    (p_losses + optimize_parameters' normalisation) with the timestep, the per-sample noise levels and the noise
+    injected - the pin a CUDA backward will have to meet.  Vectors: oracle/make_golden_train.py."""
+    from hsi_dmgasr_b200.spec import UNetConfig
+    g = golden("train_step.npz")
+    cfg = UNetConfig(in_channel=6, out_channel=3, inner_channel=32, norm_groups=8, channel_mults=(1, 2), attn_res=(8,),
+                     res_blocks=1, dropout=0.0, image_size=16)
+    sd = synth.unet_state_dict(cfg, 51)
+    hr, sr, noise = rand((3, 3, 16, 16), 61), rand((3, 3, 16, 16), 62), rand((3, 3, 16, 16), 63)
+    loss_sum, loss, grads = O.train_step(sd, cfg.as_dict(), hr, sr, noise, g[f"{loss_type}.levels"], loss_type)
+    assert abs(loss_sum - float(g[f"{loss_type}.loss_sum"])) < 1e-4 * abs(float(g[f"{loss_type}.loss_sum"]))
+    assert abs(loss - float(g[f"{loss_type}.loss"])) < 1e-5
+    checked = 0
+    for k, gr in grads.items():
+        want_norm = float(g[f"{loss_type}.gnorm.{k}"])
+        assert abs(float(gr.double().norm()) - want_norm) <= 2e-4 * want_norm + 1e-9, k
+        if f"{loss_type}.grad.{k}" in g:
+            assert rel(gr.numpy(), g[f"{loss_type}.grad.{k}"]) < 2e-4, k
+            checked += 1
+    assert len(grads) == 124 and checked > 50
