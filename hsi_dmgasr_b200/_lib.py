@@ -54,10 +54,16 @@ SIGNATURES = {
     "hsidm_unet_param_name": (C.c_char_p, [_P, C.c_int]),
     "hsidm_unet_set_param": (C.c_int, [_P, C.c_char_p, _P, _I64P, C.c_int]),
     "hsidm_unet_commit": (C.c_int, [_P]),
+    "hsidm_unet_params_changed": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int), _P]),
+    "hsidm_gae_params_changed": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int), _P]),
+    "hsidm_check_health": (C.c_int, []),
     "hsidm_set_schedule": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "hsidm_unet_forward": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P]),
     "hsidm_posterior_step": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int64, _P]),
     "hsidm_sample": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_uint64, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "hsidm_sample_at": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "hsidm_randn": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_int64, _P]),
+    "hsidm_blend_tiles": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "hsidm_snapshot_count": (C.c_int, [_P]),
     "hsidm_num_timesteps": (C.c_int, [_P]),
     "hsidm_ctx_bytes": (C.c_int64, [_P]),
@@ -106,6 +112,14 @@ def check(status: int) -> None:
     if status != 0:
         msg = load().hsidm_last_error()
         raise HsidmError(status, msg.decode("utf-8", "replace") if msg else "")
+
+
+def check_health(device) -> None:
+    """Raise if any tensor-core launch on `device` since the last check timed out on a pipeline barrier (its output
+    would be incomplete).  Synchronises the device."""
+    import torch
+    with torch.cuda.device(device):
+        check(load().hsidm_check_health())
 
 
 def precision_code(precision) -> int:

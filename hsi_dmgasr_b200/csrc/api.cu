@@ -130,6 +130,27 @@ int hsidm_quality_metrics(const float* truth, const float* pred, int N, int C, i
   return s;
 }
 
+int hsidm_randn(float* out, int64_t n, uint64_t seed, int64_t first_element, hsidm_stream stream) {
+  if (!out || n < 0 || first_element < 0 || first_element % 4) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_randn: bad argument");
+  // step 0xFFFFFFFF: a Philox stream no loop index of hsidm_sample uses (those are t = 1 .. T-1)
+  return randn_fill(out, n, seed, 0xFFFFFFFFu, (uint64_t)first_element / 4, static_cast<cudaStream_t>(stream));
+}
+
+int hsidm_blend_tiles(const float* tiles, const int32_t* ys, int ny, const int32_t* xs, int nx, int C, int tile, int overlap,
+                      int H, int W, float* out, hsidm_stream stream) {
+  if (!tiles || !ys || !xs || !out) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_blend_tiles: null argument");
+  return blend_tiles(tiles, ys, ny, xs, nx, C, tile, overlap, H, W, out, static_cast<cudaStream_t>(stream));
+}
+
+int hsidm_check_health(void) {
+  int v = 0;
+  HSIDM_TRY(conv_tc_error_flag(&v));
+  if (v != 0)
+    HSIDM_FAIL(HSIDM_CUDA_ERROR, "a tensor-core kernel gave up waiting on a pipeline barrier (code %d): results of the calls since the "
+               "last health check are invalid", v);
+  return HSIDM_OK;
+}
+
 int hsidm_debug_conv_mode(int no_halo, int variant) {
   conv_tc_set_mode(no_halo, variant);
   return HSIDM_OK;

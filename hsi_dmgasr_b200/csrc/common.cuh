@@ -43,6 +43,32 @@ extern int64_t g_launches;  // kernels launched by this library (bench.py report
     if (_s != HSIDM_OK) return _s; \
   } while (0)
 
+// Makes `device` current for the duration of an entry point and restores the caller's device afterwards (a library
+// call must not change torch.cuda.current_device() behind the caller's back).
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) prev_ = -1;
+    err_ = prev_ == device ? cudaSuccess : cudaSetDevice(device);
+    switched_ = err_ == cudaSuccess && prev_ != device && prev_ >= 0;
+  }
+  ~DeviceGuard() {
+    if (switched_) cudaSetDevice(prev_);
+  }
+  cudaError_t error() const { return err_; }
+
+ private:
+  int prev_ = -1;
+  bool switched_ = false;
+  cudaError_t err_ = cudaSuccess;
+};
+#define HSIDM_DEVICE(dev)                                                                                   \
+  ::hsidm::DeviceGuard _device_guard(dev);                                                                  \
+  if (_device_guard.error() != cudaSuccess) {                                                               \
+    ::hsidm::set_last_error("cudaSetDevice(%d) failed: %s", (dev), cudaGetErrorString(_device_guard.error())); \
+    return HSIDM_CUDA_ERROR;                                                                                \
+  }
+
 // ---- opt-in per-kernel-class timing (bench.py's roofline leg): CUDA events around each launch on its own stream ----
 enum ProfKind { PROF_CONV_TC = 0, PROF_CONV_SIMT = 1, PROF_GN_STATS = 2, PROF_GN_APPLY = 3, PROF_GEMM = 4,
                 PROF_POSTERIOR = 5, PROF_OTHER = 6, PROF_KINDS = 7 };

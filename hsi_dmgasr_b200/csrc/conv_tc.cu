@@ -437,10 +437,13 @@ int conv_tc_stats_slots(const ConvOp& op) {
   return tc::pertap_stats_slots(op);
 }
 
+static int g_route_gen = 0;
 void conv_tc_set_mode(int no_halo, int variant) {
   tc::host().no_halo = no_halo;
   tc::host().variant = variant;
+  ++g_route_gen;   // cached CUDA graphs were captured under the previous routing
 }
+int conv_tc_route_gen() { return g_route_gen; }
 
 int conv_tc_variant() { return tc::host().variant; }
 

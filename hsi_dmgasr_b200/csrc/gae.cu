@@ -40,6 +40,7 @@ struct hsidm_gae {
   int64_t* img_off_dev = nullptr;  // [cap_B * G]
   int off_B = 0, off_H = 0, off_W = 0;
   int ws_kind = 0, ws_B = 0, ws_H = 0, ws_W = 0;
+  cudaEvent_t ev_arena = nullptr;  // completion of the previous pass over the arena (calls may come from different streams)
 };
 
 namespace {
@@ -240,7 +241,7 @@ int hsidm_gae_create(const hsidm_gae_cfg* cfg, int device, hsidm_gae** out) {
     cudaGetLastError();
     HSIDM_FAIL(HSIDM_CUDA_ERROR, "no CUDA device available (this library has no CPU path)");
   }
-  HSIDM_CUDA(cudaSetDevice(device));
+  HSIDM_DEVICE(device);
   hsidm_gae* g = new hsidm_gae();
   g->cfg = *cfg;
   g->device = device;
@@ -268,6 +269,7 @@ int hsidm_gae_create(const hsidm_gae_cfg* cfg, int device, hsidm_gae** out) {
     cudaMemcpy(g->start_dev, g->start.data(), sizeof(int) * g->G, cudaMemcpyHostToDevice);
     cudaMemcpy(g->inv_count_dev, inv.data(), sizeof(float) * cfg->n_colors, cudaMemcpyHostToDevice);
     if (cfg->precision == HSIDM_BF16) s = conv_tc_init();
+    if (s == HSIDM_OK && cudaEventCreateWithFlags(&g->ev_arena, cudaEventDisableTiming) != cudaSuccess) s = HSIDM_CUDA_ERROR;
   }
   if (s != HSIDM_OK) {
     if (s == HSIDM_CUDA_ERROR && g_last_error.empty()) set_last_error("device allocation failed in hsidm_gae_create");
@@ -280,12 +282,13 @@ int hsidm_gae_create(const hsidm_gae_cfg* cfg, int device, hsidm_gae** out) {
 
 int hsidm_gae_destroy(hsidm_gae* g) {
   if (!g) return HSIDM_OK;
-  cudaSetDevice(g->device);
+  DeviceGuard guard(g->device);
   cudaDeviceSynchronize();
   for_each_conv(g, [](ConvW& w) { free_conv(w); });
   if (g->start_dev) cudaFree(g->start_dev);
   if (g->inv_count_dev) cudaFree(g->inv_count_dev);
   if (g->img_off_dev) cudaFree(g->img_off_dev);
+  if (g->ev_arena) cudaEventDestroy(g->ev_arena);
   delete g;
   return HSIDM_OK;
 }
@@ -297,14 +300,14 @@ const char* hsidm_gae_param_name(const hsidm_gae* g, int i) {
 
 int hsidm_gae_set_param(hsidm_gae* g, const char* key, const float* data, const int64_t* shape, int ndim) {
   if (!g) HSIDM_FAIL(HSIDM_BAD_ARG, "null gae handle");
-  HSIDM_CUDA(cudaSetDevice(g->device));
+  HSIDM_DEVICE(g->device);
   g->committed = false;
   return g->ps.set(key, data, shape, ndim);
 }
 
 int hsidm_gae_commit(hsidm_gae* g) {
   if (!g) HSIDM_FAIL(HSIDM_BAD_ARG, "null gae handle");
-  HSIDM_CUDA(cudaSetDevice(g->device));
+  HSIDM_DEVICE(g->device);
   HSIDM_TRY(g->ps.check_all_set());
   int status = HSIDM_OK;
   for_each_conv(g, [&](ConvW& w) {
@@ -328,24 +331,34 @@ int hsidm_gae_groups(const hsidm_gae* g, int32_t* start, int32_t* end) {
 
 int hsidm_gae_encode(hsidm_gae* g, const float* x, float* z, int B, int H, int W, hsidm_stream stream) {
   if (!g || !x || !z) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_gae_encode: null argument");
-  HSIDM_CUDA(cudaSetDevice(g->device));
+  HSIDM_DEVICE(g->device);
   HSIDM_TRY(prepare(g, 1, B, H, W));
   Exec& ex = g->ex;
   ex.stream = static_cast<cudaStream_t>(stream), ex.dry = false, ex.status = HSIDM_OK;
   ex.arena.begin(false);
+  HSIDM_CUDA(cudaStreamWaitEvent(ex.stream, g->ev_arena, 0));
   encode_pass(g, x, z, B, H, W);
+  HSIDM_CUDA(cudaEventRecord(g->ev_arena, ex.stream));
   return ex.status;
 }
 
 int hsidm_gae_decode(hsidm_gae* g, const float* z, float* y, int B, int H, int W, int clamp01, hsidm_stream stream) {
   if (!g || !z || !y) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_gae_decode: null argument");
-  HSIDM_CUDA(cudaSetDevice(g->device));
+  HSIDM_DEVICE(g->device);
   HSIDM_TRY(prepare(g, 2, B, H, W));
   Exec& ex = g->ex;
   ex.stream = static_cast<cudaStream_t>(stream), ex.dry = false, ex.status = HSIDM_OK;
   ex.arena.begin(false);
+  HSIDM_CUDA(cudaStreamWaitEvent(ex.stream, g->ev_arena, 0));
   decode_pass(g, z, y, B, H, W, clamp01);
+  HSIDM_CUDA(cudaEventRecord(g->ev_arena, ex.stream));
   return ex.status;
+}
+
+int hsidm_gae_params_changed(hsidm_gae* g, const void* const* table_dev, int n, int* changed, hsidm_stream stream) {
+  if (!g) HSIDM_FAIL(HSIDM_BAD_ARG, "null gae handle");
+  HSIDM_DEVICE(g->device);
+  return g->ps.differs(table_dev, n, changed, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -75,6 +75,7 @@ int conv_tc_init();               // resolves cuTensorMapEncodeTiled, sets kerne
 int conv_tc_bn_rows(int Cout);    // N-tile height; packed bf16 weights are padded to a multiple of it (0 = unsupported)
 void conv_tc_set_mode(int no_halo, int variant);  // test knobs
 int conv_tc_variant();                             // current variant bits (8 = no fused input GroupNorm)
+int conv_tc_route_gen();                           // bumped by every conv_tc_set_mode call (part of the sampler's graph key)
 void conv_halo_set_timing(long long* device_counters);   // developer probe, see hsidm_debug_halo_timing
 int conv_tc_error_flag(int* v);   // barrier-timeout flag of the tensor-core kernel (synchronises; tests only)
 
@@ -172,15 +173,24 @@ struct PosteriorArgs {
   int t;               // loop index (host known) or -1 -> read *t_dev
   const int* t_dev;
   uint64_t seed;
-  const unsigned long long* seed_dev;  // optional: overrides seed (graph replay)
+  const unsigned long long* seed_dev;  // optional: overrides seed (graph replay); seed_dev[1] = first element / 4 of this
+                                       // batch in the caller's global image order (Philox counter offset)
   int use_philox;
   float* snapshot_base;   // optional: [n_snap][n] written when i % inter == 0
   int inter;
 };
 int posterior_step(const PosteriorArgs& a, cudaStream_t stream);
 int step_counter_dec(int* t_dev, cudaStream_t stream);  // *t_dev -= 1
-// state[0] = t (int), state[2..3] = seed (uint64): set from kernel arguments so no host buffer has to outlive the call
-int sampler_state_set(int* state, int t, uint64_t seed, cudaStream_t stream);
+// state[0] = t (int), state[2..3] = seed (uint64), state[4..5] = Philox counter offset in float4 units (uint64): set from
+// kernel arguments so no host buffer has to outlive the call
+int sampler_state_set(int* state, int t, uint64_t seed, uint64_t offset4, cudaStream_t stream);
+// out[i] ~ N(0,1), i in [0, n): the Philox stream (seed, step) at counter first4 + i/4 (n and out 16-byte multiples)
+int randn_fill(float* out, int64_t n, uint64_t seed, uint32_t step, uint64_t first4, cudaStream_t stream);
+// Feathered overlap-add of square tiles back into a scene (pipeline.blend_tiles): tiles [ny*nx][C][t][t] fp32 in row-major
+// tile order at origins (ys[iy], xs[ix]) (device arrays), weights = separable linear ramps over `overlap` pixels, per-pixel
+// normalisation; out [C][H][W].  Gather form, fixed summation order (iy, ix ascending): deterministic.
+int blend_tiles(const float* tiles, const int* ys, int ny, const int* xs, int nx, int C, int tile, int overlap, int H, int W,
+                float* out, cudaStream_t stream);
 
 // GAE pieces (common.py:231-271, AE.py:288-295).
 int channel_mean(const void* x, int N, int HW, int C, float* mean /*[N][C]*/, int prec, cudaStream_t stream);

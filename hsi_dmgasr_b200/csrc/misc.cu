@@ -62,7 +62,7 @@ __global__ void posterior_kernel(PosteriorArgs a) {
         const int64_t j = a.T - 1 - t;
         z = *reinterpret_cast<const float4*>(a.noise + img * a.tape_image_stride + j * a.tape_step_stride + r);
       } else {
-        z = philox_normal4(a.seed_dev ? (uint64_t)*a.seed_dev : a.seed, (uint32_t)t, (uint64_t)i);
+        z = philox_normal4(a.seed_dev ? (uint64_t)a.seed_dev[0] : a.seed, (uint32_t)t, (uint64_t)i + (a.seed_dev ? (uint64_t)a.seed_dev[1] : 0ull));
       }
     }
     float4 o;
@@ -82,11 +82,16 @@ __global__ void posterior_kernel(PosteriorArgs a) {
 __global__ void dec_kernel(int* t) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *t -= 1;
 }
-__global__ void state_set_kernel(int* state, int t, unsigned long long seed) {
+__global__ void state_set_kernel(int* state, int t, unsigned long long seed, unsigned long long offset4) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     state[0] = t;
-    *reinterpret_cast<unsigned long long*>(state + 2) = seed;
+    reinterpret_cast<unsigned long long*>(state + 2)[0] = seed;
+    reinterpret_cast<unsigned long long*>(state + 2)[1] = offset4;
   }
+}
+__global__ void randn_kernel(float4* __restrict__ out, int64_t n4, unsigned long long seed, uint32_t step, unsigned long long first4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = philox_normal4(seed, step, first4 + (uint64_t)i);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -365,9 +370,17 @@ int step_counter_dec(int* t_dev, cudaStream_t stream) {
   return after_launch("dec_kernel");
 }
 
-int sampler_state_set(int* state, int t, uint64_t seed, cudaStream_t stream) {
-  state_set_kernel<<<1, 32, 0, stream>>>(state, t, (unsigned long long)seed);
+int sampler_state_set(int* state, int t, uint64_t seed, uint64_t offset4, cudaStream_t stream) {
+  state_set_kernel<<<1, 32, 0, stream>>>(state, t, (unsigned long long)seed, (unsigned long long)offset4);
   return after_launch("state_set_kernel");
+}
+
+int randn_fill(float* out, int64_t n, uint64_t seed, uint32_t step, uint64_t first4, cudaStream_t stream) {
+  if (n % 4 || ((uintptr_t)out & 15)) HSIDM_FAIL(HSIDM_BAD_ARG, "randn_fill: count and pointer must be multiples of 4 floats");
+  if (n == 0) return HSIDM_OK;
+  randn_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(reinterpret_cast<float4*>(out), n / 4, (unsigned long long)seed, step,
+                                                          (unsigned long long)first4);
+  return after_launch("randn_kernel");
 }
 
 int noise_embed(const float* level, int level_stride, int n, int dim, const float* w1, const float* b1, const float* w3,

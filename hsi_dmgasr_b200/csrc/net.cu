@@ -8,6 +8,46 @@ namespace hsidm {
 // ---- ParamStore ---------------------------------------------------------------------------------------------
 ParamStore::~ParamStore() {
   if (slab_) cudaFree(slab_);
+  if (cmp_meta_) cudaFree(cmp_meta_);
+  if (cmp_flag_) cudaFree(cmp_flag_);
+}
+
+namespace {
+// block (i, j): elements j*blockDim.x + t, stride gridDim.y*blockDim.x of parameter i, compared as raw 32-bit words
+__global__ void params_differ_kernel(const uint32_t* __restrict__ slab, const int64_t* __restrict__ meta,
+                                     const void* const* __restrict__ table, int* __restrict__ flag) {
+  const int i = blockIdx.x;
+  const uint32_t* a = slab + meta[2 * i];
+  const uint32_t* b = static_cast<const uint32_t*>(table[i]);
+  const int64_t n = meta[2 * i + 1];
+  bool diff = false;
+  for (int64_t k = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.y * blockDim.x)
+    diff |= a[k] != b[k];
+  if (__syncthreads_or(diff) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+}  // namespace
+
+int ParamStore::differs(const void* const* table_dev, int n, int* changed, cudaStream_t stream) {
+  if (!table_dev || !changed) HSIDM_FAIL(HSIDM_BAD_ARG, "params_changed: null argument");
+  if (n != size()) HSIDM_FAIL(HSIDM_BAD_ARG, "params_changed: table has %d entries, the context has %d parameters", n, size());
+  for (auto& p : params_)
+    if (!p.set) {   // nothing uploaded yet: everything counts as changed
+      *changed = 1;
+      return HSIDM_OK;
+    }
+  if (!cmp_meta_) {
+    std::vector<int64_t> meta(2 * params_.size());
+    for (size_t i = 0; i < params_.size(); ++i) meta[2 * i] = params_[i].dev - slab_, meta[2 * i + 1] = params_[i].numel();
+    HSIDM_CUDA(cudaMalloc(&cmp_meta_, sizeof(int64_t) * meta.size()));
+    HSIDM_CUDA(cudaMemcpy(cmp_meta_, meta.data(), sizeof(int64_t) * meta.size(), cudaMemcpyHostToDevice));
+    HSIDM_CUDA(cudaMalloc(&cmp_flag_, sizeof(int)));
+  }
+  HSIDM_CUDA(cudaMemsetAsync(cmp_flag_, 0, sizeof(int), stream));
+  params_differ_kernel<<<dim3(n, 16), 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(slab_), cmp_meta_, table_dev, cmp_flag_);
+  HSIDM_TRY(after_launch("params_differ_kernel"));
+  HSIDM_CUDA(cudaMemcpyAsync(changed, cmp_flag_, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  HSIDM_CUDA(cudaStreamSynchronize(stream));
+  return HSIDM_OK;
 }
 
 int ParamStore::add(const std::string& key, std::vector<int64_t> shape) {

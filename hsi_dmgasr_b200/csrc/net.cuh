@@ -33,11 +33,16 @@ class ParamStore {
   int size() const { return (int)params_.size(); }
   const Param& at(int i) const { return params_[i]; }
   int64_t bytes() const { return slab_bytes_; }
+  // Bitwise comparison of the stored fp32 master copies with the caller's current tensors: `table_dev` is a DEVICE array
+  // of size() device pointers in parameter order.  *changed = 1 if any element differs.  Synchronises `stream`.
+  int differs(const void* const* table_dev, int n, int* changed, cudaStream_t stream);
 
  private:
   std::vector<Param> params_;
   float* slab_ = nullptr;
   int64_t slab_bytes_ = 0;
+  int64_t* cmp_meta_ = nullptr;   // device [size()][2] = (slab offset in floats, numel)
+  int* cmp_flag_ = nullptr;       // device flag
 };
 
 // One convolution's parameters and packed copies.

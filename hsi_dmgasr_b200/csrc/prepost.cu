@@ -128,6 +128,43 @@ __global__ void metrics_finalize_kernel(const double* __restrict__ part, int C, 
   }
 }
 
+
+// Feathered overlap-add, gather form: one thread per scene pixel, all bands.  ramp(d) = (d+1)/(ov+1) over the first / last
+// `ov` pixels of a tile, 1 inside; weight = ramp_y * ramp_x (fp32 product, as pipeline.feather_window builds it); each band
+// accumulates tile * weight in ascending (iy, ix) order and divides by the weight sum: the same operations in the same
+// order as the host reference in tests/, so the result is bit-identical to it.
+__global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ tiles, const int* __restrict__ ys, int ny,
+                                                    const int* __restrict__ xs, int nx, int C, int t, int ov, int H, int W,
+                                                    float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  auto ramp = [&](int d) {
+    if (d < ov) return __fdiv_rn((float)d + 1.0f, (float)ov + 1.0f);
+    if (d >= t - ov) return __fdiv_rn((float)(t - 1 - d) + 1.0f, (float)ov + 1.0f);
+    return 1.0f;
+  };
+  // covering tiles along each axis (at most a handful)
+  int iy[8], ix[8], cy = 0, cx = 0;
+  for (int i = 0; i < ny && cy < 8; ++i)
+    if (y >= ys[i] && y < ys[i] + t) iy[cy++] = i;
+  for (int i = 0; i < nx && cx < 8; ++i)
+    if (x >= xs[i] && x < xs[i] + t) ix[cx++] = i;
+  float wsum = 0.f;
+  for (int a = 0; a < cy; ++a)
+    for (int b = 0; b < cx; ++b) wsum = __fadd_rn(wsum, __fmul_rn(ramp(y - ys[iy[a]]), ramp(x - xs[ix[b]])));
+  const long long tt = (long long)t * t;
+  for (int c = 0; c < C; ++c) {
+    float acc = 0.f;
+    for (int a = 0; a < cy; ++a)
+      for (int b = 0; b < cx; ++b) {
+        const int dy = y - ys[iy[a]], dx = x - xs[ix[b]];
+        const float w = __fmul_rn(ramp(dy), ramp(dx));
+        const float v = __ldg(tiles + (((long long)iy[a] * nx + ix[b]) * C + c) * tt + (long long)dy * t + dx);
+        acc = __fadd_rn(acc, __fmul_rn(v, w));
+      }
+    out[((long long)c * H + y) * W + x] = __fdiv_rn(acc, wsum);
+  }
+}
 }  // namespace
 
 int bicubic_upsample(const float* src, float* dst, int planes, int h, int w, int scale, int clamp01, cudaStream_t stream) {
@@ -157,4 +194,16 @@ int quality_metrics(const float* truth, const float* pred, int N, int C, int HW,
   return after_launch("metrics_finalize_kernel");
 }
 
+}  // namespace hsidm
+
+namespace hsidm {
+int blend_tiles(const float* tiles, const int* ys, int ny, const int* xs, int nx, int C, int tile, int overlap, int H, int W,
+                float* out, cudaStream_t stream) {
+  if (ny <= 0 || nx <= 0 || C <= 0 || tile <= 0 || overlap < 0 || 2 * overlap > tile || H < tile || W < tile)
+    HSIDM_FAIL(HSIDM_BAD_SHAPE, "blend_tiles: bad geometry (%dx%d tiles of %d, overlap %d, scene %dx%d)", ny, nx, tile, overlap, H, W);
+  if (H > 65535) HSIDM_FAIL(HSIDM_BAD_SHAPE, "blend_tiles: scene height %d exceeds 65535 rows", H);
+  ProfScope prof(PROF_OTHER, 4.0 * ((double)ny * nx * C * tile * tile + (double)C * H * W), stream, "blend_tiles");
+  blend_kernel<<<dim3((unsigned)ceil_div(W, 256), (unsigned)H), 256, 0, stream>>>(tiles, ys, ny, xs, nx, C, tile, overlap, H, W, out);
+  return after_launch("blend_kernel");
+}
 }  // namespace hsidm

@@ -76,11 +76,17 @@ struct hsidm_ctx {
     const float* tape = nullptr;
     int64_t s_img = 0, s_step = 0;
     float* snaps = nullptr;
+    int weight_gen = 0, route_gen = 0;   // packed weights / tables and kernel routing the captured nodes point at
     bool operator==(const GraphKey& o) const {
-      return N == o.N && H == o.H && W == o.W && tape == o.tape && s_img == o.s_img && s_step == o.s_step && snaps == o.snaps;
+      return N == o.N && H == o.H && W == o.W && tape == o.tape && s_img == o.s_img && s_step == o.s_step && snaps == o.snaps &&
+             weight_gen == o.weight_gen && route_gen == o.route_gen;
     }
   } graph_key;
   int64_t graph_nodes = 0;  // kernels per replay (for hsidm_launch_count)
+  int weight_gen = 0;       // bumped whenever packed weights or the noise-embedding table are (re)allocated
+  // The arena, packed weights and tables are shared by every entry point, which may be called on different streams
+  // (hsidm_unet_forward on the caller's, hsidm_sample on `side`): each pass waits for the previous one's completion.
+  cudaEvent_t ev_arena = nullptr;
   // hsidm_sample runs on its own non-blocking stream (the caller's may be the legacy default stream, which cannot
   // be captured) and is stitched into the caller's stream with two events
   cudaStream_t side = nullptr;
@@ -670,7 +676,10 @@ int run_forward(hsidm_ctx* c, const float* x0, int c0, const float* x1, int c1, 
 int ensure_table(hsidm_ctx* c, cudaStream_t stream) {
   if (!c->table_dirty) return HSIDM_OK;
   if (c->T <= 0) HSIDM_FAIL(HSIDM_BAD_STATE, "hsidm_set_schedule has not been called");
+  drop_graph(c);   // a cached graph holds the old table pointer
+  ++c->weight_gen;
   if (c->nbias_table) cudaFree(c->nbias_table);
+  c->nbias_table = nullptr;
   HSIDM_CUDA(cudaMalloc(&c->nbias_table, sizeof(float) * (int64_t)c->T * c->noise_total));
   HSIDM_TRY(noise_embed(c->levels_dev, 1, c->T, c->cfg.inner_channel, c->ps.dev(c->mlp1_w), c->ps.dev(c->mlp1_b),
                         c->ps.dev(c->mlp3_w), c->ps.dev(c->mlp3_b), c->noise_layers_dev,
@@ -700,18 +709,19 @@ int hsidm_ctx_create(const hsidm_unet_cfg* cfg, int device, hsidm_ctx** out) {
     cudaGetLastError();
     HSIDM_FAIL(HSIDM_CUDA_ERROR, "no CUDA device available (this library has no CPU path)");
   }
-  HSIDM_CUDA(cudaSetDevice(device));
+  HSIDM_DEVICE(device);
   hsidm_ctx* c = new hsidm_ctx();
   c->cfg = *cfg;
   c->device = device;
   c->ex.prec = cfg->precision;
   build_layers(c);
   int s = c->ps.alloc_all();
-  if (s == HSIDM_OK && cudaMalloc(&c->t_dev, 4 * sizeof(int)) != cudaSuccess) s = HSIDM_CUDA_ERROR;
+  if (s == HSIDM_OK && cudaMalloc(&c->t_dev, 8 * sizeof(int)) != cudaSuccess) s = HSIDM_CUDA_ERROR;
   if (s == HSIDM_OK && cfg->precision == HSIDM_BF16) s = conv_tc_init();
   if (s == HSIDM_OK && (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
                         cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
-                        cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess)) {
+                        cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&c->ev_arena, cudaEventDisableTiming) != cudaSuccess)) {
     set_last_error("could not create the sampler stream/events");
     s = HSIDM_CUDA_ERROR;
   }
@@ -725,7 +735,7 @@ int hsidm_ctx_create(const hsidm_unet_cfg* cfg, int device, hsidm_ctx** out) {
 
 int hsidm_ctx_destroy(hsidm_ctx* c) {
   if (!c) return HSIDM_OK;
-  cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
   cudaDeviceSynchronize();
   drop_graph(c);
   for_each_conv(c, [](ConvW& w) { free_conv(w); });
@@ -742,6 +752,7 @@ int hsidm_ctx_destroy(hsidm_ctx* c) {
   if (c->side) cudaStreamDestroy(c->side);
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_out) cudaEventDestroy(c->ev_out);
+  if (c->ev_arena) cudaEventDestroy(c->ev_arena);
   delete c;
   return HSIDM_OK;
 }
@@ -753,7 +764,7 @@ const char* hsidm_unet_param_name(const hsidm_ctx* c, int i) {
 
 int hsidm_unet_set_param(hsidm_ctx* c, const char* key, const float* data, const int64_t* shape, int ndim) {
   if (!c) HSIDM_FAIL(HSIDM_BAD_ARG, "null context");
-  HSIDM_CUDA(cudaSetDevice(c->device));
+  HSIDM_DEVICE(c->device);
   c->committed = false;
   drop_graph(c);
   return c->ps.set(key, data, shape, ndim);
@@ -761,8 +772,10 @@ int hsidm_unet_set_param(hsidm_ctx* c, const char* key, const float* data, const
 
 int hsidm_unet_commit(hsidm_ctx* c) {
   if (!c) HSIDM_FAIL(HSIDM_BAD_ARG, "null context");
-  HSIDM_CUDA(cudaSetDevice(c->device));
+  HSIDM_DEVICE(c->device);
   HSIDM_TRY(c->ps.check_all_set());
+  drop_graph(c);   // every packed buffer is freed and reallocated below: a cached graph would replay dangling pointers
+  ++c->weight_gen;
   int status = HSIDM_OK;
   c->packed_bytes = 0;
   for_each_conv(c, [&](ConvW& w) {
@@ -818,7 +831,7 @@ int hsidm_unet_commit(hsidm_ctx* c) {
 
 int hsidm_set_schedule(hsidm_ctx* c, const double* betas, int T) {
   if (!c || !betas || T <= 0) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_set_schedule: bad argument");
-  HSIDM_CUDA(cudaSetDevice(c->device));
+  HSIDM_DEVICE(c->device);
   drop_graph(c);
   // float64 tables then fp32 casts, as set_new_noise_schedule does (diffusion.py:103-140)
   std::vector<float> coef((size_t)T * 5), levels(T);
@@ -864,7 +877,7 @@ int hsidm_unet_forward(hsidm_ctx* c, const float* x0, int c0, const float* x1, i
   if (!c || !x0 || !noise_level || !eps_out) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_unet_forward: null argument");
   if (c1 > 0 && !x1) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_unet_forward: c1 > 0 but x1 is null");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  HSIDM_CUDA(cudaSetDevice(c->device));
+  HSIDM_DEVICE(c->device);
   HSIDM_TRY(check_shape(c, c0, c1, N, H, W));
   HSIDM_TRY(ensure_workspace(c, c0, c1, N, H, W));
   if (c->nbias_cap < N) {
@@ -877,11 +890,15 @@ int hsidm_unet_forward(hsidm_ctx* c, const float* x0, int c0, const float* x1, i
     c->nbias_cap = N;
   }
   const int n_emb = level_stride == 0 ? 1 : N;
+  HSIDM_CUDA(cudaStreamWaitEvent(stream, c->ev_arena, 0));
   HSIDM_TRY(noise_embed(noise_level, level_stride, n_emb, c->cfg.inner_channel, c->ps.dev(c->mlp1_w), c->ps.dev(c->mlp1_b),
                         c->ps.dev(c->mlp3_w), c->ps.dev(c->mlp3_b), c->noise_layers_dev, (int)c->noise_layers_host.size(),
                         c->noise_total, c->nbias_buf, stream));
   NoiseRef nz{c->nbias_buf, level_stride == 0 ? 0 : (int64_t)c->noise_total, nullptr, 0};
-  return run_forward(c, x0, c0, x1, c1, nz, eps_out, N, H, W, stream);
+  HSIDM_CUDA(cudaStreamWaitEvent(stream, c->ev_arena, 0));   // the previous pass over the arena, whatever stream it ran on
+  const int s = run_forward(c, x0, c0, x1, c1, nz, eps_out, N, H, W, stream);
+  HSIDM_CUDA(cudaEventRecord(c->ev_arena, stream));
+  return s;
 }
 
 int hsidm_posterior_step(hsidm_ctx* c, int t, const float* x_t, const float* eps, const float* noise, float* x_prev,
@@ -889,7 +906,7 @@ int hsidm_posterior_step(hsidm_ctx* c, int t, const float* x_t, const float* eps
   if (!c || !x_t || !eps || !x_prev) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_posterior_step: null argument");
   if (c->T <= 0) HSIDM_FAIL(HSIDM_BAD_STATE, "hsidm_set_schedule has not been called");
   if (t < 0 || t >= c->T) HSIDM_FAIL(HSIDM_BAD_ARG, "timestep %d outside [0,%d)", t, c->T);
-  HSIDM_CUDA(cudaSetDevice(c->device));
+  HSIDM_DEVICE(c->device);
   PosteriorArgs a{};
   a.x_t = x_t, a.eps = eps, a.noise = noise, a.x_prev = x_prev, a.n = n;
   a.per_image = n, a.tape_image_stride = 0, a.tape_step_stride = 0;  // noise is given for this very step
@@ -902,10 +919,17 @@ int hsidm_posterior_step(hsidm_ctx* c, int t, const float* x_t, const float* eps
 int hsidm_sample(hsidm_ctx* c, const float* cond, const float* x_T, const float* noise_tape, int64_t tape_image_stride,
                  int64_t tape_step_stride, uint64_t seed, float* out, float* snapshots, int N, int H, int W,
                  hsidm_stream stream_) {
+  return hsidm_sample_at(c, cond, x_T, noise_tape, tape_image_stride, tape_step_stride, seed, 0, out, snapshots, N, H, W, stream_);
+}
+
+int hsidm_sample_at(hsidm_ctx* c, const float* cond, const float* x_T, const float* noise_tape, int64_t tape_image_stride,
+                    int64_t tape_step_stride, uint64_t seed, int64_t first_image, float* out, float* snapshots, int N, int H,
+                    int W, hsidm_stream stream_) {
   if (!c || !cond || !x_T || !out) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_sample: null argument");
+  if (first_image < 0) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_sample_at: negative first_image");
   cudaStream_t caller = static_cast<cudaStream_t>(stream_);
   cudaStream_t stream = c->side;
-  HSIDM_CUDA(cudaSetDevice(c->device));
+  HSIDM_DEVICE(c->device);
   if (c->cfg.in_channel % 2 || c->cfg.out_channel * 2 != c->cfg.in_channel)
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conditional sampling needs in_channel == 2*out_channel (diffusion.py:158)");
   const int ch = c->cfg.out_channel;
@@ -929,7 +953,9 @@ int hsidm_sample(hsidm_ctx* c, const float* cond, const float* x_T, const float*
   // everything below is ordered after the caller's prior work ...
   HSIDM_CUDA(cudaEventRecord(c->ev_in, caller));
   HSIDM_CUDA(cudaStreamWaitEvent(stream, c->ev_in, 0));
+  HSIDM_CUDA(cudaStreamWaitEvent(stream, c->ev_arena, 0));
   hsidm_ctx::GraphKey key;
+  key.weight_gen = c->weight_gen, key.route_gen = conv_tc_route_gen();
   key.N = N, key.H = H, key.W = W, key.tape = noise_tape, key.s_img = tape_image_stride, key.s_step = tape_step_stride;
   key.snaps = snapshots;
   if (c->graph_exec && !(c->graph_key == key)) drop_graph(c);
@@ -969,7 +995,7 @@ int hsidm_sample(hsidm_ctx* c, const float* cond, const float* x_T, const float*
   }
   HSIDM_CUDA(cudaMemcpyAsync(cond_b, cond, sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
   HSIDM_CUDA(cudaMemcpyAsync(x_b, x_T, sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
-  HSIDM_TRY(sampler_state_set(c->t_dev, c->T - 1, seed, stream));
+  HSIDM_TRY(sampler_state_set(c->t_dev, c->T - 1, seed, (uint64_t)first_image * (uint64_t)(per_image / 4), stream));
   for (int i = 0; i < c->T; ++i) {
     HSIDM_CUDA(cudaGraphLaunch(c->graph_exec, stream));
     g_launches += c->graph_nodes;
@@ -977,8 +1003,15 @@ int hsidm_sample(hsidm_ctx* c, const float* cond, const float* x_T, const float*
   HSIDM_CUDA(cudaMemcpyAsync(out, x_b, sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
   // ... and the caller's later work is ordered after the sampler
   HSIDM_CUDA(cudaEventRecord(c->ev_out, stream));
+  HSIDM_CUDA(cudaEventRecord(c->ev_arena, stream));
   HSIDM_CUDA(cudaStreamWaitEvent(caller, c->ev_out, 0));
   return HSIDM_OK;
+}
+
+int hsidm_unet_params_changed(hsidm_ctx* c, const void* const* table_dev, int n, int* changed, hsidm_stream stream) {
+  if (!c) HSIDM_FAIL(HSIDM_BAD_ARG, "null context");
+  HSIDM_DEVICE(c->device);
+  return c->ps.differs(table_dev, n, changed, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

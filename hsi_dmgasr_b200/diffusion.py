@@ -8,6 +8,7 @@ latent images it is given.  ``p_sample`` / ``p_mean_variance`` keep the referenc
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -28,6 +29,13 @@ class GaussianDiffusion(nn.Module):
         self.conditional = conditional
         self.num_timesteps = 0
         self._betas64: Optional[np.ndarray] = None
+        # Where the random draws of p_sample_loop come from when the caller injects none:
+        #   "philox" (default): x_T from torch.randn, per-step noise from the library's counter-based generator inside the
+        #            CUDA-graph loop (hsidm_sample);
+        #   "torch":  exactly the reference's call sequence - torch.randn(shape) once, then torch.randn_like(x) for
+        #            t = T-1 .. 1 (diffusion.py:174, 192) - through the step-wise path, so a driver that seeds or patches
+        #            torch's generators sees the same stream of draws as with the reference.
+        self.rng_mode = os.environ.get("HSIDM_RNG", "philox")
         # like the reference (diffusion.py:82-84) the schedule is NOT installed here; DDPM.__init__ does it.
 
     # ---- schedule -------------------------------------------------------------------------------------------
@@ -113,7 +121,7 @@ class GaussianDiffusion(nn.Module):
 
     # ---- whole loop -----------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def p_sample_loop(self, x_in, continous=False, *, x_T=None, noise_tape=None, return_all=False, seed=None):
+    def p_sample_loop(self, x_in, continous=False, *, x_T=None, noise_tape=None, return_all=False, seed=None, first_image=0):
         """diffusion.py:177-201.
 
         Conditional: ``x_in`` is the condition [N,c,H,W]; all N images are sampled as one batch.
@@ -122,6 +130,10 @@ class GaussianDiffusion(nn.Module):
         default generator.  Return shapes follow the reference: ``continous`` -> cat([x_in, snapshots...], 0);
         else the LAST batch element of the final image as a 3-D tensor (diffusion.py:198-201), unless
         ``return_all`` asks for the whole batch [N,c,H,W].
+
+        ``seed`` (explicit) makes every draw - x_T included - come from the library's counter-based generator, keyed
+        by (seed, position of the image in the caller's list): with ``first_image`` = index of this batch's first image
+        in that list, an image gets the same noise whatever batch or GPU it is sampled in.
         """
         device = self.betas.device
         if not self.conditional:
@@ -136,8 +148,26 @@ class GaussianDiffusion(nn.Module):
             return ret if continous else (img if return_all else ret[-1])
         cond = _lib.require_cuda_f32(x_in, "x_in")
         n, c, hh, ww = cond.shape
+        if self.rng_mode == "torch" and x_T is None and noise_tape is None:
+            # the reference's own loop, draw for draw (diffusion.py:188-201)
+            img = torch.randn(cond.shape, device=device)
+            ret_img = cond
+            inter = 1 | (self.num_timesteps // 10)
+            for i in reversed(range(self.num_timesteps)):
+                img = self.p_sample(img, i, condition_x=cond)
+                if i % inter == 0:
+                    ret_img = torch.cat([ret_img, img], dim=0)
+            if continous:
+                return ret_img
+            return img if return_all else ret_img[-1]
+        if self.rng_mode not in ("philox", "torch"):
+            raise ValueError(f"rng_mode must be 'philox' or 'torch', not {self.rng_mode!r}")
         h = self._native(cond.device)
         lib = _lib.load()
+        if x_T is None and seed is not None:
+            x_T = torch.empty_like(cond)
+            _lib.check(lib.hsidm_randn(x_T.data_ptr(), x_T.numel(), int(seed), int(first_image) * c * hh * ww,
+                                       _lib.stream_ptr(cond.device)))
         x_T = torch.randn(cond.shape, device=cond.device) if x_T is None else _lib.require_cuda_f32(x_T, "x_T")
         if tuple(x_T.shape) != tuple(cond.shape):
             raise _lib.HsidmError(-1, f"x_T shape {tuple(x_T.shape)} != condition shape {tuple(cond.shape)}")
@@ -155,8 +185,8 @@ class GaussianDiffusion(nn.Module):
         if continous:
             n_snap = lib.hsidm_snapshot_count(h.ptr)
             snaps = torch.empty((n_snap,) + tuple(cond.shape), device=cond.device, dtype=torch.float32)
-        _lib.check(lib.hsidm_sample(h.ptr, cond.data_ptr(), x_T.data_ptr(), tape_ptr, s_img, s_step, seed, out.data_ptr(),
-                                    _lib.ptr(snaps), n, hh, ww, _lib.stream_ptr(cond.device)))
+        _lib.check(lib.hsidm_sample_at(h.ptr, cond.data_ptr(), x_T.data_ptr(), tape_ptr, s_img, s_step, seed, int(first_image),
+                                       out.data_ptr(), _lib.ptr(snaps), n, hh, ww, _lib.stream_ptr(cond.device)))
         if continous:
             return torch.cat([cond, snaps.reshape(-1, c, hh, ww)], dim=0)
         return out if return_all else out[-1]

@@ -114,9 +114,28 @@ class _GAEHandle:
         idx = device.index if device.index is not None else torch.cuda.current_device()
         _lib.check(lib.hsidm_gae_create(C.byref(c), idx, C.byref(self.ptr)))
         self.param_sig = None
+        self._ptr_table = None
+
+    def keys(self):
+        lib = _lib.load()
+        return [lib.hsidm_gae_param_name(self.ptr, i).decode() for i in range(lib.hsidm_gae_param_count(self.ptr))]
+
+    def data_changed(self, named_params: dict) -> bool:
+        """Bitwise comparison of the library's weight copies with the live tensors (in-place ``.data`` edits)."""
+        params = [named_params[k] for k in self.keys()]
+        if not all(p.device == self.device and p.dtype == torch.float32 and p.is_contiguous() for p in params):
+            return True
+        ptrs = tuple(p.data_ptr() for p in params)
+        if self._ptr_table is None or self._ptr_table[0] != ptrs:
+            self._ptr_table = (ptrs, torch.tensor(ptrs, dtype=torch.int64, device=self.device))
+        changed = C.c_int(0)
+        _lib.check(_lib.load().hsidm_gae_params_changed(self.ptr, self._ptr_table[1].data_ptr(), len(ptrs), C.byref(changed),
+                                                        _lib.stream_ptr(self.device)))
+        return changed.value != 0
 
     def upload(self, state: dict) -> None:
         lib = _lib.load()
+        torch.cuda.current_stream(self.device).synchronize()   # set_param copies on the legacy stream
         for i in range(lib.hsidm_gae_param_count(self.ptr)):
             key = lib.hsidm_gae_param_name(self.ptr, i).decode()
             t = state[key].detach().to(device=self.device, dtype=torch.float32).contiguous()
@@ -156,6 +175,11 @@ class GAE(nn.Module):
         self.start_idx, self.end_idx = geom.groups()
         self.precision = precision
 
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_native", None)          # the hsidm_gae handle is process-local
+        return state
+
     # ---- geometry is re-derived from the tensors so that unpickled reference objects (no __init__) work too ----------
     def geometry(self) -> GAEGeometry:
         head = self.Encoder.branch.head.weight
@@ -181,10 +205,17 @@ class GAE(nn.Module):
             h = _GAEHandle(self.geometry(), precision, device)
             self.__dict__["_native"] = h
         sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if h.param_sig != sig:
+        if h.param_sig != sig or (self.__dict__.get("track_data_edits", True) and h.data_changed(dict(self.named_parameters()))):
             h.upload(dict(self.state_dict()))
             h.param_sig = sig
         return h
+
+    def invalidate_native(self) -> "GAE":
+        """Force a re-upload of every weight on the next encode/decode."""
+        h = self.__dict__.get("_native")
+        if h is not None:
+            h.param_sig = None
+        return self
 
     @torch.no_grad()
     def encode_batched(self, x: torch.Tensor) -> torch.Tensor:
@@ -242,13 +273,30 @@ _PICKLE_CLASSES = {
 }
 
 
+# Exact (module, name) pairs a whole-module GAE pickle may reference besides the remapped classes above: what the four
+# shipped GAE_4_*.pth name (inspected with pickletools) plus the storage / rebuild helpers newer torch versions emit.
+# Nothing under builtins / numpy / torch.hub is reachable: no eval, exec, getattr, __import__ or os.system.
+_PICKLE_GLOBALS = {
+    ("collections", "OrderedDict"), ("__builtin__", "set"), ("builtins", "set"),
+    ("torch", "device"), ("torch", "Size"), ("torch", "FloatStorage"), ("torch", "HalfStorage"), ("torch", "BFloat16Storage"),
+    ("torch", "DoubleStorage"), ("torch", "LongStorage"), ("torch", "IntStorage"), ("torch", "BoolStorage"),
+    ("torch.storage", "UntypedStorage"), ("torch.storage", "TypedStorage"),
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_parameter"),
+    ("torch._utils", "_rebuild_parameter_with_state"), ("torch.nn.parameter", "Parameter"),
+    ("torch.nn.modules.activation", "LeakyReLU"), ("torch.nn.modules.activation", "ReLU"),
+    ("torch.nn.modules.activation", "Sigmoid"), ("torch.nn.modules.container", "Sequential"),
+    ("torch.nn.modules.conv", "Conv2d"), ("torch.nn.modules.pooling", "AdaptiveAvgPool2d"),
+}
+
+
 class _RemapUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         hit = _PICKLE_CLASSES.get((module, name))
         if hit is not None:
             return hit
-        if module.split(".")[0] not in ("torch", "collections", "numpy", "builtins", "__builtin__", "_codecs", "copyreg"):
-            raise pickle.UnpicklingError(f"refusing to import {module}.{name} while loading a GAE checkpoint")
+        if (module, name) not in _PICKLE_GLOBALS:
+            raise pickle.UnpicklingError(f"refusing to import {module}.{name} while loading a GAE checkpoint "
+                                         "(not on the exact allow-list of hsi_dmgasr_b200.gae)")
         return super().find_class(module, name)
 
 
@@ -265,6 +313,42 @@ class _PickleModule:
     UnpicklingError = pickle.UnpicklingError
 
 
+def save_reference_style_pickle(gae: "GAE", path: str) -> str:
+    """Write `gae` as a whole-module pickle laid out like the reference's ``torch.save(model, 'GAE_4_*.pth')`` from
+    ``AE.py`` run as a script (AE.py:637): classes named ``__main__.{GAE,Encoder,Decoder,BranchUnit,SSPN,SSB}`` and
+    ``common.{ResBlock,ResAttentionBlock,CALayer,Upsampler}``.  Used to exercise the pickle loader on boxes that do not
+    have the reference tree, and to hand a GAE back to reference-side tooling."""
+    import sys
+    import types
+    remap = {cls: (mod, name) for (mod, name), cls in _PICKLE_CLASSES.items() if mod in ("__main__", "common")}
+    saved_mod = {cls: cls.__module__ for cls in remap}
+    saved_sys = {m: sys.modules.get(m) for m in ("common",)}
+    main = sys.modules["__main__"]
+    saved_main = {name: getattr(main, name, None) for cls, (mod, name) in remap.items() if mod == "__main__"}
+    common = types.ModuleType("common")
+    try:
+        for cls, (mod, name) in remap.items():
+            cls.__module__ = mod
+            setattr(main if mod == "__main__" else common, name, cls)
+        sys.modules["common"] = common
+        torch.save(gae, path)
+    finally:
+        for cls, mod in saved_mod.items():
+            cls.__module__ = mod
+        for name, old in saved_main.items():
+            if old is None:
+                if hasattr(main, name):
+                    delattr(main, name)
+            else:
+                setattr(main, name, old)
+        for m, old in saved_sys.items():
+            if old is None:
+                sys.modules.pop(m, None)
+            else:
+                sys.modules[m] = old
+    return path
+
+
 GAE_STATE_FORMAT = "hsidm-gae-state-v1"
 
 
@@ -279,12 +363,19 @@ def save_gae_state(gae: GAE, path: str) -> str:
     return path
 
 
-def load_gae(path: str, map_location="cpu", precision: str = "fp32") -> GAE:
+def load_gae(path: str, map_location="cpu", precision: str = "fp32", allow_pickle: bool = True) -> GAE:
     """Load ``GAE_pretrained/GAE_4_*.pth`` (whole-module pickle, AE.py:637), a ``save_gae_state`` file, or a plain
-    ``state_dict`` file."""
+    ``state_dict`` file.
+
+    Tensors-only files load with ``weights_only=True``.  Only when that is refused because the file names classes
+    (an ``UnpicklingError``; any other failure propagates) and ``allow_pickle`` is true does the remapping unpickler
+    run; it resolves an exact allow-list of (module, name) pairs - the GAE classes of this module and the handful of
+    ``torch`` / ``collections`` globals a module pickle needs - and refuses everything else, ``builtins`` included."""
     try:   # tensors-only files first: no unpickling of arbitrary globals
         obj = torch.load(path, map_location=map_location, weights_only=True)
-    except Exception:
+    except pickle.UnpicklingError:
+        if not allow_pickle:
+            raise
         obj = torch.load(path, map_location=map_location, weights_only=False, pickle_module=_PickleModule)
     if isinstance(obj, dict) and obj.get("format") == GAE_STATE_FORMAT:
         geo = obj["geometry"]

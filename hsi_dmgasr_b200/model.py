@@ -14,7 +14,7 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
-from . import networks
+from . import _lib, networks
 
 logger = logging.getLogger("base")
 
@@ -59,6 +59,7 @@ class DDPM:
         self.netG.eval()
         with torch.no_grad():
             self.SR = self.netG.super_resolution(self.data["SR"], continous)
+        _lib.check_health(self.SR.device)
         self.netG.train()
 
     def sample(self, batch_size=1, continous=False):

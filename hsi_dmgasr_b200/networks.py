@@ -33,6 +33,9 @@ def init_weights(net: nn.Module, init_type: str = "kaiming", scale: float = 1, s
             raise NotImplementedError("initialization method [{:s}] not implemented".format(init_type))
         if m.bias is not None:
             m.bias.data.zero_()
+    for m in net.modules():        # the edits above go through .data: make the native weight copies stale explicitly
+        if hasattr(m, "invalidate_native"):
+            m.invalidate_native()
 
 
 def define_G(opt):

@@ -12,6 +12,7 @@ from typing import List, Optional, Tuple
 
 import torch
 
+from . import _lib
 from .diffusion import GaussianDiffusion
 from .gae import GAE
 
@@ -35,13 +36,16 @@ class SRPipeline:
 
     @torch.no_grad()
     def super_resolve(self, sr: torch.Tensor, *, x_T: Optional[torch.Tensor] = None,
-                      noise_tape: Optional[torch.Tensor] = None, seed: Optional[int] = None,
+                      noise_tape: Optional[torch.Tensor] = None, seed: Optional[int] = None, first_cube: int = 0,
                       clamp: bool = True, return_latents: bool = False):
         """sr: bicubic-upsampled cubes [B,C,H,W] on the GPU -> SR cubes [B,C,H,W] (clamped to [0,1] like sr_gae.py:474-475).
 
-        x_T [B*G,3,H,W] / noise_tape [B*G,T-1,3,H,W] inject the random draws in (cube, group)-major order."""
+        x_T [B*G,3,H,W] / noise_tape [B*G,T-1,3,H,W] inject the random draws in (cube, group)-major order.
+        With an explicit `seed` the draws are keyed by (seed, first_cube + position of the cube): a cube's result does not
+        depend on which batch or rank it is processed in."""
         z = self.gae.encode_batched(sr)
         n = z.shape[0]
+        g = n // sr.shape[0]
         step = self.max_latents or n
         outs = []
         for lo in range(0, n, step):
@@ -49,9 +53,10 @@ class SRPipeline:
             outs.append(self.diffusion.super_resolution(
                 z[lo:hi], False, return_all=True, x_T=None if x_T is None else x_T[lo:hi],
                 noise_tape=None if noise_tape is None else noise_tape[lo:hi],
-                seed=None if seed is None else seed + lo))
+                seed=seed, first_image=first_cube * g + lo))
         lat = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
         y = self.gae.decode_batched(lat, clamp01=clamp)
+        _lib.check_health(y.device)        # results are about to leave the library: a barrier timeout must not pass silently
         return (y, lat) if return_latents else y
 
     @torch.no_grad()
@@ -99,30 +104,51 @@ def validate(pipeline: SRPipeline, loader, device: torch.device, **kw) -> dict:
 
 
 def run_sharded(pipeline: SRPipeline, cubes_host: torch.Tensor, device: torch.device, rank: int, world: int,
-                batch: int, gather: bool = False, **kw) -> Optional[torch.Tensor]:
+                batch: int, gather: bool = False, keep_on_device: bool = False, **kw) -> Optional[torch.Tensor]:
     """Each rank super-resolves its contiguous slice of `cubes_host` in batches of `batch` cubes.
 
-    No data-path collective. With gather=True the per-rank results are collected on rank 0 through
-    torch.distributed (NCCL on GPUs, gloo on CPU tests) once at the end; other ranks return None."""
+    No data-path collective.  With gather=True the per-rank results are collected on rank 0 once at the end with one
+    torch.distributed gather of equally padded tensors (NCCL on device tensors, gloo on the CPU tests); other ranks
+    return None.  keep_on_device=True leaves the results on the GPU (pipeline.super_resolve on pinned H2D copies) so that
+    the gather and the blend never touch host memory.  An explicit `seed` in **kw keys the noise by global cube index."""
     lo, hi = shard_bounds(cubes_host.shape[0], rank, world)
     parts: List[torch.Tensor] = []
     for b0 in range(lo, hi, batch):
-        parts.append(pipeline.super_resolve_host(cubes_host[b0:min(hi, b0 + batch)], device, **kw))
-    mine = torch.cat(parts, dim=0) if parts else cubes_host.new_zeros((0,) + tuple(cubes_host.shape[1:]))
+        chunk = cubes_host[b0:min(hi, b0 + batch)]
+        extra = dict(kw, first_cube=b0) if kw.get("seed") is not None else kw
+        if keep_on_device:
+            src = chunk if chunk.is_pinned() else chunk.pin_memory()
+            parts.append(pipeline.super_resolve(src.to(device, non_blocking=True), **extra))
+        else:
+            parts.append(pipeline.super_resolve_host(chunk, device, **extra))
+    if parts:
+        mine = torch.cat(parts, dim=0) if len(parts) > 1 else parts[0]
+    else:
+        mine = torch.zeros((0,) + tuple(cubes_host.shape[1:]), dtype=cubes_host.dtype, device=device if keep_on_device else "cpu")
     if not gather or world == 1:
         return mine
     import torch.distributed as dist
-    gathered = gather_variable(mine, rank, world, dist)
-    return gathered
+    return gather_rows(mine, cubes_host.shape[0], rank, world, dist)
 
 
-def gather_variable(mine: torch.Tensor, rank: int, world: int, dist) -> Optional[torch.Tensor]:
-    """Gather per-rank row blocks of differing length on rank 0 (host tensors; backend-agnostic)."""
-    objs = [None] * world if rank == 0 else None
-    dist.gather_object(mine.cpu(), objs, dst=0)
+def gather_rows(mine: torch.Tensor, n_total: int, rank: int, world: int, dist) -> Optional[torch.Tensor]:
+    """Row blocks of the contiguous shards (shard_bounds) -> the full [n_total, ...] tensor on rank 0, through ONE
+    dist.gather of tensors padded to the largest shard (device tensors travel over NCCL/NVLink, no pickling)."""
+    most = max(shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0] for r in range(world))
+    send = mine
+    if mine.shape[0] < most:
+        send = torch.zeros((most,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+        send[:mine.shape[0]] = mine
+    send = send.contiguous()
+    bufs = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, bufs, dst=0)
     if rank != 0:
         return None
-    return torch.cat(objs, dim=0)
+    rows = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, r, world)
+        rows.append(bufs[r][:hi - lo])
+    return torch.cat(rows, dim=0)
 
 
 # ---- overlapping-tile scene driver (BASELINE config 3; SURVEY.md 8f N1) ------------------------------------------------
@@ -158,23 +184,33 @@ def feather_window(tile: int, overlap: int, device=None) -> torch.Tensor:
 
 
 def blend_tiles(tiles: torch.Tensor, pos: List[Tuple[int, int]], height: int, width: int, overlap: int = 16) -> torch.Tensor:
-    """Weighted overlap-add of [T,C,t,t] tiles back into a [C,H,W] scene (weights normalised per pixel)."""
+    """Weighted overlap-add of [T,C,t,t] CUDA tiles (row-major grid `pos` from tile_scene) back into a [C,H,W] scene on the
+    device (hsidm_blend_tiles: gather form, weights of `feather_window`, normalised per pixel, deterministic).  There is no
+    host implementation in the package; tests/ keep a torch restatement as the checker."""
+    tiles = _lib.require_cuda_f32(tiles, "tiles")
+    ys = sorted({y for y, _ in pos})
+    xs = sorted({x for _, x in pos})
+    if [(y, x) for y in ys for x in xs] != list(pos) or tiles.shape[0] != len(pos):
+        raise _lib.HsidmError(-1, "blend_tiles expects the row-major tile grid produced by tile_scene")
     t = tiles.shape[-1]
-    win = feather_window(t, overlap, tiles.device)
-    acc = torch.zeros((tiles.shape[1], height, width), device=tiles.device, dtype=torch.float32)
-    wsum = torch.zeros((height, width), device=tiles.device, dtype=torch.float32)
-    for k, (y, x) in enumerate(pos):
-        acc[:, y:y + t, x:x + t] += tiles[k].float() * win
-        wsum[y:y + t, x:x + t] += win
-    return acc / wsum
+    ys_d = torch.tensor(ys, dtype=torch.int32, device=tiles.device)
+    xs_d = torch.tensor(xs, dtype=torch.int32, device=tiles.device)
+    out = torch.empty((tiles.shape[1], height, width), dtype=torch.float32, device=tiles.device)
+    _lib.check(_lib.load().hsidm_blend_tiles(tiles.data_ptr(), ys_d.data_ptr(), len(ys), xs_d.data_ptr(), len(xs), tiles.shape[1],
+                                             t, overlap, height, width, out.data_ptr(), _lib.stream_ptr(tiles.device)))
+    return out
 
 
 def super_resolve_scene(pipeline: SRPipeline, sr_scene: torch.Tensor, device: torch.device, tile: int = 128, overlap: int = 16,
-                        batch: int = 8, rank: int = 0, world: int = 1, **kw) -> Optional[torch.Tensor]:
-    """Full-scene SR: tile the bicubic-upsampled scene [C,H,W] (host), shard the tiles over `world` ranks, super-resolve
-    them in batches, gather on rank 0 and blend.  Returns the [C,H,W] result on rank 0 (None elsewhere)."""
+                        batch: int = 8, rank: int = 0, world: int = 1, blend_fn=None, keep_on_device: bool = True,
+                        **kw) -> Optional[torch.Tensor]:
+    """Full-scene SR (BASELINE configs[2]): tile the bicubic-upsampled scene [C,H,W] (host), shard the tiles over `world`
+    ranks (contiguous slices, no per-step collective), super-resolve them in batches, gather the tiles on rank 0 (one
+    NCCL gather of device tensors) and blend them there on the GPU.  Returns the [C,H,W] device tensor on rank 0 (None
+    elsewhere).  Pass an explicit seed=... for results that do not depend on `world` or `batch`."""
     tiles, pos = tile_scene(sr_scene, tile, overlap)
-    mine = run_sharded(pipeline, tiles.contiguous(), device, rank, world, batch, gather=world > 1, **kw)
+    mine = run_sharded(pipeline, tiles.contiguous(), device, rank, world, batch, gather=world > 1,
+                       keep_on_device=keep_on_device, **kw)
     if rank != 0:
         return None
-    return blend_tiles(mine, pos, sr_scene.shape[1], sr_scene.shape[2], overlap)
+    return (blend_fn or blend_tiles)(mine, pos, sr_scene.shape[1], sr_scene.shape[2], overlap)

@@ -90,6 +90,11 @@ HSIDM_API int hsidm_version(void);
 HSIDM_API const char* hsidm_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (all contexts); used by bench.py. */
 HSIDM_API int64_t hsidm_launch_count(void);
+/* The tensor-core kernels bound every pipeline-barrier wait: a protocol or descriptor fault raises a device flag instead of
+ * hanging the GPU, and the launch then leaves incomplete output.  hsidm_check_health() synchronises the current device,
+ * reads and clears that flag and returns HSIDM_CUDA_ERROR if it was raised by any launch since the previous check
+ * (HSIDM_OK otherwise).  The Python mirror calls it before results leave the library (SRPipeline, DDPM.test). */
+HSIDM_API int hsidm_check_health(void);
 /* Opt-in per-kernel-class timing used by bench.py's roofline leg: while enabled, every launch outside graph capture
  * is bracketed by CUDA events on its own stream. kind: 0 tensor-core conv, 1 CUDA-core conv, 2 GroupNorm stats,
  * 3 GroupNorm apply, 4 attention GEMM, 5 posterior step. read() synchronises and returns the summed event time (ms),
@@ -113,6 +118,12 @@ HSIDM_API const char* hsidm_unet_param_name(const hsidm_ctx* ctx, int index);
 /* nn.Module.load_state_dict for one tensor (model/model.py:177-202 loads "<prefix>_gen.pth").
  * `data` is fp32, host or device (copied); shape must match the reference parameter's shape. */
 HSIDM_API int hsidm_unet_set_param(hsidm_ctx* ctx, const char* key, const float* data, const int64_t* shape, int ndim);
+/* Whether the caller's current parameter tensors still equal the copies uploaded by set_param (bitwise).  In-place edits
+ * through `.data` (networks.py:13-74 init_weights, model.py finetune_norm, EMA swaps) do not bump a tensor's autograd
+ * version, so the Python mirror asks the device: `table_dev` is a DEVICE array of hsidm_unet_param_count() device
+ * pointers in parameter order.  *changed (host) = 1 if any element differs or nothing was uploaded yet.  Synchronises
+ * `stream`. */
+HSIDM_API int hsidm_unet_params_changed(hsidm_ctx* ctx, const void* const* table_dev, int n, int* changed, hsidm_stream stream);
 /* Pack weights into kernel layouts (bf16 K-major for tcgen05, fp32 [K][Cout] for the fp32 path). Must be
  * called after the last set_param and before forward/sample; fails if a parameter was never set. */
 HSIDM_API int hsidm_unet_commit(hsidm_ctx* ctx);
@@ -145,6 +156,17 @@ HSIDM_API int hsidm_posterior_step(hsidm_ctx* ctx, int t, const float* x_t, cons
 HSIDM_API int hsidm_sample(hsidm_ctx* ctx, const float* cond, const float* x_T, const float* noise_tape,
                  int64_t tape_image_stride, int64_t tape_step_stride, uint64_t seed, float* out, float* snapshots,
                  int N, int H, int W, hsidm_stream stream);
+/* Same, for a batch that is the slice [first_image, first_image + N) of a longer list of latent images sampled in several
+ * calls or on several GPUs: the built-in generator's counters are offset so that image k of the list sees the same
+ * per-step noise whatever batch or rank it lands in (tile-sharded scenes, SURVEY 8e/8f N1, give bit-identical results on
+ * 1 and N GPUs).  first_image is ignored when a noise tape is injected. */
+HSIDM_API int hsidm_sample_at(hsidm_ctx* ctx, const float* cond, const float* x_T, const float* noise_tape,
+                    int64_t tape_image_stride, int64_t tape_step_stride, uint64_t seed, int64_t first_image, float* out,
+                    float* snapshots, int N, int H, int W, hsidm_stream stream);
+/* n standard-normal draws (n and first_element multiples of 4) from the same counter-based generator, stream `seed`,
+ * starting at element first_element of that stream: the x_T draw of torch.randn(shape) (diffusion.py:192) made
+ * independent of batch composition.  out is a device pointer. */
+HSIDM_API int hsidm_randn(float* out, int64_t n, uint64_t seed, int64_t first_element, hsidm_stream stream);
 HSIDM_API int hsidm_snapshot_count(const hsidm_ctx* ctx);
 HSIDM_API int hsidm_num_timesteps(const hsidm_ctx* ctx);
 /* Workspace bytes currently held by the context (arena + packed weights + tables). */
@@ -159,6 +181,8 @@ HSIDM_API int hsidm_gae_param_count(const hsidm_gae* gae);
 HSIDM_API const char* hsidm_gae_param_name(const hsidm_gae* gae, int index);
 HSIDM_API int hsidm_gae_set_param(hsidm_gae* gae, const char* key, const float* data, const int64_t* shape, int ndim);
 HSIDM_API int hsidm_gae_commit(hsidm_gae* gae);
+/* Same contract as hsidm_unet_params_changed, over hsidm_gae_param_count() pointers. */
+HSIDM_API int hsidm_gae_params_changed(hsidm_gae* gae, const void* const* table_dev, int n, int* changed, hsidm_stream stream);
 /* Group count and band ranges computed by AE.py:264-280. start/end receive G entries each (may be NULL). */
 HSIDM_API int hsidm_gae_groups(const hsidm_gae* gae, int32_t* start, int32_t* end);
 
@@ -182,6 +206,13 @@ HSIDM_API int hsidm_bicubic_upsample(const float* lr, float* sr, int N, int C, i
  * truth / pred: [N,C,H,W] fp32 device pointers; out: [N][2] fp32 device pointer.  Deterministic (fixed-order folds in
  * float64); allocates its scratch with cudaMallocAsync on `stream`. */
 HSIDM_API int hsidm_quality_metrics(const float* truth, const float* pred, int N, int C, int H, int W, float* out, hsidm_stream stream);
+
+/* Overlapping-tile scene driver (the reference only crops non-overlapping 128x128 blocks offline,
+ * GAE/crop.py:12-36, HStest.py:33-45): feathered overlap-add of super-resolved tiles back into the scene on the device.
+ * tiles [ny*nx, C, tile, tile] fp32 in row-major tile order, tile (iy, ix) at origin (ys[iy], xs[ix]); ys / xs are DEVICE
+ * int32 arrays; weights ramp linearly over `overlap` pixels at every tile border; out [C, H, W].  Deterministic. */
+HSIDM_API int hsidm_blend_tiles(const float* tiles, const int32_t* ys, int ny, const int32_t* xs, int nx, int C, int tile,
+                      int overlap, int H, int W, float* out, hsidm_stream stream);
 
 #ifdef __cplusplus
 }

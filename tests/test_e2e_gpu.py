@@ -62,6 +62,34 @@ def test_cube_and_metric_gates(golden, tag, precision):
             assert d_sam <= 0.01
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag,cfg", [("small", SMALL), ("full", FULL)])
+def test_headline_schedule_T2000_metric_gates(golden, tag, cfg, precision):
+    """The same gates at the schedule length the bench is quoted on: T = 2000 cosine steps with an injected noise tape,
+    against the unmodified reference's sequential val loop (oracle/make_golden_r2.py section `long`).  No autocast escape
+    hatch: |dMPSNR| <= 0.05 dB and |dSAM| <= 0.01 deg in both precisions."""
+    g = golden(f"e2e_T2000_{tag}.npz")
+    T, hw = int(g["T"]), int(g["hw"])
+    assert T == 2000
+    pipe, geom = build(precision, T, cfg)
+    sr = synth.sr_cube(1, 31, hw, seed=53).cuda()
+    hr = synth.sr_cube(1, 31, hw, seed=54)
+    draws = [synth.noise_tape(1, T, 3, hw, hw, seed=5500 + k) for k in range(geom.G)]      # per group, like the generator
+    x_T = torch.cat([d[0] for d in draws]).cuda()
+    tape = torch.cat([d[1] for d in draws]).cuda()
+    cube, lat = pipe.super_resolve(sr, x_T=x_T, noise_tape=tape, return_latents=True)
+    true = hr[0].permute(1, 2, 0).numpy()
+    pred = cube[0].permute(1, 2, 0).cpu().numpy()
+    d_psnr = abs(mpsnr(true, pred) - float(g["mpsnr"]))
+    d_sam = abs(sam_degrees(true, pred) - float(g["sam"]))
+    ctx = ""
+    if "autocast_dsam" in g.files:
+        ctx = f" (reference under torch bf16 autocast: {float(g['autocast_dpsnr']):.5f} dB, {float(g['autocast_dsam']):.5f} deg)"
+    print(f"T=2000 {tag} {precision}: cube rel-L2 {rel_l2(cube, torch.from_numpy(g['cube'])):.3e} latents "
+          f"{rel_l2(lat, torch.from_numpy(g['latents'])):.3e} dMPSNR {d_psnr:.5f} dB dSAM {d_sam:.5f} deg{ctx}")
+    assert d_psnr <= 0.05 and d_sam <= 0.01
+
+
 def test_host_buffer_call_and_batch_independence():
     pipe, geom = build("fp32", 5)
     sr = synth.sr_cube(3, 31, 16, seed=60)

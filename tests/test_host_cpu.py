@@ -118,6 +118,56 @@ def test_gae_state_file_round_trip(tmp_path):
     assert load_gae(bare).geometry() == geom
 
 
+def test_gae_unpickler_refuses_code_execution(tmp_path):
+    """The remapping unpickler resolves an exact allow-list only: a checkpoint whose __reduce__ names builtins.eval (or
+    anything else off the list) is refused before anything runs, and allow_pickle=False never leaves weights_only."""
+    import pickle
+    import torch
+    from hsi_dmgasr_b200 import load_gae
+
+    marker = tmp_path / "pwned"
+
+    class Evil:
+        def __reduce__(self):
+            return (eval, (f"open({str(marker)!r}, 'w').close()",))
+
+    bad = str(tmp_path / "evil.pth")
+    torch.save({"x": Evil()}, bad)
+    with pytest.raises(pickle.UnpicklingError):
+        load_gae(bad)
+    assert not marker.exists()
+
+    class Evil2:
+        def __reduce__(self):
+            import os as _os
+            return (_os.system, ("true",))
+
+    bad2 = str(tmp_path / "evil2.pth")
+    torch.save([Evil2()], bad2)
+    with pytest.raises(pickle.UnpicklingError):
+        load_gae(bad2)
+    with pytest.raises(pickle.UnpicklingError):
+        load_gae(bad2, allow_pickle=False)
+
+
+def test_whole_module_pickle_round_trip_without_reference(tmp_path):
+    """A whole-module pickle shaped like GAE_pretrained/GAE_4_*.pth (classes named __main__.* / common.*, AE.py:637) built
+    from this package's own classes loads through the allow-listed unpickler - runs on boxes without /root/reference."""
+    import torch
+    from hsi_dmgasr_b200 import gae as G, load_gae, synth
+    geom = GAE_PRESETS["Cav"]
+    m = G.GAE(n_subs=geom.n_subs, n_ovls=geom.n_ovls, n_colors=geom.n_colors, n_feats=geom.n_feats)
+    m.load_state_dict(synth.gae_state_dict(geom, 9))
+    path = str(tmp_path / "GAE_4_fake.pth")
+    G.save_reference_style_pickle(m, path)
+    import zipfile
+    names = zipfile.ZipFile(path).read([n for n in zipfile.ZipFile(path).namelist() if n.endswith("data.pkl")][0])
+    assert b"__main__" in names and b"common" in names and b"hsi_dmgasr_b200" not in names
+    back = load_gae(path)
+    assert isinstance(back, G.GAE) and back.geometry() == geom
+    assert all(torch.equal(a, b) for a, b in zip(back.state_dict().values(), m.state_dict().values()))
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
 def test_reference_gae_pickles_load_through_the_shim():
     from hsi_dmgasr_b200 import load_gae

@@ -7,8 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from hsi_dmgasr_b200.pipeline import (blend_tiles, feather_window, run_sharded, shard_bounds, super_resolve_scene, tile_scene,
-                                      tile_starts)
+from hsi_dmgasr_b200.pipeline import feather_window, run_sharded, shard_bounds, super_resolve_scene, tile_scene, tile_starts
+from tests.host_ref import blend_tiles_ref as blend_tiles     # the package blends on the GPU only; this is the checker
 
 
 class FakePipeline:
@@ -42,9 +42,16 @@ def test_tile_then_blend_is_identity():
 
 def test_scene_driver_single_rank():
     scene = torch.rand(4, 200, 150)
-    out = super_resolve_scene(FakePipeline(), scene, torch.device("cpu"), batch=3)
+    out = super_resolve_scene(FakePipeline(), scene, torch.device("cpu"), batch=3, blend_fn=blend_tiles, keep_on_device=False)
     want = scene * 2 + torch.arange(4.0).view(-1, 1, 1)
     assert torch.allclose(out, want, atol=1e-5)
+
+
+def test_package_blend_has_no_host_path():
+    from hsi_dmgasr_b200 import _lib, pipeline
+    tiles, pos = tile_scene(torch.rand(2, 140, 140), 128, 16)
+    with pytest.raises(_lib.HsidmError):
+        pipeline.blend_tiles(tiles, pos, 140, 140, 16)
 
 
 def _free_port():
@@ -62,7 +69,8 @@ def _worker(rank, world, port, ret):
         lo, hi = shard_bounds(7, rank, world)
         got = run_sharded(FakePipeline(), cubes, torch.device("cpu"), rank, world, batch=2, gather=True)
         scene = torch.rand(2, 240, 250)
-        blended = super_resolve_scene(FakePipeline(), scene, torch.device("cpu"), batch=2, rank=rank, world=world)
+        blended = super_resolve_scene(FakePipeline(), scene, torch.device("cpu"), batch=2, rank=rank, world=world,
+                                      blend_fn=blend_tiles, keep_on_device=False)
         if rank == 0:
             want = cubes * 2 + torch.arange(3.0).view(1, -1, 1, 1)
             ret["cubes_ok"] = bool(torch.allclose(got, want))

@@ -69,6 +69,35 @@ def test_weights_follow_parameter_updates():
         net.final_conv["block"]["3"].bias.add_(1.0)
     b = net(x, lv)
     assert torch.allclose(b - a, torch.ones_like(a), atol=1e-5)
+    # edits through .data bump no version counter (networks.py init_weights, finetune_norm, EMA swaps): the library
+    # compares its copies with the live tensors on the device
+    v0 = net.final_conv["block"]["3"].bias._version
+    net.final_conv["block"]["3"].bias.data.add_(2.0)
+    assert net.final_conv["block"]["3"].bias._version == v0
+    c = net(x, lv)
+    assert torch.allclose(c - b, 2 * torch.ones_like(a), atol=1e-5)
+    net.downs["0"].weight.data.mul_(0.0)
+    d = net(x, lv)
+    assert not torch.allclose(d, c)
+    # explicit invalidation with tracking off
+    net.track_data_edits = False
+    net.final_conv["block"]["3"].bias.data.sub_(3.0)
+    assert torch.equal(net(x, lv), d)                      # stale by request
+    assert torch.allclose(net.invalidate_native()(x, lv) - d, -3 * torch.ones_like(a), atol=1e-5)
+
+
+def test_gae_weights_follow_data_edits():
+    from hsi_dmgasr_b200 import GAE, synth
+    from tests.cfgs import GAE_CASES
+    geom, seed, hw = GAE_CASES["Cav"]
+    gae = GAE(n_subs=geom.n_subs, n_ovls=geom.n_ovls, n_colors=geom.n_colors, n_feats=geom.n_feats)
+    gae.load_state_dict(synth.gae_state_dict(geom, seed))
+    gae = gae.cuda().eval()
+    x = synth.sr_cube(1, geom.n_colors, hw, seed=3).cuda()
+    z0 = gae.encode_batched(x)
+    gae.Encoder.final.bias.data.add_(1.0)
+    z1 = gae.encode_batched(x)
+    assert torch.allclose(z1 - z0, torch.ones_like(z0), atol=1e-5)
 
 
 @pytest.mark.parametrize("tag,hw,n", [("full32", 128, 2), ("full32", 64, 3), ("full32", 128, 12)])
