@@ -130,7 +130,7 @@ def unet_topology(inner_channel: int, channel_mults: Sequence[int], attn_res: Se
 def noise_embedding(sd: SD, level: torch.Tensor, dim: int) -> torch.Tensor:
     """PositionalEncoding + 2-layer MLP (unet.py:18-31, 182-187). level: [N,1] -> [N,1,dim]."""
     half = dim // 2
-    step = torch.arange(half, dtype=level.dtype) / half
+    step = torch.arange(half, dtype=level.dtype, device=level.device) / half
     enc = level.unsqueeze(1) * torch.exp(-math.log(1e4) * step.unsqueeze(0))
     enc = torch.cat([torch.sin(enc), torch.cos(enc)], dim=-1)
     h = F.linear(enc, sd["noise_level_mlp.1.weight"], sd["noise_level_mlp.1.bias"])

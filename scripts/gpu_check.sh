@@ -13,3 +13,5 @@ run unet_bf16 tests/test_unet_gpu.py -k "bf16" -s
 run sampler tests/test_sampler_gpu.py -s
 run gae tests/test_gae_gpu.py -s
 run e2e tests/test_e2e_gpu.py -s
+run dropin tests/test_dropin_gpu.py -s
+run scene tests/test_scene_gpu.py tests/test_prepost_gpu.py -s
