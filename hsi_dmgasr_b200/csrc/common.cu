@@ -1,12 +1,15 @@
 // Error state, launch counter and the stream-ordered workspace arena.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 namespace hsidm {
 
 thread_local std::string g_last_error;
 int64_t g_launches = 0;
+bool g_pdl_on = std::getenv("HSIDM_NO_PDL") == nullptr;
+bool g_pdl_pass = true;
 
 void set_last_error(const char* fmt, ...) {
   char buf[1024];

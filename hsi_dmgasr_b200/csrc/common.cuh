@@ -88,6 +88,42 @@ struct ProfScope {
   }
 };
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// Every kernel of the denoise step is launched with programmatic stream serialization: its CTAs may be scheduled while the
+// previous kernel of the stream is still draining (as SMs free up), run their prologue (barrier init, tensor-memory
+// allocation, descriptor prefetch, weight-tile prefetch: nothing that depends on the predecessor) and then block in
+// griddep_wait() until the predecessor grid has completed and its writes are visible.  Rule for kernels launched through
+// launch_pdl(): every thread executes griddep_wait() before its first access to global memory that is not constant for
+// the lifetime of the launch (activations, statistics, per-step tables); packed weights may be read before it.
+extern bool g_pdl_on;   // HSIDM_NO_PDL=1 switches the attribute off (A/B runs); the device-side calls are then no-ops
+// Set per pass by the executors: PDL pays when kernels are short (small batches: -5 % per step at 1-11 latents) and
+// measured neutral to slightly negative at 176 latents, where each kernel runs for tens of microseconds.
+extern bool g_pdl_pass;
+#if defined(__CUDACC__)
+static __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+static __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_pdl_on && g_pdl_pass) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr, cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 inline int after_launch(const char* what) {
   ++g_launches;
   cudaError_t e = cudaPeekAtLastError();

@@ -162,6 +162,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0) {
     // =============================== TMA producer: halo tiles (A) ===============================
     if (lane == 0) {
+      griddep_wait();     // activations come from the previous kernel(s) of the stream
+      griddep_launch();   // ... and from here on the next kernel's CTAs may take the SMs this grid frees
       int as = 0;
       uint32_t aph = 0;
       bool ok = true;
@@ -360,6 +362,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // at physical chunk j ^ (row & 7) (128B swizzle).  Same arithmetic as gn_apply (norm.cu), so fused and unfused
     // paths agree bit for bit.
     if (PAIR || p.gn_ab) {   // a pair always routes halo readiness through these warps (the leader hears both CTAs)
+      griddep_wait();          // gn_ab is the previous kernel's output
       const int tid = threadIdx.x - 32 * kFirstXformWarp;
       // a_ready of the CTA whose issuer consumes the stage: this CTA's own, or the pair leader's
       auto ready_arrive = [&](int stage) {
@@ -438,6 +441,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else {
     // =============================== epilogue (warps 3..10) ===============================
+    griddep_wait();   // residual / noise-bias reads and the output writes must follow the previous kernels of the stream
     const int quarter = warp & 3;
     const int half = (warp - kFirstEpiWarp) >> 2;      // which of the two warps of this lane quarter
     const int row = quarter * 32 + lane;   // accumulator row: pixel (row/8, row%8) of a sub-tile
@@ -637,16 +641,12 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   if constexpr (PAIR) {
     // one cluster of two CTAs per pair of adjacent pixel tiles; an even grid of at most one CTA per SM
     const int pairs = std::min((p.m_tiles / 2) * p.n_tiles, host().num_sms / 2);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = C::kSmemBytes, cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    HSIDM_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<MT, BN, NT, true>, tmA0, tmA1, tmR0, tmR1, tmB, tmO, p));
+    HSIDM_CUDA(launch_pdl(conv_halo_kernel<MT, BN, NT, true>, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, 2, tmA0, tmA1,
+                          tmR0, tmR1, tmB, tmO, p));
   } else {
     const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
-    conv_halo_kernel<MT, BN, NT, false><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA0, tmA1, tmR0, tmR1, tmB, tmO, p);
+    HSIDM_CUDA(launch_pdl(conv_halo_kernel<MT, BN, NT, false>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, 1, tmA0, tmA1, tmR0,
+                          tmR1, tmB, tmO, p));
   }
   return after_launch("conv_halo_kernel");
 }

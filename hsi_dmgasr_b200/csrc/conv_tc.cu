@@ -98,6 +98,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
+      griddep_wait();     // activations come from the previous kernel(s) of the stream
+      griddep_launch();
       int stage = 0, grp = 0, gcnt = 0;
       uint32_t phase = 0;
       bool ok = true;
@@ -174,6 +176,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else {
     // =============================== epilogue (warps 2..5) ===============================
+    griddep_wait();
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;        // which of the two warps of this quarter
     const int row = quarter * 32 + lane;     // accumulator row = pixel within the tile
@@ -509,10 +512,10 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
            op.Win, op.N);
   ProfScope prof(PROF_CONV_TC, 2.0 * p.M * (double)op.Cout * K, stream, tag);
   switch (BN) {
-    case 16: conv_tc_kernel<16><<<grid, kThreads, Cfg<16>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, tmO, p); break;
-    case 64: conv_tc_kernel<64><<<grid, kThreads, Cfg<64>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, tmO, p); break;
-    case 128: conv_tc_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, tmO, p); break;
-    default: conv_tc_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, stream>>>(tmA0, tmA1, tmB, tmO, p); break;
+    case 16: HSIDM_CUDA(launch_pdl(conv_tc_kernel<16>, dim3(grid), dim3(kThreads), Cfg<16>::kSmemBytes, stream, 1, tmA0, tmA1, tmB, tmO, p)); break;
+    case 64: HSIDM_CUDA(launch_pdl(conv_tc_kernel<64>, dim3(grid), dim3(kThreads), Cfg<64>::kSmemBytes, stream, 1, tmA0, tmA1, tmB, tmO, p)); break;
+    case 128: HSIDM_CUDA(launch_pdl(conv_tc_kernel<128>, dim3(grid), dim3(kThreads), Cfg<128>::kSmemBytes, stream, 1, tmA0, tmA1, tmB, tmO, p)); break;
+    default: HSIDM_CUDA(launch_pdl(conv_tc_kernel<256>, dim3(grid), dim3(kThreads), Cfg<256>::kSmemBytes, stream, 1, tmA0, tmA1, tmB, tmO, p)); break;
   }
   return after_launch("conv_tc_kernel");
 }

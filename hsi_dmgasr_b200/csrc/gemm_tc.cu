@@ -83,6 +83,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
+      griddep_wait();     // both operands are activations of earlier kernels
+      griddep_launch();
       int stage = 0, grp = 0, gcnt = 0;
       uint32_t phase = 0;
       bool ok = true;
@@ -136,6 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
+    griddep_wait();
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     int acc = 0;
@@ -268,7 +271,7 @@ int launch(const GemmTcOp& op, cudaStream_t stream) {
   char tag[96];
   snprintf(tag, sizeof(tag), "gemm_tc BN%d m%d n%d k%d b%d%s", BN, op.M, op.N, op.K, op.batch, op.row_softmax ? " +softmax" : "");
   ProfScope prof(PROF_GEMM, 2.0 * op.M * (double)op.N * op.K * op.batch, stream, tag);
-  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
+  HSIDM_CUDA(launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, 1, tmA, tmB, p));
   return after_launch("gemm_tc_kernel");
 }
 

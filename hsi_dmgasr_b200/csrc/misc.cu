@@ -40,6 +40,8 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t step, u
 // One fused pass: read x_t, eps, (noise) ; write x_{t-1} (and a snapshot).  16 B/element fp32 traffic with a tape,
 // 12 B/element with the in-kernel generator.  4 elements per thread, 128-bit accesses.
 __global__ void posterior_kernel(PosteriorArgs a) {
+  griddep_wait();
+  griddep_launch();
   const int t = a.t >= 0 ? a.t : *a.t_dev;
   const float k_recip = a.coef[t * 5 + 0], k_recipm1 = a.coef[t * 5 + 1];
   const float k_c1 = a.coef[t * 5 + 2], k_c2 = a.coef[t * 5 + 3], k_sigma = a.coef[t * 5 + 4];
@@ -80,6 +82,7 @@ __global__ void posterior_kernel(PosteriorArgs a) {
 }
 
 __global__ void dec_kernel(int* t) {
+  griddep_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) *t -= 1;
 }
 __global__ void state_set_kernel(int* state, int t, unsigned long long seed, unsigned long long offset4) {
@@ -157,6 +160,8 @@ __global__ void upsample2x_kernel(const AT* __restrict__ x, AT* __restrict__ out
 // out[n, oy, ox, tap*C + c] = x[n, 2*oy+ky-1, 2*ox+kx-1, c] (zero outside)
 __global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, int W, int CV,
                                  int64_t total) {
+  griddep_wait();
+  griddep_launch();
   const int Ho = H / 2, Wo = W / 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cv = (int)(i % CV);
@@ -181,6 +186,8 @@ template <int CT>
 __global__ void __launch_bounds__(128)
 im2col_small_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, bf16* __restrict__ out,
                     int H, int W, int64_t total) {
+  griddep_wait();
+  griddep_launch();
   const int64_t plane = (int64_t)H * W;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % W);
@@ -361,12 +368,12 @@ int posterior_step(const PosteriorArgs& a, cudaStream_t stream) {
   if (((uintptr_t)a.x_t | (uintptr_t)a.eps | (uintptr_t)a.x_prev | (uintptr_t)a.noise) & 15)
     HSIDM_FAIL(HSIDM_BAD_ARG, "posterior_step: pointers must be 16-byte aligned");
   ProfScope prof(PROF_POSTERIOR, (double)a.n * 4 * (a.noise ? 4 : 3), stream);
-  posterior_kernel<<<grid_for(a.n / 4, 256), 256, 0, stream>>>(a);
+  HSIDM_CUDA(launch_pdl(posterior_kernel, dim3(grid_for(a.n / 4, 256)), dim3(256), 0, stream, 1, a));
   return after_launch("posterior_kernel");
 }
 
 int step_counter_dec(int* t_dev, cudaStream_t stream) {
-  dec_kernel<<<1, 32, 0, stream>>>(t_dev);
+  HSIDM_CUDA(launch_pdl(dec_kernel, dim3(1), dim3(32), 0, stream, 1, t_dev));
   return after_launch("dec_kernel");
 }
 
@@ -410,13 +417,13 @@ int im2col_small(const float* x0, int C0, const float* x1, int C1, void* out, in
   bf16* o = static_cast<bf16*>(out);
   const int grid = grid_for(total, 128);
   switch (C0 + C1) {
-    case 1: im2col_small_kernel<1><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
-    case 2: im2col_small_kernel<2><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
-    case 3: im2col_small_kernel<3><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
-    case 4: im2col_small_kernel<4><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
-    case 5: im2col_small_kernel<5><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
-    case 6: im2col_small_kernel<6><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
-    default: im2col_small_kernel<7><<<grid, 128, 0, stream>>>(x0, C0, x1, C1, o, H, W, total); break;
+    case 1: HSIDM_CUDA(launch_pdl(im2col_small_kernel<1>, dim3(grid), dim3(128), 0, stream, 1, x0, C0, x1, C1, o, H, W, total)); break;
+    case 2: HSIDM_CUDA(launch_pdl(im2col_small_kernel<2>, dim3(grid), dim3(128), 0, stream, 1, x0, C0, x1, C1, o, H, W, total)); break;
+    case 3: HSIDM_CUDA(launch_pdl(im2col_small_kernel<3>, dim3(grid), dim3(128), 0, stream, 1, x0, C0, x1, C1, o, H, W, total)); break;
+    case 4: HSIDM_CUDA(launch_pdl(im2col_small_kernel<4>, dim3(grid), dim3(128), 0, stream, 1, x0, C0, x1, C1, o, H, W, total)); break;
+    case 5: HSIDM_CUDA(launch_pdl(im2col_small_kernel<5>, dim3(grid), dim3(128), 0, stream, 1, x0, C0, x1, C1, o, H, W, total)); break;
+    case 6: HSIDM_CUDA(launch_pdl(im2col_small_kernel<6>, dim3(grid), dim3(128), 0, stream, 1, x0, C0, x1, C1, o, H, W, total)); break;
+    default: HSIDM_CUDA(launch_pdl(im2col_small_kernel<7>, dim3(grid), dim3(128), 0, stream, 1, x0, C0, x1, C1, o, H, W, total)); break;
   }
   return after_launch("im2col_small_kernel");
 }
@@ -425,7 +432,7 @@ int im2col_s2(const void* x, void* out, int N, int H, int W, int C, cudaStream_t
   if (C % 8) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "im2col_s2: C=%d not a multiple of 8", C);
   const int64_t total = (int64_t)N * (H / 2) * (W / 2) * 9 * (C / 8);
   ProfScope prof(PROF_OTHER, (double)total * 16 * 1.45, stream, "im2col_s2");
-  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const bf16*)x, (bf16*)out, H, W, C / 8, total);
+  HSIDM_CUDA(launch_pdl(im2col_s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, 1, (const bf16*)x, (bf16*)out, H, W, C / 8, total));
   return after_launch("im2col_s2_kernel");
 }
 

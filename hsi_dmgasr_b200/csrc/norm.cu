@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(kMaxThreads, 4)
 gn_apply_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, int C1, int HW, int groups, int CV,
                 int lanes, int pix_per_block, const float* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int swish, AT* __restrict__ out) {
+  griddep_wait();
+  griddep_launch();
   const int C = C0 + C1;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
@@ -271,6 +273,8 @@ gn_finalize_kernel(const float* __restrict__ part0, int slots0, int C0, const fl
                    int groups, int lanes, double cnt, float eps, float* __restrict__ stats, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ ab) {
   extern __shared__ double dsm[];   // [lanes][C/2][4], then reused as double[2][C]
+  griddep_wait();
+  griddep_launch();
   const int C = C0 + C1, n = blockIdx.x, tid = threadIdx.x;
   const int pairs = C >> 1;
   const int pr = tid % pairs, lane = tid / pairs;
@@ -344,8 +348,8 @@ int gn_finalize(const float* part0, int slots0, int C0, const float* part1, int 
   const int threads = (int)round_up(lanes * pairs, 32);
   const size_t smem = std::max<size_t>(sizeof(double) * 4 * lanes * pairs, sizeof(double) * 2 * C);
   ProfScope prof(PROF_GN_STATS, 8.0 * N * ((double)slots0 * C0 + (double)slots1 * C1), stream, "finalize");
-  gn_finalize_kernel<<<N, threads, smem, stream>>>(part0, slots0, C0, part1, slots1, C1, groups, lanes,
-                                                   (double)(C / groups) * HW, eps, stats, gamma, beta, ab);
+  HSIDM_CUDA(launch_pdl(gn_finalize_kernel, dim3(N), dim3(threads), smem, stream, 1, part0, slots0, C0, part1, slots1, C1, groups, lanes,
+                        (double)(C / groups) * HW, eps, stats, gamma, beta, ab));
   return after_launch("gn_finalize_kernel");
 }
 
@@ -359,12 +363,11 @@ int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int 
   snprintf(tag, sizeof(tag), "apply c%d+%d hw%d n%d grid%dx%d", C0, C1, HW, N, g.slabs, N);
   ProfScope prof(PROF_GN_APPLY, 2.0 * N * HW * (C0 + C1) * (prec == HSIDM_BF16 ? 2 : 4), stream, tag);
   if (prec == HSIDM_BF16)
-    gn_apply_kernel<bf16><<<grid, g.threads, 0, stream>>>((const bf16*)x0, C0, (const bf16*)x1, C1, HW, groups, g.CV,
-                                                           g.lanes, g.pix_per_block, stats, gamma, beta, swish, (bf16*)out);
+    HSIDM_CUDA(launch_pdl(gn_apply_kernel<bf16>, grid, dim3(g.threads), 0, stream, 1, (const bf16*)x0, C0, (const bf16*)x1, C1, HW, groups,
+                          g.CV, g.lanes, g.pix_per_block, stats, gamma, beta, swish, (bf16*)out));
   else
-    gn_apply_kernel<float><<<grid, g.threads, 0, stream>>>((const float*)x0, C0, (const float*)x1, C1, HW, groups, g.CV,
-                                                            g.lanes, g.pix_per_block, stats, gamma, beta, swish,
-                                                            (float*)out);
+    HSIDM_CUDA(launch_pdl(gn_apply_kernel<float>, grid, dim3(g.threads), 0, stream, 1, (const float*)x0, C0, (const float*)x1, C1, HW,
+                          groups, g.CV, g.lanes, g.pix_per_block, stats, gamma, beta, swish, (float*)out));
   return after_launch("gn_apply_kernel");
 }
 

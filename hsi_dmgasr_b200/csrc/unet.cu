@@ -429,7 +429,9 @@ void res_block(hsidm_ctx* c, const ResW& r, const Act& x, const Act* skip, const
   bool fused = false;
   ConvW wf;
   static const int fuse_id_max = std::getenv("HSIDM_FUSE_ID_MAX") ? atoi(std::getenv("HSIDM_FUSE_ID_MAX")) : 0;
-  if (ex.prec == HSIDM_BF16 && r.fused.w && (r.has_res || r.cout <= fuse_id_max)) {
+  // A/B switch: res_conv of the blocks with at most this many output channels as its own 1x1 launch instead of extra K columns
+  static const int no_rsfuse_max = std::getenv("HSIDM_NO_RSFUSE_MAX") ? atoi(std::getenv("HSIDM_NO_RSFUSE_MAX")) : 0;
+  if (ex.prec == HSIDM_BF16 && r.fused.w && (r.has_res || r.cout <= fuse_id_max) && !(r.has_res && r.cout <= no_rsfuse_max)) {
     ConvOp probe = conv_op_nhwc(h, nullptr, y);
     probe.rsrc[0].p = x.p, probe.rsrc[0].C = x.C;
     if (skip) probe.rsrc[1].p = skip->p, probe.rsrc[1].C = skip->C;
@@ -498,6 +500,8 @@ void unet_forward_pass(hsidm_ctx* c, const float* x0, int c0, const float* x1, i
   Exec& ex = c->ex;
   const size_t es = ex.esize();
   std::vector<Act> feats;
+  static const int pdl_max_px = std::getenv("HSIDM_PDL_MAX_PIXELS") ? atoi(std::getenv("HSIDM_PDL_MAX_PIXELS")) : 48 * 128 * 128;
+  g_pdl_pass = (long long)N * H * W <= pdl_max_px;   // programmatic dependent launch only where kernels are short
   // ------------------------------------------------ down path ------------------------------------------------
   Act stage_in;   // full-N input of the current stage (empty for the first: raw NCHW halves)
   int Hc = H, Wc = W;
