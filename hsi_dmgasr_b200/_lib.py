@@ -64,6 +64,10 @@ SIGNATURES = {
     "hsidm_sample_at": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_uint64, C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "hsidm_randn": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_int64, _P]),
     "hsidm_blend_tiles": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "hsidm_train_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P, _P]),
+    "hsidm_train_backward": (C.c_int, [_P, C.c_float, _P]),
+    "hsidm_train_grad_numel": (C.c_int64, [_P]),
+    "hsidm_train_grad_offset": (C.c_int64, [_P, C.c_int]),
     "hsidm_snapshot_count": (C.c_int, [_P]),
     "hsidm_num_timesteps": (C.c_int, [_P]),
     "hsidm_ctx_bytes": (C.c_int64, [_P]),

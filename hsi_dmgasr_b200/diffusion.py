@@ -199,14 +199,84 @@ class GaussianDiffusion(nn.Module):
     def super_resolution(self, x_in, continous=False, **kw):
         return self.p_sample_loop(x_in, continous, **kw)
 
-    # ---- training side: SURVEY.md 8f row N2, not built yet ---------------------------------------------------------------
+    # ---- training side -------------------------------------------------------------------------------
     def q_sample(self, x_start, continuous_sqrt_alpha_cumprod, noise=None):
         noise = torch.randn_like(x_start) if noise is None else noise
         return continuous_sqrt_alpha_cumprod * x_start + (1 - continuous_sqrt_alpha_cumprod ** 2).sqrt() * noise
 
     def p_losses(self, x_in, noise=None):
-        raise NotImplementedError("p_losses (training forward+backward) is a 'next' row of the scope table (SURVEY.md 8f N2); "
-                                  "this package implements the inference hot path only")
+        """diffusion.py:222-250: one shared integer t from ``np.random.randint``, per-sample continuous noise levels from
+        ``np.random.uniform`` between the neighbouring schedule levels, q_sample, UNet on cat([SR, x_noisy]) and the summed
+        L1 / L2 loss.  The forward and the hand-written backward run in the native library (hsidm_train_forward /
+        hsidm_train_backward, fp32); the returned scalar carries an autograd node, so ``loss.backward()`` followed by a stock
+        ``torch.optim`` step works exactly as in ``DDPM.optimize_parameters`` (model.py:49-59)."""
+        if not self.conditional:
+            raise NotImplementedError("unconditional training is not used by HSI-DMGASR (every config sets conditional: true)")
+        x_start = _lib.require_cuda_f32(x_in["HR"], "x_in['HR']")
+        cond = _lib.require_cuda_f32(x_in["SR"], "x_in['SR']")
+        b = x_start.shape[0]
+        t = np.random.randint(1, self.num_timesteps + 1)
+        levels = np.random.uniform(self.sqrt_alphas_cumprod_prev[t - 1], self.sqrt_alphas_cumprod_prev[t], size=b)
+        levels = np.ascontiguousarray(np.asarray(levels, dtype=np.float32).reshape(-1))      # torch.FloatTensor(...) in the reference
+        noise = torch.randn_like(x_start) if noise is None else _lib.require_cuda_f32(noise, "noise")
+        if self.loss_type not in ("l1", "l2"):
+            raise NotImplementedError()
+        h = self._native(x_start.device)
+        named = dict(self.denoise_fn.named_parameters())
+        params = [named[k] for k in h.keys()]
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self.denoise_fn.cfg.dropout > 0 else 0
+        return _PLosses.apply(self, h, x_start, cond, noise, levels, seed, *params)
 
     def forward(self, x, *args, **kwargs):
         return self.p_losses(x, *args, **kwargs)
+
+
+class _PLosses(torch.autograd.Function):
+    """Autograd node around the native training step: forward = hsidm_train_forward (saves activations inside the library),
+    backward = hsidm_train_backward; the parameter gradients are views of ONE contiguous slab (``gd.last_grad_slab``), which is
+    what a data-parallel job all-reduces."""
+
+    @staticmethod
+    def forward(ctx, gd, h, hr, sr, noise, levels, seed, *params):
+        lib = _lib.load()
+        n, c, hh, ww = hr.shape
+        if tuple(sr.shape) != tuple(hr.shape) or tuple(noise.shape) != tuple(hr.shape):
+            raise _lib.HsidmError(-1, f"HR {tuple(hr.shape)}, SR {tuple(sr.shape)} and noise {tuple(noise.shape)} must agree")
+        slab = torch.empty(lib.hsidm_train_grad_numel(h.ptr), device=hr.device, dtype=torch.float32)
+        loss = torch.empty(1, device=hr.device, dtype=torch.float32)
+        _lib.check(lib.hsidm_train_forward(h.ptr, hr.data_ptr(), sr.data_ptr(), noise.data_ptr(), levels.ctypes.data, n, hh, ww,
+                                           0 if gd.loss_type == "l1" else 1, seed, slab.data_ptr(), loss.data_ptr(),
+                                           _lib.stream_ptr(hr.device)))
+        ctx.h, ctx.slab, ctx.count, ctx.device = h, slab, n * c * hh * ww, hr.device
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.offsets = [lib.hsidm_train_grad_offset(h.ptr, i) for i in range(len(params))]
+        gd.last_grad_slab = slab
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        upstream = float(grad_out) * ctx.count          # the library differentiates loss_sum / count
+        _lib.check(lib.hsidm_train_backward(ctx.h.ptr, upstream, _lib.stream_ptr(ctx.device)))
+        grads = []
+        for shape, off in zip(ctx.shapes, ctx.offsets):
+            numel = 1
+            for d in shape:
+                numel *= d
+            grads.append(ctx.slab[off:off + numel].view(shape))
+        return (None,) * 7 + tuple(grads)
+
+
+def allreduce_gradients(gd: "GaussianDiffusion", world: int, dist=None) -> None:
+    """Data-parallel gradient averaging for one process per GPU (BASELINE configs[4]; the reference wraps netG in
+    nn.DataParallel instead, networks.py:113-115): ONE all-reduce of the contiguous gradient slab of the last backward
+    (NCCL over NVLink on GPUs), then 1/world.  Every ``p.grad`` is a view of that slab."""
+    if world <= 1:
+        return
+    if dist is None:
+        import torch.distributed as dist
+    slab = getattr(gd, "last_grad_slab", None)
+    if slab is None:
+        raise _lib.HsidmError(-7, "no backward pass to all-reduce")
+    dist.all_reduce(slab)
+    slab.mul_(1.0 / world)

@@ -34,6 +34,19 @@ class DDPM:
         self.set_new_noise_schedule(opt["model"]["beta_schedule"]["train"], schedule_phase="train")
         if opt["phase"] == "train":
             self.netG.train()
+            # model.py:26-44: which parameters train, and the Adam optimiser over them
+            if opt["model"]["finetune_norm"]:
+                optim_params = []
+                for k, v in self.netG.named_parameters():
+                    v.requires_grad = False
+                    if k.find("transformer") >= 0:
+                        v.requires_grad = True
+                        v.data.zero_()
+                        optim_params.append(v)
+                        logger.info("Params [{:s}] initialized to 0 and will optimize.".format(k))
+            else:
+                optim_params = list(self.netG.parameters())
+            self.optG = torch.optim.Adam(optim_params, lr=opt["train"]["optimizer"]["lr"])
             self.log_dict = OrderedDict()
         self.load_network()
 
@@ -52,8 +65,19 @@ class DDPM:
     def feed_data(self, data):
         self.data = self.set_device(data)
 
-    def optimize_parameters(self):
-        raise NotImplementedError("training step is a 'next' row of the scope table (SURVEY.md 8f N2)")
+    def optimize_parameters(self, world: int = 1):
+        """model.py:49-59.  ``world`` > 1 (one process per GPU) averages the gradients over the ranks with one NCCL
+        all-reduce between backward and the optimiser step (the reference uses nn.DataParallel in one process)."""
+        self.optG.zero_grad()
+        l_pix = self.netG(self.data)
+        b, c, h, w = self.data["HR"].shape
+        l_pix = l_pix.sum() / int(b * c * h * w)
+        l_pix.backward(retain_graph=True)
+        if world > 1:
+            from .diffusion import allreduce_gradients
+            allreduce_gradients(self.netG, world)
+        self.optG.step()
+        self.log_dict["l_pix"] = l_pix.item()
 
     def test(self, continous=False):
         self.netG.eval()

@@ -172,6 +172,26 @@ HSIDM_API int hsidm_num_timesteps(const hsidm_ctx* ctx);
 /* Workspace bytes currently held by the context (arena + packed weights + tables). */
 HSIDM_API int64_t hsidm_ctx_bytes(const hsidm_ctx* ctx);
 
+/* ---- training step ---------------------------------------------------------------------------------- */
+
+/* GaussianDiffusion.p_losses (diffusion.py:222-250) for one batch: x_noisy = level*HR + sqrt(1-level^2)*noise (q_sample,
+ * diffusion.py:213-220), eps = UNet(cat([SR, x_noisy]), level), loss_sum = sum|noise - eps| (loss_type 0, "l1") or
+ * sum (noise - eps)^2 (loss_type 1, "l2").  hr / sr / noise: device [B, out_channel, H, W] fp32 (the GAE latents of the HR cube,
+ * of the bicubic cube, and the N(0,1) draw of diffusion.py:238); levels: B continuous sqrt(alpha_bar) values (host or device;
+ * the np.random.uniform draw of diffusion.py:228-234); dropout_seed keys the counter-based dropout mask of block2
+ * (unet.py:102; the mask is regenerated, not stored, by the backward).  Saves every activation the backward needs in a
+ * workspace owned by the context; grad_slab (device, hsidm_train_grad_numel floats) is where hsidm_train_backward will leave
+ * the gradients.  loss_sum: one float (host or device).  fp32 on CUDA cores, deterministic (no atomics). */
+HSIDM_API int hsidm_train_forward(hsidm_ctx* ctx, const float* hr, const float* sr, const float* noise, const float* levels, int B,
+                        int H, int W, int loss_type, uint64_t dropout_seed, float* grad_slab, float* loss_sum, hsidm_stream stream);
+/* Backward of upstream * loss_sum / (B*out_channel*H*W) (DDPM.optimize_parameters, model.py:49-55): gradients of every
+ * parameter into the slab given to the forward; parameter i (hsidm_unet_param_name order) starts at element
+ * hsidm_train_grad_offset(ctx, i) and has the parameter's own shape and layout.  The slab is contiguous so that a
+ * data-parallel job all-reduces it with ONE NCCL call (BASELINE configs[4]).  Consumes the saved forward. */
+HSIDM_API int hsidm_train_backward(hsidm_ctx* ctx, float upstream, hsidm_stream stream);
+HSIDM_API int64_t hsidm_train_grad_numel(const hsidm_ctx* ctx);
+HSIDM_API int64_t hsidm_train_grad_offset(const hsidm_ctx* ctx, int index);
+
 /* ---- group autoencoder ------------------------------------------------------------------------------ */
 
 /* GAE.__init__ (AE.py:256-280). */
