@@ -17,6 +17,7 @@ Other workloads (not what the driver runs; lines committed under profiles/):
   --workload c3   BASELINE configs[2]: one 102-band Pavia-Centre-shaped scene (1096x715) as 70 overlapping 128x128 tiles,
                   STRONG scaling: tiles sharded over the ranks, NCCL gather of the device tensors to rank 0 and the blend
                   on the GPU inside the timed region; value = tiles (patches) per second.
+  --workload c5   BASELINE configs[4]: data-parallel TRAINING step (fp32 first version), value = cubes per second through training.
   --workload c1   BASELINE configs[0]: one 31-band CAVE-shaped cube, batch 1, T = 50 (5 group latents per step): the
                   reference's own call pattern; CPU arm run in full.
 
@@ -54,6 +55,10 @@ WORKLOADS = {
     "c3": dict(bands=102, geom=(102, 16, 4), T=2000, batch=16, gae_gflop=75.71 + 78.97, scene=(1096, 715), tile=128, overlap=16,
                text="configs[2]: 102-band Pavia-Centre-shaped scene 1096x715, GAE_4_Pav geometry (G=9), 70 overlapping 128x128 tiles "
                     "(overlap 16) sharded over the GPUs, T=2000 cosine DDPM sampling, NCCL gather + GPU blend in the timed region"),
+    "c5": dict(bands=31, geom=(31, 8, 2), T=2000, batch=4, gae_gflop=41.30 + 43.23,
+               text="configs[4]: training step (p_losses forward + hand-written backward + NCCL all-reduce of the gradient slab + Adam) of the "
+                    "16_128ae UNet on 31-band Harvard-shaped 128x128 synthetic batches, 4 cubes per GPU, one optimiser step per band "
+                    "group (G=5) like sr_gae.py:245-250; fp32 CUDA-core kernels (the bf16 tensor-core backward is not built yet)"),
     "c1": dict(bands=31, geom=(31, 8, 2), T=50, batch=1, gae_gflop=41.30 + 43.23,
                text="configs[0]: one 31-band CAVE-shaped 128x128 cube, GAE_4_Cav geometry (G=5), batch 1, T=50 cosine schedule "
                     "(5 group latents per step)"),
@@ -314,6 +319,67 @@ def roofline_leg(lib, gd, z, K, n_lat, ms_per_step, pk) -> dict:
             "whole_step_frac_of_peak": UNET_GFLOP * n_lat / ms_per_step / pk["tf_sustained"]}
 
 
+def run_training(args, wl, gd, gae, dev, rank, world, local, lib, barrier, max_over_ranks) -> None:
+    """BASELINE configs[4]: K optimiser steps (default 10) of the reference's training loop body (sr_gae.py:236-250): encode HR
+    and SR cubes once, then for each band group p_losses -> backward -> gradient all-reduce -> Adam."""
+    import torch
+    from hsi_dmgasr_b200 import synth
+    from hsi_dmgasr_b200.diffusion import allreduce_gradients
+    from hsi_dmgasr_b200.spec import GAEGeometry
+    geom = GAEGeometry(*wl["geom"])
+    B = args.batch or wl["batch"]
+    K = 10 if args.steps >= wl["T"] else max(1, args.steps)
+    W = max(args.warmup, 3)
+    gd.train()
+    gd.set_loss(dev)
+    gd.set_new_noise_schedule(dict(SCHED, n_timestep=wl["T"]), dev)
+    opt = torch.optim.Adam(list(gd.parameters()), lr=1e-5)          # config "train.optimizer.lr"
+    hr = synth.sr_cube(B, wl["bands"], HW, seed=200 + rank).to(dev)
+    sr = synth.sr_cube(B, wl["bands"], HW, seed=300 + rank).to(dev)
+    z_hr, z_sr = gae.encode(hr), gae.encode(sr)
+
+    def step(i):
+        g = i % geom.G
+        opt.zero_grad()
+        l_pix = gd({"HR": z_hr[g], "SR": z_sr[g]})
+        b, c, h, w = z_hr[g].shape
+        l = l_pix.sum() / int(b * c * h * w)
+        l.backward()
+        allreduce_gradients(gd, world)
+        opt.step()
+        return l
+
+    for i in range(W):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.hsidm_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for i in range(K):
+        last = step(i)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / K
+    clk = clocks.stop(t0, t1) if clocks else None
+    if rank == 0:
+        # fwd + bwd of a conv net = 3x the forward FLOPs (dgrad + wgrad), per latent image
+        tflops = 3 * UNET_GFLOP * B / ms
+        line = {"metric": "HSI SR patches/sec (training step, cubes through G optimiser steps)", "value": world * B / (geom.G * ms * 1e-3),
+                "unit": "patches/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl, B),
+                "latents_per_step": B, "loss": float(last), "clocks": clk, "gpu_launches": int(lib.hsidm_launch_count() - launches0),
+                "achieved_tflops_fwd_bwd": tflops, "e2e": None, "roofline": None, "cpu_baseline": None,
+                "note": "optimizer = torch.optim.Adam (as the reference); gradient all-reduce = one NCCL call on the contiguous slab"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -383,6 +449,8 @@ def main() -> None:
         return float(t.item())
 
     extra = {}
+    if args.workload == "c5":
+        return run_training(args, wl, gd, gae, dev, rank, world, local, lib, barrier, max_over_ranks)
     if args.workload == "c3":
         # ---- strong scaling over the tiles of one scene ------------------------------------------------------------------
         hs, ws = wl["scene"]

@@ -94,3 +94,37 @@ def test_two_rank_sharding_and_gather_gloo():
         assert p.exitcode == 0
     assert ret["cubes_ok"] and ret["scene_ok"] and ret["other_none"]
     assert ret["slice0"] == (0, 4) and ret["slice1"] == (4, 7)
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hsi_dmgasr_b200.diffusion import allreduce_gradients
+
+        class Holder:
+            pass
+        h = Holder()
+        h.last_grad_slab = torch.arange(6, dtype=torch.float32) * (rank + 1)
+        view = h.last_grad_slab[2:4]                       # a parameter's .grad is a view of the slab
+        allreduce_gradients(h, world, dist)
+        ret[f"slab{rank}"] = h.last_grad_slab.tolist()
+        ret[f"view{rank}"] = view.tolist()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_averages_the_slab_gloo():
+    """Data-parallel training (BASELINE configs[4]): one all-reduce of the contiguous gradient slab, then 1/world; the
+    per-parameter .grad views see the averaged values."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    want = [1.5 * i for i in range(6)]                     # mean of i*1 and i*2
+    assert ret["slab0"] == want and ret["slab1"] == want and ret["view0"] == want[2:4]

@@ -159,3 +159,63 @@ def test_dropout_mask_statistics_and_regeneration():
     assert abs(fd - float(grad[1])) < 2e-3 * max(1.0, abs(fd)), (fd, float(grad[1]))
     # a different dropout seed gives a different loss, the same seed the same loss
     assert float(loss_at(0.0, 9)) == float(base) and float(loss_at(0.0, 10)) != float(base)
+
+
+def _dp_worker(rank, world, port, path):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from hsi_dmgasr_b200.diffusion import allreduce_gradients
+        g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_step.npz"))
+        with torch.cuda.device(rank):
+            net = UNet(in_channel=6, out_channel=3, inner_channel=32, norm_groups=8, channel_mults=(1, 2), attn_res=(8,), res_blocks=1,
+                       dropout=0.0, image_size=16, precision="fp32")
+            net.load_state_dict(synth.unet_state_dict(TRAIN, SEED))
+            dev = torch.device("cuda", rank)
+            gd = GaussianDiffusion(net, image_size=HW, channels=3, loss_type="l1", conditional=True).to(dev).train()
+            gd.set_new_noise_schedule(dict(schedule="cosine", n_timestep=T, linear_start=1e-6, linear_end=1e-2), dev)
+            gd.set_loss(dev)
+            hr, sr, noise = rand((B, 3, HW, HW), 61), rand((B, 3, HW, HW), 62), rand((B, 3, HW, HW), 63)
+            # rank r takes sample r of the golden batch (the third one is dropped): the averaged gradient must equal the gradient
+            # of the two-sample batch normalised by ITS element count
+            sl = slice(rank, rank + 1)
+            with injected_numpy_draws(g["l1.levels"][sl]):
+                l_pix = gd({"HR": hr[sl].to(dev), "SR": sr[sl].to(dev)}, noise=noise[sl].to(dev))
+            (l_pix.sum() / int(1 * 3 * HW * HW)).backward()
+            allreduce_gradients(gd, world)
+            if rank == 0:
+                torch.save({k: p.grad.cpu() for k, p in gd.denoise_fn.named_parameters()}, path)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_data_parallel_gradients_equal_the_joint_batch(tmp_path, golden):
+    """BASELINE configs[4]: one process per GPU, NCCL all-reduce of the gradient slab.  Two ranks with one sample each
+    give the gradient of the joint two-sample batch computed on one GPU."""
+    import socket
+    import torch.multiprocessing as mp
+    g = golden("train_step.npz")
+    gd = build("l1")
+    hr, sr, noise = rand((B, 3, HW, HW), 61).cuda(), rand((B, 3, HW, HW), 62).cuda(), rand((B, 3, HW, HW), 63).cuda()
+    with injected_numpy_draws(g["l1.levels"][:2]):
+        l_pix = gd({"HR": hr[:2], "SR": sr[:2]}, noise=noise[:2])
+    (l_pix.sum() / int(2 * 3 * HW * HW)).backward()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    path = str(tmp_path / "dp.pt")
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, path)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    dp = torch.load(path)
+    worst = max(rel_l2(dp[k], p.grad) for k, p in gd.denoise_fn.named_parameters())
+    print(f"2-rank data-parallel vs joint batch: worst gradient rel-L2 {worst:.2e}")
+    assert worst < 1e-5
