@@ -17,6 +17,7 @@ Other workloads (not what the driver runs; lines committed under profiles/):
   --workload c3   BASELINE configs[2]: one 102-band Pavia-Centre-shaped scene (1096x715) as 70 overlapping 128x128 tiles,
                   STRONG scaling: tiles sharded over the ranks, NCCL gather of the device tensors to rank 0 and the blend
                   on the GPU inside the timed region; value = tiles (patches) per second.
+  --workload c4   BASELINE configs[3]: the 64_512 UNet at 512x512 on one Harvard-shaped cube (5 latents per step).
   --workload c5   BASELINE configs[4]: data-parallel TRAINING step (fp32 first version), value = cubes per second through training.
   --workload c1   BASELINE configs[0]: one 31-band CAVE-shaped cube, batch 1, T = 50 (5 group latents per step): the
                   reference's own call pattern; CPU arm run in full.
@@ -55,6 +56,11 @@ WORKLOADS = {
     "c3": dict(bands=102, geom=(102, 16, 4), T=2000, batch=16, gae_gflop=75.71 + 78.97, scene=(1096, 715), tile=128, overlap=16,
                text="configs[2]: 102-band Pavia-Centre-shaped scene 1096x715, GAE_4_Pav geometry (G=9), 70 overlapping 128x128 tiles "
                     "(overlap 16) sharded over the GPUs, T=2000 cosine DDPM sampling, NCCL gather + GPU blend in the timed region"),
+    "c4": dict(bands=31, geom=(31, 8, 2), T=2000, batch=1, gae_gflop=16 * (41.30 + 43.23), hw=512, unet_gflop=1246.11,
+               unet=dict(in_channel=6, out_channel=3, inner_channel=64, norm_groups=16, channel_mults=(1, 2, 4, 8, 16), attn_res=(),
+                         res_blocks=1, dropout=0.2, image_size=128),
+               text="configs[3]: config/sr_sr3_64_512.json UNet (155.3 M params, mid-block attention at 32x32 = 1024 tokens) on one 31-band "
+                    "Harvard-shaped 512x512 cube, GAE_4_Har geometry (G=5): 5 latents of 512x512 per step, T=2000"),
     "c5": dict(bands=31, geom=(31, 8, 2), T=2000, batch=4, gae_gflop=41.30 + 43.23,
                text="configs[4]: training step (p_losses forward + hand-written backward + NCCL all-reduce of the gradient slab + Adam) of the "
                     "16_128ae UNet on 31-band Harvard-shaped 128x128 synthetic batches, 4 cubes per GPU, one optimiser step per band "
@@ -243,7 +249,8 @@ def run_reference(args, wl) -> None:
 
 def workload_config(args, wl, batch) -> dict:
     geom_g = -(-(wl["geom"][0] - wl["geom"][2]) // (wl["geom"][1] - wl["geom"][2]))
-    return {"workload": wl["text"], "unet": "config/sr_sr3_16_128ae.json (97.8 M params)", "timesteps": wl["T"],
+    return {"workload": wl["text"], "unet": "config/sr_sr3_64_512.json (155.3 M params)" if "unet" in wl else "config/sr_sr3_16_128ae.json (97.8 M params)",
+            "timesteps": wl["T"],
             "patches_per_gpu": batch, "groups": geom_g,
             "parallelism": (f"tiles sharded over {args.gpus} GPU(s), one gather at the end" if args.workload == "c3"
                             else f"replica per GPU x{args.gpus}, patches sharded, no per-step collective"),
@@ -396,6 +403,8 @@ def main() -> None:
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager GPU library baseline leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    global UNET, HW, UNET_GFLOP
+    UNET, HW, UNET_GFLOP = wl.get("unet", UNET), wl.get("hw", HW), wl.get("unet_gflop", UNET_GFLOP)
     T_FULL = wl["T"]
     if args.steps is None:
         args.steps = T_FULL
@@ -429,6 +438,8 @@ def main() -> None:
     net = UNet(**{**UNET, "attn_res": list(UNET["attn_res"])}, precision=args.precision)
     net.load_state_dict(synth.unet_state_dict(cfg, 0))
     gd = GaussianDiffusion(net, image_size=128, channels=3, conditional=True).to(dev).eval()
+    if args.workload == "c4":
+        args.no_gpu_baseline = True     # the torch-eager leg is sized for the 128x128 workloads
     gae = GAE(n_subs=geom.n_subs, n_ovls=geom.n_ovls, n_colors=geom.n_colors, n_feats=geom.n_feats, precision=args.gae_precision)
     gae.load_state_dict(synth.gae_state_dict(geom, 1))
     gae = gae.to(dev).eval()
@@ -587,7 +598,8 @@ def main() -> None:
 
     cpu = gpu_base = None
     if rank == 0 and not args.no_cpu:
-        cpu = cpu_reference_leg(wl, steps=20, warmup=2, full=args.workload == "c1")
+        cpu = cpu_reference_leg(wl, steps=4 if args.workload == "c4" else 20, warmup=1 if args.workload == "c4" else 2,
+                                full=args.workload == "c1")
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
         torch.cuda.empty_cache()

@@ -8,6 +8,7 @@ TEST INFRASTRUCTURE (like make_golden.py; same import shims).  Sections, selecta
   dropin   the reference's own call pattern of the validation loop (sr_gae.py:444-475): Model.create_model(opt) with
            config/sr_sr3_16_128ae.json, per band group feed_data / test / get_current_visuals, GAE_4_Cav.pth decode,
            clamp - on one 31-band 32x32 cube, val schedule (T = 20), injected noise -> dropin.npz
+  c4       one forward of the sr_sr3_64_512.json UNet at 512x512 (BASELINE configs[3]) -> c4_512.npz
   long     the same loop at the HEADLINE schedule length (T = 2000, cosine) with injected noise, for the tiny UNet at
            16x16 and the full 16_128ae UNet at 32x32, plus the reference's own drift under torch bf16 autocast for
            the tiny one -> e2e_T2000_small.npz, e2e_T2000_full.npz
@@ -251,8 +252,23 @@ def section_long(AE, eval_hsi, unet_mod, diff_mod):
                             mpsnr=np.float64(psnr), T=T, hw=hw, **extra)
 
 
+def section_c4(unet_mod):
+    """BASELINE configs[3]: the sr_sr3_64_512.json UNet (inner 64, mults 1-2-4-8-16, norm_groups 16, mid-block attention only)
+    on one 512x512 latent: eps of the unmodified reference, stored on the stride-4 pixel lattice plus full-resolution
+    per-channel mean / rms and per-row-block fingerprints -> c4_512.npz."""
+    net = MG.ref_unet(unet_mod, MG.WIDE, 13)
+    x = MG.rand((1, 6, 512, 512), 2013)
+    lv = torch.tensor([[0.37]], dtype=torch.float32)
+    t0 = time.time()
+    y = net(x, lv)
+    print(f"c4 512x512 forward {time.time() - t0:.0f}s", tuple(y.shape), float(y.abs().mean()))
+    np.savez_compressed(os.path.join(OUT, "c4_512.npz"), eps_s4=y[..., ::4, ::4].contiguous().numpy(), level=lv.numpy(),
+                        mean=y.double().mean(dim=(-1, -2)).numpy(), rms=y.double().pow(2).mean(dim=(-1, -2)).sqrt().numpy(),
+                        block_rms=y.double().pow(2).view(1, 3, 16, 32, 16, 32).mean(dim=(3, 5)).sqrt().numpy())
+
+
 def main():
-    sections = sys.argv[1:] or ["ckpt", "gae128", "dropin", "long"]
+    sections = sys.argv[1:] or ["ckpt", "gae128", "dropin", "long", "c4"]
     AE, eval_hsi, unet_mod, diff_mod = MG.import_reference()
     torch.set_grad_enabled(False)
     if "ckpt" in sections:
@@ -263,6 +279,8 @@ def main():
         section_dropin(AE)
     if "long" in sections:
         section_long(AE, eval_hsi, unet_mod, diff_mod)
+    if "c4" in sections:
+        section_c4(unet_mod)
 
 
 if __name__ == "__main__":

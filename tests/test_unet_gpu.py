@@ -153,3 +153,24 @@ def test_c4_shape_512_bf16_tracks_fp32():
     print(f"C4 512x512: bf16 vs fp32 rel-L2 {err:.3e}")
     assert torch.isfinite(outs["bf16"]).all() and outs["bf16"].shape == (1, 3, 512, 512)
     assert err < TOL["bf16"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_c4_512_against_the_unmodified_reference(golden, precision):
+    """BASELINE configs[3] pinned at its own size: eps of the sr_sr3_64_512.json UNet on one 512x512 latent against the
+    unmodified reference (tests/golden/c4_512.npz, oracle/make_golden_r2.py section c4): the stride-4 pixel lattice in full,
+    plus full-resolution per-channel mean / rms and 16x16 block rms."""
+    g = golden("c4_512.npz")
+    cfg, seed, *_ = UNET_CASES["wide64"]
+    x = torch.from_numpy(np.random.default_rng(2013).standard_normal((1, 6, 512, 512), dtype=np.float32)).cuda()
+    lv = torch.from_numpy(g["level"]).cuda()
+    net = build(cfg, seed, precision)
+    with torch.no_grad():
+        y = net(x, lv)
+    err = rel_l2(y[..., ::4, ::4], torch.from_numpy(g["eps_s4"]))
+    rms = y.double().pow(2).mean(dim=(-1, -2)).sqrt().cpu()
+    blk = y.double().pow(2).view(1, 3, 16, 32, 16, 32).mean(dim=(3, 5)).sqrt().cpu()
+    e_rms = float((rms - torch.from_numpy(g["rms"])).abs().max() / torch.from_numpy(g["rms"]).abs().max())
+    e_blk = float((blk - torch.from_numpy(g["block_rms"])).abs().max() / torch.from_numpy(g["block_rms"]).abs().max())
+    print(f"C4 512x512 {precision}: eps rel-L2 vs reference {err:.3e}, channel rms rel {e_rms:.1e}, block rms rel {e_blk:.1e}, flag {tc_flag()}")
+    assert err < TOL[precision] and e_blk < 10 * TOL[precision]
