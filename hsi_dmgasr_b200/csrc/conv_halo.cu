@@ -18,7 +18,7 @@
 // Forms (template NT): 9 = 3x3 stride 1; 4 = the sub-pixel form of nearest-2x upsampling + 3x3 (a 2x2-tap conv over the
 // low-res source per output parity); 1 = a short-K 1x1 conv (centre tap); 0 = 3x3 stride 2 over the four phase
 // lattices of the input.  Optional per op: GroupNorm(+Swish) of the input applied in place to each halo tile
-// (gn_ab), a 1x1 shortcut over other tensors as extra centre-tap K columns (rsrc), per-slot GroupNorm partial sums
+// (gn), a 1x1 shortcut over other tensors as extra centre-tap K columns (rsrc), per-slot GroupNorm partial sums
 // of the output (stats).
 //
 // Warp roles (15 warps): 0 = TMA producer of the halo ring (2-3 stages), 1 = TMA producer of the weight ring (stages
@@ -30,6 +30,7 @@
 // the weight rows split between the CTAs, MMAs (M = 256) issued by the leader and completed on both CTAs' barriers.
 #include <cstdlib>
 
+#include "gn_fold.cuh"
 #include "tc_common.cuh"
 
 namespace hsidm {
@@ -55,11 +56,20 @@ struct HaloP {
   int kb0;                // first 64-wide k-block of this launch's weight columns (parity * 4 * chunks)
   int oscale, oy, ox;     // output pixel of source-tile pixel (i,j) = (oscale*i + oy, oscale*j + ox)
   int slot_base;          // first statistics slot of this launch
+  int seg_max;            // statistics slots (x 2 for a pair) per (image, channel tile) group and launch: max CTA segments of a group
   int Hin, Win;           // source image size (the fused GroupNorm must leave the zero padding at zero)
-  const float* gn_ab;     // fused input GroupNorm: per-image per-channel (A, B), [N][chunks*64][2]; null = none
+  // fused input GroupNorm (kernels.cuh GnIn): the transform warps fold the statistics of the images this CTA works on
+  int gn_on;
+  const float* gn_part0; const float* gn_part1;   // [N][slots][C][2] partial sums of source 0 / 1
+  int gn_slots0, gn_slots1;
+  const float* gn_stats;  // alternative: precomputed (mean, rstd) [N][groups][2]
+  const float* gn_gamma; const float* gn_beta;
+  int gn_groups, gn_cpg;
+  float gn_eps, gn_inv_cnt;
   int gn_swish;
   EpiP e;
   int* err;
+  int tiles_q, tiles_r;   // tiles per CTA (pair): quotient and remainder of tiles / CTAs (the first tiles_r get one more)
   int variant;            // developer experiments (timing only, results invalid): 1 skip epilogue, 2 skip B loads, 4 skip A loads
   long long* dbg;         // developer timing probe (null in production): per-CTA wait cycles of every role
 };
@@ -85,7 +95,10 @@ struct HCfg {
   static constexpr int kBRows = PAIR ? BN / 2 : BN;                         // weight rows this CTA holds (a pair splits them)
   static constexpr int kBStage = kBRows * 128;
   static constexpr int kStageBytes = kEpiWarps * 4096;                     // epilogue staging, 4 KB per epilogue warp
-  static constexpr int kBStagesRaw = (232448 - 1536 - kEpiWarps * 512 - kStageBytes - kAStages * kAStage) / kBStage;
+  // Per-tile fold of the epilogue warps' GroupNorm partial sums: 512 B per warp and 64-channel chunk.  With at most one
+  // chunk per warp (BN <= 128) the warps' bias slots double as the fold area; BN = 256 (two chunks per warp) has its own.
+  static constexpr int kFoldBytes = BN / 64 > 2 ? kEpiWarps * 1024 : 0;
+  static constexpr int kBStagesRaw = (232448 - 1536 - 2048 - kEpiWarps * 512 - kFoldBytes - kStageBytes - kAStages * kAStage) / kBStage;
   // Weight tiles land in groups of kBGroup taps that share ONE full barrier: every barrier wait of the MMA issuer
   // stalls the tensor pipe for ~160 clk (measured, scripts/mma_rate.cu), so it waits once per group, not per tap.
   // Stages are still released (tcgen05.commit, free) and refilled one tap at a time.
@@ -94,7 +107,8 @@ struct HCfg {
   static constexpr int kBStages = kBGroups * kBGroup;
   static constexpr int kTmemCols = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;
   static constexpr int kBiasBytes = kEpiWarps * 512;                       // 2 x 64 bias floats per epilogue warp
-  static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + kStageBytes + kBiasBytes + 1024 + 512;
+  static constexpr int kStatBytes = 2048;   // (mean, rstd) of a window of images x groups for the fused input GroupNorm
+  static constexpr int kSmemBytes = kAStages * kAStage + kBStages * kBStage + kStageBytes + kBiasBytes + kFoldBytes + kStatBytes + 1024 + 512;
   static_assert(kBGroups >= 2, "not enough shared memory for the B ring");
   static_assert(2 * MT * BN <= 512, "accumulators do not fit TMEM");
 };
@@ -110,7 +124,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint8_t* smem_b = smem + C::kAStages * C::kAStage;
   uint8_t* smem_stage = smem_b + C::kBStages * C::kBStage;
   uint8_t* smem_bias = smem_stage + C::kStageBytes;
-  uint8_t* tail = smem_bias + C::kBiasBytes;
+  uint8_t* smem_fold = smem_bias + C::kBiasBytes;   // BN = 256 only; otherwise the bias slots are reused
+  uint8_t* smem_stat = smem_fold + C::kFoldBytes;
+  uint8_t* tail = smem_stat + C::kStatBytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* a_empty = a_full + C::kAStages;
   uint64_t* a_ready = a_empty + C::kAStages;   // halo tile normalised in place (fused GroupNorm only)
@@ -125,13 +141,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // tile; each holds its own halo tiles and half of the weight rows, and the leader (rank 0) issues M = 256
   // cta_group::2 MMAs over both.  Per MMA a CTA then reads its A slice plus HALF a B slice from shared memory.
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-  const int total_tiles = PAIR ? (p.m_tiles / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
-  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  auto m_tile_of = [&](int tile) { return PAIR ? 2 * (tile / p.n_tiles) + (int)rank : tile / p.n_tiles; };
+  // Tile order: every CTA (pair) walks a CONTIGUOUS range of tiles.  It then touches only a few consecutive images, whose
+  // GroupNorm statistics its transform warps fold once (window in shared memory) - no finalize kernel in front.  (Groups
+  // of CTAs striding through a shared range measured slower the larger the group: more images per CTA, more refills.)
+  // The tile loops below run over an ARGUMENT-ONLY trip count (tiles_q + 1) and leave through a break: with a loop bound
+  // derived from blockIdx ptxas takes every loop-carried ring index of the MMA issuer out of the uniform datapath and
+  // the issuer pays five R2UR moves per tcgen05.mma (measured: 86 -> 122 clk per MMA on the 64-channel layers).
+  const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile0 = cta * p.tiles_q + min(cta, p.tiles_r);
+  const int total_tiles = tile0 + p.tiles_q + (cta < p.tiles_r ? 1 : 0);   // end of this CTA's range
+  // tile -> (image n, channel tile nt, pixel tile r of the image): the tiles of one (image, channel tile) GROUP are
+  // consecutive, pixel tile fastest (a pair's CTAs take the pixel tiles 2*rp and 2*rp + 1), so that an epilogue warp
+  // can keep the group's GroupNorm partial sums in registers from tile to tile (see the epilogue)
+  const int tpi = p.tiles_x * p.tiles_y;
+  const int tpp = PAIR ? tpi >> 1 : tpi;   // tiles (pair tiles) per group
+  auto decode = [&](int tile, int& n, int& nt, int& r) {
+    const int u = tile / tpp, rp = tile - u * tpp;
+    n = u / p.n_tiles, nt = u - n * p.n_tiles;
+    r = PAIR ? 2 * rp + (int)rank : rp;
+  };
   const int chunks = p.chunks0 + p.chunks1;
   const int rchunks = p.rchunks0 + p.rchunks1;
-  const int tpi = p.tiles_x * p.tiles_y;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -157,7 +187,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // REDUX leaves the (identical) value in a UNIFORM register: otherwise ptxas may treat the address read back from shared
+  // memory as divergent and re-broadcast it (R2UR) in front of every tcgen05.mma - 10 clk per MMA on the issuer's path
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);
 
   if (warp == 0) {
     // =============================== TMA producer: halo tiles (A) ===============================
@@ -168,9 +200,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t aph = 0;
       bool ok = true;
       long long w_ae = 0;
-      for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
-        const int mt = m_tile_of(tile);
-        const int n = mt / tpi, r = mt - n * tpi;
+      for (int kt = 0; kt <= p.tiles_q && ok; ++kt) {   // argument-only trip count, see tile0
+        const int tile = tile0 + kt;
+        if (tile >= total_tiles) break;
+        int n, nt_unused, r;
+        decode(tile, n, nt_unused, r);
         const int y0 = (r / p.tiles_x) * kRows, x0 = (r % p.tiles_x) * (8 * MT);
         for (int ch = 0; ch < chunks + rchunks; ++ch) {
           ok = timed_wait(smem_u32(&a_empty[as]), aph ^ 1, p.err, 1, p.dbg, w_ae);
@@ -223,8 +257,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (++bs == C::kBStages) bs = 0, bph ^= 1;
         if (++gcnt == C::kBGroup) gcnt = 0, grp = grp + 1 == C::kBGroups ? 0 : grp + 1;
       };
-      for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
-        const int nt = tile % p.n_tiles;
+      for (int kt = 0; kt <= p.tiles_q && ok; ++kt) {   // argument-only trip count, see tile0
+        const int tile = tile0 + kt;
+        if (tile >= total_tiles) break;
+        const int nt = (tile / tpp) % p.n_tiles;
         if constexpr (NT == 0) {   // stride-2 form: weights are packed in consumption order, 9 k-blocks per channel block
           for (int kb = 0; kb < 9 * (chunks >> 2) && ok; ++kb) load_b(kb, nt);
         }
@@ -262,13 +298,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       bool ok = true;
       long long w_te = 0, w_af = 0, w_bf = 0;
       const long long t_start = p.dbg ? clock64() : 0;
-      for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
+      for (int kt = 0; kt <= p.tiles_q && ok; ++kt) {   // argument-only trip count, see tile0
+        const int tile = tile0 + kt;
+        if (tile >= total_tiles) break;
         ok = timed_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.err, 2, p.dbg, w_te);
         if (!ok) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (MT * BN);
         for (int ch = 0; ch < chunks && ok; ++ch) {
-          ok = timed_wait(smem_u32((PAIR || p.gn_ab) ? &a_ready[as] : &a_full[as]), aph, p.err, 3, p.dbg, w_af);
+          ok = timed_wait(smem_u32((PAIR || p.gn_on) ? &a_ready[as] : &a_full[as]), aph, p.err, 3, p.dbg, w_af);
           if (!ok) break;
           const uint64_t adesc0 = desc_hi | (uint64_t)((smem_u32(smem + as * C::kAStage) + tap0) >> 4);
           // one tap: (group barrier) -> MT*4 MMAs from the halo tile at byte offset `off` -> release the weight stage
@@ -322,7 +360,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (++as == C::kAStages) as = 0, aph ^= 1;
         }
         for (int rc = 0; rc < rchunks && ok; ++rc) {   // shortcut: centre tap of the un-normalised block input
-          ok = timed_wait(smem_u32((PAIR || p.gn_ab) ? &a_ready[as] : &a_full[as]), aph, p.err, 3, p.dbg, w_af);
+          ok = timed_wait(smem_u32((PAIR || p.gn_on) ? &a_ready[as] : &a_full[as]), aph, p.err, 3, p.dbg, w_af);
           if (!ok) break;
           if (gcnt == 0) {
             ok = timed_wait(smem_u32(&b_full[grp]), gph, p.err, 6, p.dbg, w_bf);
@@ -361,8 +399,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // channels, so 16 affine coefficients in registers) of rows tid/8, tid/8 + 16, ...; a row's logical chunk j sits
     // at physical chunk j ^ (row & 7) (128B swizzle).  Same arithmetic as gn_apply (norm.cu), so fused and unfused
     // paths agree bit for bit.
-    if (PAIR || p.gn_ab) {   // a pair always routes halo readiness through these warps (the leader hears both CTAs)
-      griddep_wait();          // gn_ab is the previous kernel's output
+    if (PAIR || p.gn_on) {   // a pair always routes halo readiness through these warps (the leader hears both CTAs)
+      griddep_wait();          // the statistics are the previous kernels' output
       const int tid = threadIdx.x - 32 * kFirstXformWarp;
       // a_ready of the CTA whose issuer consumes the stage: this CTA's own, or the pair leader's
       auto ready_arrive = [&](int stage) {
@@ -372,25 +410,68 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int j8 = tid & 7, row0 = tid >> 3;
       constexpr int kRowsTot = kHaloRows * C::kPW;
       constexpr int kRowStep = 32 * kXformWarps / 8;
-      const int ctot = chunks * kBK;
+      const int C0 = p.chunks0 * kBK, C1 = p.chunks1 * kBK;
+      // Statistics window: (mean, rstd) of images [win_lo, win_lo + win_n) x groups in shared memory.  This CTA's tiles
+      // are consecutive, so the window moves forward a few times per launch at most.  Thread -> one (image, group), see
+      // gn_fold_group.
+      float2* win = reinterpret_cast<float2*>(smem_stat);
+      const GnFoldP fold{p.gn_part0, p.gn_part1, p.gn_slots0, p.gn_slots1, C0, C1, p.gn_cpg, p.gn_inv_cnt, p.gn_eps};
+      const int win_n = max(1, min(C::kStatBytes / 8 / max(1, p.gn_groups), 64));
+      int win_lo = -(1 << 30);
+      const int n_end = total_tiles > tile0 ? (total_tiles - 1) / tpp / p.n_tiles : 0;   // last image this CTA touches
+      auto fill_window = [&](int n0) {
+        named_bar_sync(2, 32 * kXformWarps);   // nobody still reads the old window
+        // images [n0, n0 + cnt) x groups; with few of them, 2 or 4 adjacent lanes share one (image, group)
+        const int cnt = min(win_n, min(p.e.N_img, n_end + 1) - n0), items = cnt * p.gn_groups;
+        const int S = p.gn_stats ? 1 : items <= 32 ? 4 : items <= 64 ? 2 : 1, per_pass = 32 * kXformWarps / S;
+        for (int base = 0; base < items; base += per_pass) {
+          const int i = base + tid / S;
+          const bool valid = i < items;
+          const int wi = i / p.gn_groups, g = i - wi * p.gn_groups, n = n0 + wi;
+          float2 v;
+          if (p.gn_stats) v = valid ? *reinterpret_cast<const float2*>(p.gn_stats + ((long long)n * p.gn_groups + g) * 2) : make_float2(0.f, 0.f);
+          else v = gn_fold_group(fold, n, g, tid % S, S, valid);
+          if (valid && tid % S == 0) win[i] = v;
+        }
+        named_bar_sync(2, 32 * kXformWarps);
+        win_lo = n0;
+      };
       int as = 0;
       uint32_t aph = 0;
       bool ok = true;
-      for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
-        const int mt = m_tile_of(tile);
-        const int n = mt / tpi, r = mt - n * tpi;
+      for (int kt = 0; kt <= p.tiles_q && ok; ++kt) {   // argument-only trip count, see tile0
+        const int tile = tile0 + kt;
+        if (tile >= total_tiles) break;
+        int n, nt_unused, r;
+        decode(tile, n, nt_unused, r);
         const int y0 = (r / p.tiles_x) * kRows - 1, x0 = (r % p.tiles_x) * (8 * MT) - 1;   // image coordinates of halo (0,0)
+        if (p.gn_on && n >= win_lo + win_n) fill_window(n);
+        const float2* wst = win + (p.gn_on ? (n - win_lo) * p.gn_groups : 0);
         for (int ch = 0; ch < chunks && ok; ++ch) {
-          // coefficients of this thread's 8 channels (issued before the wait: independent of the tile data)
+          // coefficients of this thread's 8 channels (before the wait: independent of the tile data): A = rstd*gamma,
+          // B = beta - mean*A, the expressions gn_apply evaluates
           float4 ab[4];
-          if (p.gn_ab) {
-            const float4* abp = reinterpret_cast<const float4*>(p.gn_ab + ((long long)n * ctot + ch * kBK + j8 * 8) * 2);
+          if (p.gn_on) {
+            const int c0 = ch * kBK + j8 * 8;
+            const float4* gp = reinterpret_cast<const float4*>(p.gn_gamma + c0);
+            const float4* bp = reinterpret_cast<const float4*>(p.gn_beta + c0);
+            const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), b0 = __ldg(bp), b1 = __ldg(bp + 1);
+            const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            int g = c0 / p.gn_cpg, rem = c0 - g * p.gn_cpg;
+            float2 st = wst[g];
+            float A[8], B[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ab[q] = __ldg(abp + q);
+            for (int q = 0; q < 8; ++q) {
+              A[q] = st.y * gam[q], B[q] = bet[q] - st.x * A[q];
+              if (++rem == p.gn_cpg && q < 7) rem = 0, st = wst[++g];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ab[q] = make_float4(A[2 * q], B[2 * q], A[2 * q + 1], B[2 * q + 1]);
           }
           ok = mbar_wait(smem_u32(&a_full[as]), aph, p.err, 7);
           if (!ok) break;
-          if (!p.gn_ab) {   // pair without a fused GroupNorm: relay only
+          if (!p.gn_on) {   // pair without a fused GroupNorm: relay only
             __syncwarp();
             if (lane == 0) ready_arrive(as);
             if (++as == C::kAStages) as = 0, aph ^= 1;
@@ -452,9 +533,58 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     bool ok = true;
     long long w_tf = 0;
     const long long t_start = p.dbg ? clock64() : 0;
-    for (int tile = tile0; tile < total_tiles && ok; tile += tile_step) {
-      const int mt = m_tile_of(tile), nt = tile % p.n_tiles;
-      const int n = mt / tpi, r = mt - n * tpi;
+    // GroupNorm partial sums of the output: every warp keeps the (sum, sumsq) of its rows x its 64-channel chunk(s) in
+    // registers across the consecutive tiles of one (image, channel tile) group; when the group changes the eight warps
+    // fold them through shared memory (two named barriers - per GROUP, not per tile: a barrier per tile puts the warps
+    // in lock step and costs the epilogue-bound layers 20-30 %) and publish ONE slot per (group segment, CTA).
+    // A group cut by the CTA ranges has one slot per segment; the CTA holding its last tile zero-fills the rest.
+    constexpr int kFoldK = C::kFoldBytes ? 2 : 1;   // chunks per warp the fold area holds
+    const uint32_t fold_base = smem_u32(C::kFoldBytes ? smem_fold : smem_bias);
+    const bool stats_on = nC >= 1 && p.e.stats && !(p.variant & 1);
+    float4 gsum[kFoldK];
+    int u_cur = -1;
+    auto flush_group = [&]() {
+      if constexpr (nC >= 1) {
+        constexpr bool by_chunk = nC >= 2;
+        const int we = warp - kFirstEpiWarp;
+#pragma unroll
+        for (int k = 0; k < kFoldK; ++k)
+          sts128(fold_base + (uint32_t)(((we * kFoldK + k) * 32 + lane) * 16),
+                 make_uint4(__float_as_uint(gsum[k].x), __float_as_uint(gsum[k].y), __float_as_uint(gsum[k].z), __float_as_uint(gsum[k].w)));
+        named_bar_sync(1, 32 * kEpiWarps);
+        if (we < nC) {
+          // epilogue warp `we` adds, in warp order, the partial sums of the warps that worked on chunk `we`
+          const int w0 = by_chunk ? 4 * (we & 1) : 0, w1 = by_chunk ? w0 + 4 : kEpiWarps, kk = by_chunk ? we >> 1 : 0;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int w = w0; w < w1; ++w) {
+            const uint4 u = lds128(fold_base + (uint32_t)(((w * kFoldK + kk) * 32 + lane) * 16));
+            t.x += __uint_as_float(u.x), t.y += __uint_as_float(u.y), t.z += __uint_as_float(u.z), t.w += __uint_as_float(u.w);
+          }
+          // segment index of this CTA within the group = CTAs between the owner of the group's first tile and this one
+          const int first = u_cur * tpp, cut = p.tiles_r * (p.tiles_q + 1);
+          const int owner = first < cut ? first / (p.tiles_q + 1) : p.tiles_r + (first - cut) / p.tiles_q;
+          const int n_g = u_cur / p.n_tiles, nt_g = u_cur - n_g * p.n_tiles;
+          constexpr int R = PAIR ? 2 : 1;
+          int slot = p.slot_base + (cta - owner) * R + (int)rank;
+          stats_store(p.e, n_g, slot, nt_g * BN + we * 64, lane, t);
+          if (total_tiles >= first + tpp)   // this CTA held the group's last tile: the segments nobody wrote count as zero
+            for (slot += R; slot < p.slot_base + p.seg_max * R; slot += R)
+              stats_store(p.e, n_g, slot, nt_g * BN + we * 64, lane, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        named_bar_sync(1, 32 * kEpiWarps);   // the fold area (= the bias slots) may be overwritten from here on
+      }
+    };
+    for (int kt = 0; kt <= p.tiles_q && ok; ++kt) {   // argument-only trip count, see tile0
+      const int tile = tile0 + kt;
+      if (tile >= total_tiles) break;
+      int n, nt, r;
+      decode(tile, n, nt, r);
+      if (stats_on && tile / tpp != u_cur) {
+        if (u_cur >= 0) flush_group();
+        u_cur = tile / tpp;
+#pragma unroll
+        for (int k = 0; k < kFoldK; ++k) gsum[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       const int y = (r / p.tiles_x) * kRows + (row >> 3);
       const int xb = (r % p.tiles_x) * (8 * MT) + (row & 7);
       // this warp's share of the tile: with several 64-channel chunks (BN >= 128) the two warps of a lane quarter take
@@ -508,8 +638,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int s = s_first; s < MT; s += s_step)
             epilogue_tma64(p.e, &tmO, have_bias ? bias_base + k * 256 : 0u, taddr + s * BN + ci * 64, lane, stage, co0, tx0 + 8 * s,
                            ty0 + quarter * 4, n, resid_lane ? resid_lane + 8 * s * xstep : nullptr, pitch, 4 * xstep, st);
-          if (p.e.stats)
-            stats_store(p.e, n, p.slot_base + r * (by_chunk ? 4 : 8) + quarter + (by_chunk ? 0 : 4 * half), co0, lane, st);
+          if (stats_on) {   // this tile's sums of chunk ci (the warp's k-th) join the group's
+            if (kFoldK == 2 && (k & 1)) gsum[kFoldK - 1].x += st.x, gsum[kFoldK - 1].y += st.y, gsum[kFoldK - 1].z += st.z, gsum[kFoldK - 1].w += st.w;
+            else gsum[0].x += st.x, gsum[0].y += st.y, gsum[0].z += st.z, gsum[0].w += st.w;
+          }
         }
       } else {
 #pragma unroll 1
@@ -532,6 +664,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       if (++acc == 2) acc = 0, acc_phase ^= 1;
     }
+    if (stats_on && u_cur >= 0) flush_group();
     if (lane == 0) tma_store_wait_all();   // the staging tiles must outlive the stores reading them
     if (p.dbg && warp == kFirstEpiWarp && lane == 0) p.dbg[blockIdx.x * 8 + 6] = w_tf, p.dbg[blockIdx.x * 8 + 7] = clock64() - t_start;
   }
@@ -563,9 +696,10 @@ void pick_shape(const ConvOp& op, int* MT, int* BN, bool* pair) {
   // advances at the pace of its slower CTA on every chunk); variant bits 64 / 128 switch them on for A/B runs, bit 32
   // switches the N = 256 pair off.
   const int var = host().variant ^ (64 | 128);
-  auto even_tiles = [&](int mt) { return (((long long)op.N * (op.Hin / kRows) * (op.Win / (8 * mt))) & 1) == 0; };
+  // the two CTAs of a pair take the pixel tiles 2*rp and 2*rp + 1 of the SAME image
+  auto even_tiles = [&](int mt) { return (((op.Hin / kRows) * (op.Win / (8 * mt))) & 1) == 0; };
   const bool pair_ok = op.ksize == 3 && !op.s2 && host().pairs_ok;
-  if (op.s2 && (op.ksize != 3 || op.src[1].C || op.rsrc[0].C || op.up_parity >= 0 || op.gn_ab)) return;
+  if (op.s2 && (op.ksize != 3 || op.src[1].C || op.rsrc[0].C || op.up_parity >= 0 || op.gn.on())) return;
   if (op.Cout % 256 == 0 && op.Win % 8 == 0 && pair_ok && !(var & 32) && even_tiles(1)) {
     *MT = 1, *BN = 256, *pair = true;   // N = 256 is the only shape whose MMAs run at the tensor pipe's full rate
   } else if (op.Cout % 128 == 0 && op.Win % 16 == 0) {
@@ -579,6 +713,22 @@ void pick_shape(const ConvOp& op, int* MT, int* BN, bool* pair) {
   } else if (op.Cout <= 16 && op.Win % 32 == 0 && op.ksize == 3 && !op.s2) {
     *MT = 4, *BN = 16;
   }
+}
+
+// Grid and tile partition of a launch: CTAs (pairs), tiles per CTA (quotient / remainder) and the largest number of CTA
+// ranges that can cut one (image, channel tile) group of `tpp` consecutive tiles.
+struct Partition {
+  int ctas, q, r, seg_max;
+};
+Partition partition(const ConvOp& op, int MT, int BN, bool pair) {
+  const int tpi = (op.Win / (8 * MT)) * (op.Hin / kRows), n_tiles = (int)ceil_div(op.Cout, BN);
+  const int tpp = pair ? tpi / 2 : tpi;
+  const long long tiles = (long long)op.N * n_tiles * tpp;
+  Partition pt;
+  pt.ctas = (int)std::min<long long>(tiles, pair ? host().num_sms / 2 : host().num_sms);
+  pt.q = (int)(tiles / pt.ctas), pt.r = (int)(tiles % pt.ctas);
+  pt.seg_max = (tpp - 1) / pt.q + 2;
+  return pt;
 }
 
 template <int MT, int BN, int NT, bool PAIR>
@@ -596,14 +746,29 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   fill_epilogue(&p.e, op);
   p.err = host().err_flag;
   p.dbg = host().halo_dbg;
-  p.Hin = op.Hin, p.Win = op.Win, p.gn_ab = op.gn_ab, p.gn_swish = op.gn_swish;
+  p.Hin = op.Hin, p.Win = op.Win;
+  const GnIn& gn = op.gn;
+  p.gn_on = gn.on() ? 1 : 0;
+  p.gn_part0 = gn.part[0], p.gn_part1 = gn.part[1], p.gn_slots0 = gn.slots[0], p.gn_slots1 = gn.slots[1];
+  p.gn_stats = gn.stats, p.gn_gamma = gn.gamma, p.gn_beta = gn.beta, p.gn_groups = gn.groups, p.gn_swish = gn.swish, p.gn_eps = gn.eps;
+  p.gn_cpg = 1, p.gn_inv_cnt = 0.f;
+  if (p.gn_on) {
+    const int Ct = op.src[0].C + op.src[1].C;
+    if (gn.groups <= 0 || Ct % gn.groups || (!gn.stats && ((Ct / gn.groups) & 1)) || 8 * gn.groups > C::kStatBytes ||
+        (!gn.stats && (gn.C[0] != op.src[0].C || gn.C[1] != op.src[1].C || (op.src[1].C && !gn.part[1]))))
+      HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_halo: fused GroupNorm over %d+%d channels in %d groups is not supported", op.src[0].C, op.src[1].C, gn.groups);
+    p.gn_cpg = Ct / gn.groups;
+    p.gn_inv_cnt = (float)(1.0 / ((double)p.gn_cpg * op.Hin * op.Win));
+  }
   p.variant = host().variant & 7;
   p.dy0 = p.dx0 = NT == 1 ? 1 : 0, p.kb0 = 0, p.oscale = 1, p.oy = p.ox = 0, p.slot_base = 0;
+  const Partition pt = partition(op, MT, BN, PAIR);
+  p.tiles_q = pt.q, p.tiles_r = pt.r, p.seg_max = pt.seg_max;
   if (op.up_parity >= 0) {
     const int py = op.up_parity >> 1, px = op.up_parity & 1;
     p.dy0 = py, p.dx0 = px, p.kb0 = op.up_parity * 4 * (p.chunks0 + p.chunks1);
     p.oscale = 2, p.oy = py, p.ox = px;
-    p.slot_base = op.up_parity * (p.tiles_x * p.tiles_y * (BN / 64 >= 2 ? 4 : 8));
+    p.slot_base = op.up_parity * (pt.seg_max * (PAIR ? 2 : 1));
   }
   CUtensorMap tmA0, tmA1, tmB;
   if (NT == 0) {
@@ -633,18 +798,18 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   char tag[120];
   snprintf(tag, sizeof(tag), "halo%s MT%d BN%d cin%d+%d cout%d %dx%d n%d%s%s%s%s%s", PAIR ? "2" : "", MT, BN, op.src[0].C, op.src[1].C, op.Cout,
            op.Hin, op.Win, op.N, op.resid ? " +res" : "", op.nbias ? " +nb" : "", op.stats_out ? " +st" : "", op.up_parity >= 0 ? " up2x" : op.s2 ? " s2" : "",
-           op.gn_ab ? " +gn" : "");
+           op.gn.on() ? " +gn" : "");
   // algorithmic FLOPs: for the sub-pixel form, the share of the reference's 3x3 conv over the upsampled tensor
   const double flops = op.up_parity >= 0 ? 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * 9 * (op.src[0].C + op.src[1].C)
                                          : 2.0 * op.N * op.Hin * (double)op.Win * op.Cout * K;
   ProfScope prof(PROF_CONV_TC, flops, stream, tag);
   if constexpr (PAIR) {
     // one cluster of two CTAs per pair of adjacent pixel tiles; an even grid of at most one CTA per SM
-    const int pairs = std::min((p.m_tiles / 2) * p.n_tiles, host().num_sms / 2);
+    const int pairs = pt.ctas;
     HSIDM_CUDA(launch_pdl(conv_halo_kernel<MT, BN, NT, true>, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, 2, tmA0, tmA1,
                           tmR0, tmR1, tmB, tmO, p));
   } else {
-    const int grid = std::min(p.m_tiles * p.n_tiles, host().num_sms);
+    const int grid = pt.ctas;
     HSIDM_CUDA(launch_pdl(conv_halo_kernel<MT, BN, NT, false>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, 1, tmA0, tmA1, tmR0,
                           tmR1, tmB, tmO, p));
   }
@@ -689,8 +854,8 @@ int conv_halo_stats_slots(const ConvOp& op) {
   bool pair;
   pick_shape(op, &MT, &BN, &pair);
   if (MT == 0 || BN % 64 || op.out_layout != L_NHWC) return 0;
-  const int tpi = (op.Win / (8 * MT)) * (op.Hin / kRows);
-  return tpi * (BN / 64 >= 2 ? 4 : 8) * (op.up_parity >= 0 ? 4 : 1);
+  // one slot per CTA segment of an (image, channel tile) group (x 2 CTAs of a pair, x 4 output parities of the sub-pixel form)
+  return partition(op, MT, BN, pair).seg_max * (pair ? 2 : 1) * (op.up_parity >= 0 ? 4 : 1);
 }
 
 // Assumes conv_tc_supported(op) already holds (bf16 NHWC sources with 64-multiple channels, Cout fits an N tile).

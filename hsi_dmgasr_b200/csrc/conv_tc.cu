@@ -60,7 +60,7 @@ struct Cfg {
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const TcP p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const __grid_constant__ TcP p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -93,7 +93,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);   // uniform register, see conv_halo.cu
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -428,6 +428,7 @@ int conv_tc_init() {
     g_init_status = do_init();
     if (std::getenv("HSIDM_NO_HALO")) tc::host().no_halo = 1;   // A/B switches for profiling runs
     if (std::getenv("HSIDM_NO_PAIRS")) tc::host().pairs_ok = 0;
+    if (const char* v = std::getenv("HSIDM_VARIANT")) tc::host().variant = std::atoi(v);   // hsidm_debug_conv_mode's variant bits
   });
   return g_init_status;
 }
@@ -475,7 +476,7 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: op (Cin %d+%d, Cout %d, k%d s%d, %dx%d) does not fit the tensor-core kernel",
                op.src[0].C, op.src[1].C, op.Cout, op.ksize, op.stride, op.Hin, op.Win);
   if (!host().no_halo && conv_halo_supported(op)) return conv_halo(op, stream);
-  if (op.rsrc[0].C || op.rsrc[1].C || op.up_parity >= 0 || op.gn_ab || op.s2)
+  if (op.rsrc[0].C || op.rsrc[1].C || op.up_parity >= 0 || op.gn.on() || op.s2)
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: fused shortcut sources / sub-pixel upsampling / fused input GroupNorm need the halo kernel, which does not take this shape");
   TcP p;
   tile_geometry(op.Hin, op.Win, &p.bw, &p.bh, &p.bn);

@@ -79,7 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __reduce_or_sync(0xffffffffu, *tmem_slot);   // uniform register, see conv_halo.cu
 
   if (warp == 0) {
     if (lane == 0) {

@@ -17,6 +17,22 @@ struct ConvSrc {
   const int64_t* img_off = nullptr;  // NCHW only: per-image element offset (device); null -> n*C*H*W
 };
 
+// GroupNorm over cat(src0, src1) as its CONSUMER evaluates it (no kernel between the producing convolution and the consumer):
+// either from the per-slot partial sums the producing convolutions left ([N][slots][C][2] = (sum, sumsq), folded in slot
+// order in float64 by the consumer's prologue), or from precomputed statistics [N][groups][2] = (mean, rstd).
+struct GnIn {
+  const float* part[2] = {nullptr, nullptr};   // per-slot partial sums of src0 / src1 (part[1] unused when C[1] == 0)
+  int slots[2] = {0, 0};
+  int C[2] = {0, 0};
+  const float* stats = nullptr;                // alternative to part[]: (mean, rstd) per image and group
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  int groups = 0;
+  float eps = 0.f;
+  int swish = 0;
+  bool on() const { return gamma && (stats || part[0]); }
+};
+
 // out = [clamp01]( act(conv(cat(src0,src1)) + bias + nbias[n]) * scale + resid )
 struct ConvOp {
   ConvSrc src[2];
@@ -52,11 +68,10 @@ struct ConvOp {
   float* stats_out = nullptr;
   int stats_slots = 0;
   // optional GroupNorm(+Swish) of the INPUT fused into the load path (halo tensor-core kernel only): src[] hold the
-  // un-normalised tensors and gn_ab the per-image per-channel affine [N][C0+C1][2] = (A, B) from gn_finalize, so that
-  // the conv sees act(x*A + B) with zero padding applied AFTER the activation, as in GroupNorm -> Swish -> Conv2d.
-  // The shortcut sources rsrc[] are never normalised.
-  const float* gn_ab = nullptr;
-  int gn_swish = 0;
+  // un-normalised tensors; the kernel derives the group statistics of the images it works on from gn (see GnIn) and
+  // applies act(x*A + B) to each halo tile in shared memory, zero padding AFTER the activation, as in
+  // GroupNorm -> Swish -> Conv2d.  The shortcut sources rsrc[] are never normalised.
+  GnIn gn;
   int K() const {
     if (up_parity >= 0) return 16 * (src[0].C + src[1].C);
     return ksize * ksize * (src[0].C + src[1].C) + rsrc[0].C + rsrc[1].C;
@@ -133,6 +148,11 @@ int gn_finalize(const float* part0, int slots0, int C0, const float* part1, int 
                 float* ab = nullptr);
 int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const float* stats,
              const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream);
+// The same with the statistics taken from `gn` (per-slot partial sums folded in each block's prologue, or gn.stats):
+// no statistics / finalize kernel in front.  gn.C[] are the channel counts of x0 / x1.
+int gn_apply_fused(const void* x0, const void* x1, int N, int HW, const GnIn& gn, void* out, int prec, cudaStream_t stream);
+// bf16 only: y [N][S][C] = GroupNorm(x) (no activation) and the same values transposed, yt [N][C][S] (attention block).
+int gn_apply_transposed(const void* x, int N, int S, const GnIn& gn, void* y, void* yt, cudaStream_t stream);
 
 int upsample2x(const void* x, void* out, int N, int H, int W, int C, int prec, cudaStream_t stream);
 

@@ -286,6 +286,44 @@ __global__ void pack_fused_kernel(const float* __restrict__ w2, const float* __r
 }
 }  // namespace
 
+namespace {
+// Attention weight folding (n_head = 1, unet.py:124-143).  With Xn the normalised input [S][C]:
+//   scores = (Xn Wq^T)(Xn Wk^T)^T = (Xn Mqk^T) Xn^T,  Mqk = Wk^T Wq          -> one C x C projection instead of q and k
+//   out    = Wout (P (Xn Wv^T))^T + b = Wov (P Xn)^T + b,  Wov = Wout Wv     -> no v projection at all
+// which: 0 -> o[co][ci] = sum_r a[r][co] * b[r][ci]  (a = Wk, b = Wq);  1 -> o[co][ci] = sum_r a[co][r] * b[r][ci]  (a = Wout, b = Wv)
+__global__ void fold_attn_kernel(const float* __restrict__ a, const float* __restrict__ b, int C, int which, bf16* __restrict__ o) {
+  const int co = blockIdx.x, ci = threadIdx.x + blockIdx.y * blockDim.x;
+  if (ci >= C) return;
+  float acc = 0.f;
+  for (int r = 0; r < C; ++r) acc = fmaf(which == 0 ? a[(int64_t)r * C + co] : a[(int64_t)co * C + r], b[(int64_t)r * C + ci], acc);
+  o[(int64_t)co * C + ci] = __float2bfloat16_rn(acc);
+}
+}  // namespace
+
+void free_attn_fold(AttnFoldW& f) {
+  if (f.w_qk) cudaFree(f.w_qk);
+  if (f.w_ov) cudaFree(f.w_ov);
+  f.w_qk = nullptr, f.w_ov = nullptr, f.bytes = 0;
+}
+
+int pack_attn_fold(const ParamStore& ps, const ConvW& qkv, const ConvW& aout, AttnFoldW& f) {
+  free_attn_fold(f);
+  const int C = aout.Cout;
+  const int bn = conv_tc_bn_rows(C);
+  if (bn <= 0 || C % 64 || qkv.Cout != 3 * C || qkv.Cin != C || aout.Cin != C) return HSIDM_OK;   // not a tensor-core shape: stay unfolded
+  const int64_t rows = round_up(C, bn);
+  HSIDM_CUDA(cudaMalloc(&f.w_qk, sizeof(bf16) * rows * C));
+  HSIDM_CUDA(cudaMalloc(&f.w_ov, sizeof(bf16) * rows * C));
+  HSIDM_CUDA(cudaMemset(f.w_qk, 0, sizeof(bf16) * rows * C));
+  HSIDM_CUDA(cudaMemset(f.w_ov, 0, sizeof(bf16) * rows * C));
+  f.C = C, f.bytes = 2 * (int64_t)sizeof(bf16) * rows * C;
+  const float* w = ps.dev(qkv.pw);   // [3C][C]: q rows, k rows, v rows
+  const dim3 grid(C, (unsigned)ceil_div(C, 256));
+  fold_attn_kernel<<<grid, 256>>>(w + (int64_t)C * C, w, C, 0, f.w_qk);
+  fold_attn_kernel<<<grid, 256>>>(ps.dev(aout.pw), w + 2LL * C * C, C, 1, f.w_ov);
+  return after_launch("fold_attn_kernel");
+}
+
 void free_fused(FusedW& f) {
   if (f.w) cudaFree(f.w);
   if (f.bias) cudaFree(f.bias);
@@ -372,7 +410,7 @@ void run_conv(Exec& ex, ConvOp op, const ConvW& w, const ParamStore& ps) {
   const int prec = ex.prec;
   ConvOp g;
   const Route route = plan_conv(ex, op, w, &g);
-  if (op.gn_ab && route != R_TC) {   // only the halo tensor-core kernel normalises its input on the fly
+  if (op.gn.on() && route != R_TC) {   // only the halo tensor-core kernel normalises its input on the fly
     if (ex.status == HSIDM_OK) {
       set_last_error("run_conv: fused input GroupNorm requested for an op the halo kernel does not take");
       ex.status = HSIDM_UNSUPPORTED_CFG;

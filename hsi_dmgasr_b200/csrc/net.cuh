@@ -69,6 +69,16 @@ struct FusedW {
 int pack_fused(const ParamStore& ps, const ConvW& c2, const ConvW* rc, FusedW& f);
 void free_fused(FusedW& f);
 
+// SelfAttention with its projections folded (BF16 mode, n_head = 1): see pack_attn_fold in net.cu.
+struct AttnFoldW {
+  bf16* w_qk = nullptr;   // [rows >= C][C] = Wk^T Wq : scores = (Xn w_qk^T) Xn^T
+  bf16* w_ov = nullptr;   // [rows >= C][C] = Wout Wv : out = (P Xn) w_ov^T + b_out
+  int C = 0;
+  int64_t bytes = 0;
+};
+int pack_attn_fold(const ParamStore& ps, const ConvW& qkv, const ConvW& aout, AttnFoldW& f);
+void free_attn_fold(AttnFoldW& f);
+
 // Registers "<prefix>.weight" / "<prefix>.bias" and returns the ConvW.
 ConvW make_conv(ParamStore& ps, const std::string& prefix, int Cin, int Cout, int ks, bool bias = true);
 // (Re)packs w_f32 always and w_bf16 when `bf16_too`. Idempotent; frees previous packs.

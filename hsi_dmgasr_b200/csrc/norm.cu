@@ -9,13 +9,14 @@
 //   gn_apply : read x once, write y once   -> y = swish?(x * A[n,c] + B[n,c])
 #include <algorithm>
 
-#include "kernels.cuh"
+#include "gn_fold.cuh"
 
 namespace hsidm {
 namespace {
 
 constexpr int kMaxThreads = 256;
 constexpr int kUnroll = 4;
+constexpr int kMaxGroups = 128;   // groups a block can fold itself (gn_apply_fused)
 
 // Swish.  fp32 mode keeps the exact x*sigmoid(x); bf16 mode uses the single-MUFU identity sigmoid(y) = 0.5 + 0.5*tanh(y/2)
 // (tanh.approx error ~2^-11, far below the bf16 rounding of the result) so the pass stays HBM-bound, not MUFU-bound.
@@ -143,7 +144,8 @@ template <typename AT>
 __global__ void __launch_bounds__(kMaxThreads, 4)
 gn_apply_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, int C1, int HW, int groups, int CV,
                 int lanes, int pix_per_block, const float* __restrict__ stats, const float* __restrict__ gamma,
-                const float* __restrict__ beta, int swish, AT* __restrict__ out) {
+                const float* __restrict__ beta, int swish, AT* __restrict__ out, const GnFoldP fold, float eps_unused) {
+  __shared__ float2 gs[kMaxGroups];   // (mean, rstd) per group when the block folds the statistics itself
   griddep_wait();
   griddep_launch();
   const int C = C0 + C1;
@@ -163,11 +165,17 @@ gn_apply_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, in
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) v[u].load(src_ptr<AT>(x0, C0, x1, C1, img + pix + u * lanes, c));
   }
+  if (fold.part0) {   // statistics from the producers' per-slot partial sums: no statistics / finalize kernel ran
+    for (int g = tid; g < groups; g += blockDim.x) gs[g] = gn_fold_group(fold, n, g);
+    __syncthreads();
+  }
   float A[8], B[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int g = (c + j) / cpg;
-    const float mean = stats[((int64_t)n * groups + g) * 2], rstd = stats[((int64_t)n * groups + g) * 2 + 1];
+    float mean, rstd;
+    if (fold.part0) mean = gs[g].x, rstd = gs[g].y;
+    else mean = stats[((int64_t)n * groups + g) * 2], rstd = stats[((int64_t)n * groups + g) * 2 + 1];
     A[j] = rstd * __ldg(gamma + c + j);
     B[j] = __ldg(beta + c + j) - mean * A[j];
   }
@@ -206,7 +214,93 @@ gn_apply_kernel(const AT* __restrict__ x0, int C0, const AT* __restrict__ x1, in
   }
 }
 
+// GroupNorm-apply for the attention block (bf16): y = x*A[n,c] + B[n,c] written twice - as [N][S][C] (the tensor the
+// projections read) and transposed as [N][C][S] (keys contiguous: the K-major B operand of P.X).  One block = 64 pixels
+// x 64 channels of one image: 128-byte rows in, 128-byte rows out in both layouts, transposed through shared memory.
+__global__ void __launch_bounds__(256)
+gn_apply_t_kernel(const bf16* __restrict__ x, int S, int C, const GnFoldP fold, const float* __restrict__ stats, int groups,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ y, bf16* __restrict__ yt) {
+  __shared__ bf16 tile[64][66];   // [channel][pixel], padded: both access patterns conflict-free enough
+  __shared__ float2 gs[64];       // (mean, rstd) of the groups this block's 64 channels belong to
+  griddep_wait();
+  griddep_launch();
+  const int n = blockIdx.z, p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tid = threadIdx.x;
+  const int j8 = tid & 7;          // 16-byte chunk (8 channels) of a pixel's 64-channel row
+  const int cpg = C / groups, g_lo = c0 / cpg, g_n = (c0 + 63) / cpg - g_lo + 1;
+  if (tid < g_n) {
+    const int g = g_lo + tid;
+    gs[tid] = fold.part0 ? gn_fold_group(fold, n, g) : make_float2(stats[((int64_t)n * groups + g) * 2], stats[((int64_t)n * groups + g) * 2 + 1]);
+  }
+  __syncthreads();
+  float A[8], B[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j8 * 8 + j;
+    const float2 st = gs[c / cpg - g_lo];
+    A[j] = st.y * __ldg(gamma + c);
+    B[j] = __ldg(beta + c) - st.x * A[j];
+  }
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int px = (tid >> 3) + 32 * it;
+    const int64_t off = ((int64_t)n * S + p0 + px) * C + c0 + j8 * 8;
+    float f[8];
+    load8(x + off, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], A[j], B[j]);
+    store8(y + off, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tile[j8 * 8 + j][px] = __float2bfloat16_rn(f[j]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int ch = (tid >> 3) + 32 * it;
+    uint4 o;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __halves2bfloat162(tile[ch][j8 * 8 + 2 * j], tile[ch][j8 * 8 + 2 * j + 1]);
+    *reinterpret_cast<uint4*>(yt + ((int64_t)n * C + c0 + ch) * S + p0 + j8 * 8) = o;
+  }
+}
+
 }  // namespace
+
+static int gn_apply_impl(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const float* stats,
+                         const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream, const GnFoldP& f);
+
+// Fills the device-side fold descriptor; fails when the block-local fold cannot take this GroupNorm.
+static int make_fold(const GnIn& gn, int HW, GnFoldP* f) {
+  const int Ct = gn.C[0] + gn.C[1];
+  if (gn.groups <= 0 || Ct % gn.groups) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "GroupNorm: %d channels not divisible by %d groups", Ct, gn.groups);
+  *f = GnFoldP{nullptr, nullptr, 0, 0, gn.C[0], gn.C[1], Ct / gn.groups, (float)(1.0 / ((double)(Ct / gn.groups) * HW)), gn.eps};
+  if (gn.stats) return HSIDM_OK;
+  if (!gn.part[0] || (gn.C[1] && !gn.part[1]) || (f->cpg & 1) || gn.C[0] % 2)
+    HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "GroupNorm from partial sums needs both sources' slots and an even number of channels per group");
+  f->part0 = gn.part[0], f->part1 = gn.part[1], f->slots0 = gn.slots[0], f->slots1 = gn.slots[1];
+  return HSIDM_OK;
+}
+
+int gn_apply_transposed(const void* x, int N, int S, const GnIn& gn, void* y, void* yt, cudaStream_t stream) {
+  const int C = gn.C[0];
+  if (S % 64 || C % 64 || gn.C[1]) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "gn_apply_transposed: S=%d and C=%d must be multiples of 64 (one source)", S, C);
+  GnFoldP f;
+  HSIDM_TRY(make_fold(gn, S, &f));
+  char tag[64];
+  snprintf(tag, sizeof(tag), "apply+T c%d hw%d n%d", C, S, N);
+  ProfScope prof(PROF_GN_APPLY, 3.0 * N * S * C * 2, stream, tag);
+  HSIDM_CUDA(launch_pdl(gn_apply_t_kernel, dim3(S / 64, C / 64, N), dim3(256), 0, stream, 1, (const bf16*)x, S, C, f, gn.stats, gn.groups,
+                        gn.gamma, gn.beta, (bf16*)y, (bf16*)yt));
+  return after_launch("gn_apply_t_kernel");
+}
+
+int gn_apply_fused(const void* x0, const void* x1, int N, int HW, const GnIn& gn, void* out, int prec, cudaStream_t stream) {
+  GnFoldP f;
+  HSIDM_TRY(make_fold(gn, HW, &f));
+  if (!gn.stats && gn.groups > kMaxGroups) HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "gn_apply_fused: more than %d groups", kMaxGroups);
+  return gn_apply_impl(x0, gn.C[0], x1, gn.C[1], N, HW, gn.groups, gn.stats, gn.gamma, gn.beta, gn.swish, out, prec, stream, f);
+}
 
 int gn_geometry(int C0, int C1, int N, int HW, GnGeo* g) {
   const int C = C0 + C1;
@@ -355,6 +449,11 @@ int gn_finalize(const float* part0, int slots0, int C0, const float* part1, int 
 
 int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const float* stats,
              const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream) {
+  return gn_apply_impl(x0, C0, x1, C1, N, HW, groups, stats, gamma, beta, swish, out, prec, stream, GnFoldP{});
+}
+
+static int gn_apply_impl(const void* x0, int C0, const void* x1, int C1, int N, int HW, int groups, const float* stats,
+                         const float* gamma, const float* beta, int swish, void* out, int prec, cudaStream_t stream, const GnFoldP& f) {
   GnGeo g0, g;
   HSIDM_TRY(gn_geometry(C0, C1, N, HW, &g0));
   apply_geometry(g0, N, HW, &g);
@@ -364,10 +463,10 @@ int gn_apply(const void* x0, int C0, const void* x1, int C1, int N, int HW, int 
   ProfScope prof(PROF_GN_APPLY, 2.0 * N * HW * (C0 + C1) * (prec == HSIDM_BF16 ? 2 : 4), stream, tag);
   if (prec == HSIDM_BF16)
     HSIDM_CUDA(launch_pdl(gn_apply_kernel<bf16>, grid, dim3(g.threads), 0, stream, 1, (const bf16*)x0, C0, (const bf16*)x1, C1, HW, groups,
-                          g.CV, g.lanes, g.pix_per_block, stats, gamma, beta, swish, (bf16*)out));
+                          g.CV, g.lanes, g.pix_per_block, stats, gamma, beta, swish, (bf16*)out, f, 0.f));
   else
     HSIDM_CUDA(launch_pdl(gn_apply_kernel<float>, grid, dim3(g.threads), 0, stream, 1, (const float*)x0, C0, (const float*)x1, C1, HW,
-                          groups, g.CV, g.lanes, g.pix_per_block, stats, gamma, beta, swish, (float*)out));
+                          groups, g.CV, g.lanes, g.pix_per_block, stats, gamma, beta, swish, (float*)out, f, 0.f));
   return after_launch("gn_apply_kernel");
 }
 

@@ -486,6 +486,10 @@ static __device__ __forceinline__ void stats_store(const EpiP& p, int n, int slo
         make_float4(st.x, st.z, st.y, st.w);   // (sum, sumsq) of channel 2*lane, then of channel 2*lane+1
 }
 
+static __device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // ---- host side shared state ----------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

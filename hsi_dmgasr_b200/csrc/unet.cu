@@ -133,16 +133,38 @@ struct NoiseRef {
   int64_t t_stride;
 };
 
+// GroupNorm(weight gw, bias gb) over cat(x, skip) described for a consumer that evaluates the statistics itself from the
+// per-slot partial sums the producers left (no kernel in between).  False when a tensor carries no partial sums or the
+// grouping does not fit the consumers' fold (odd channels per group): the caller then computes statistics first.
+bool gn_from_slots(hsidm_ctx* c, const Act& x, const Act* skip, int gw, int gb, bool swish, GnIn* gn) {
+  const int C1 = skip ? skip->C : 0, groups = c->cfg.norm_groups, Ct = x.C + C1;
+  *gn = GnIn();
+  gn->C[0] = x.C, gn->C[1] = C1, gn->groups = groups, gn->eps = kGnEps, gn->swish = swish ? 1 : 0;
+  gn->gamma = c->ps.dev(gw), gn->beta = c->ps.dev(gb);
+  if ((conv_tc_variant() & 256) || !x.stats || (skip && !skip->stats) || x.C % 64 || C1 % 64 || Ct % groups || ((Ct / groups) & 1) || groups > 128)
+    return false;
+  gn->part[0] = x.stats, gn->slots[0] = x.slots;
+  if (skip) gn->part[1] = skip->stats, gn->slots[1] = skip->slots;
+  return true;
+}
+
 // GroupNorm(+Swish) over cat(a, b) -> new tensor with a.C + b.C channels.  Statistics come from the partial sums the
-// producing convolutions left behind when both inputs carry them; otherwise from a pass over the tensors.
+// producing convolutions left behind when both inputs carry them (folded inside the apply kernel); otherwise from a
+// finalize launch or a pass over the tensors.
 Act gn_act(hsidm_ctx* c, const Act& a, const Act* b, int gw, int gb, bool swish) {
   Exec& ex = c->ex;
   const int C1 = b ? b->C : 0;
   const int groups = c->cfg.norm_groups;
   const int HW = a.H * a.W;
+  const void* p1 = b ? b->p : nullptr;
+  GnIn gn;
+  if (gn_from_slots(c, a, b, gw, gb, swish, &gn)) {
+    Act out = ex.alloc_act(a.N, a.H, a.W, a.C + C1);
+    ex.run([&] { return gn_apply_fused(a.p, p1, a.N, HW, gn, out.p, ex.prec, ex.stream); });
+    return out;
+  }
   float* stats = static_cast<float*>(ex.alloc_raw(sizeof(float) * 2 * a.N * groups));
   Act out = ex.alloc_act(a.N, a.H, a.W, a.C + C1);
-  const void* p1 = b ? b->p : nullptr;
   const bool fused = a.stats && (!b || b->stats) && a.C % 64 == 0 && C1 % 64 == 0;
   if (fused) {
     const float* s1 = b ? b->stats : nullptr;
@@ -185,7 +207,66 @@ Act conv_out(hsidm_ctx* c, const ConvW& w, int N, int Hin, int Win, int C0, int 
   return alloc_conv_out(c->ex, proto, w, c->ps);
 }
 
-// SelfAttention.forward (unet.py:124-143), n_head = 1, on tensor cores (BF16 mode).  Every contraction is a K-major
+// SelfAttention.forward (unet.py:124-143), n_head = 1, with the projections folded at commit (pack_attn_fold):
+//   Xn = GroupNorm(x) written as [S][C] and as [C][S];  T = Xn Mqk^T;  P = softmax(T Xn^T / sqrt(C));  Y = P Xn;
+//   out = Y Wov^T + b_out + x.     5 launches, 0.40 GFLOP per image instead of 0.67 (no q/k/v tensors).
+// Needs the GroupNorm affine of x (from the producer's tail, or from gn_finalize when x carries slot statistics).
+bool attention_folded(hsidm_ctx* c, const ResW& r, const Act& x, Act& out) {
+  Exec& ex = c->ex;
+  const int C = x.C, S = x.H * x.W, N = x.N;
+  static const bool off = std::getenv("HSIDM_NO_ATTNFOLD") != nullptr;   // A/B switch
+  if (off || (conv_tc_variant() & 512) || ex.prec != HSIDM_BF16 || !r.afold.w_qk || C % 64 || S % 64) return false;
+  if (!(S == 64 || S == 128 || S == 256)) return false;   // the softmax runs in the scores GEMM's epilogue (one tile per row)
+  ConvW wqk, wov;
+  wqk.Cin = C, wqk.Cout = C, wqk.ks = 1, wqk.w_bf16 = r.afold.w_qk;
+  wov = r.aout, wov.w_bf16 = r.afold.w_ov, wov.w_f32 = nullptr;
+  {
+    ConvOp t;
+    t.src[0].C = C, t.N = N, t.Hin = t.Hout = x.H, t.Win = t.Wout = x.W, t.ksize = 1, t.Cout = C, t.w_bf16 = wqk.w_bf16;
+    if (!conv_tc_supported(t, ex.prec)) return false;
+    GemmTcOp probe;
+    probe.M = S, probe.N = S, probe.K = C, probe.lda = C, probe.ldb = C, probe.ldc = S, probe.row_softmax = 1, probe.alpha = 1.f;
+    probe.sA = probe.sB = (int64_t)S * C, probe.sC = (int64_t)S * S;
+    if (!gemm_tc_supported(probe)) return false;
+  }
+  GnIn gn;
+  float* stats = nullptr;
+  if (!gn_from_slots(c, x, nullptr, r.an_w, r.an_b, false, &gn)) {
+    if (!x.stats) return false;
+    stats = static_cast<float*>(ex.alloc_raw(sizeof(float) * 2 * N * gn.groups));
+    ex.run([&] { return gn_finalize(x.stats, x.slots, C, nullptr, 0, 0, N, S, gn.groups, kGnEps, stats, ex.stream); });
+    gn.stats = stats;
+  }
+  Act nrm = ex.alloc_act(N, x.H, x.W, C);
+  bf16* xt = static_cast<bf16*>(ex.alloc_raw(sizeof(bf16) * (int64_t)N * C * S));   // [N][C][S]
+  ex.run([&] { return gn_apply_transposed(x.p, N, S, gn, nrm.p, xt, ex.stream); });
+  if (stats) ex.release_raw(stats);
+  Act t = ex.alloc_act(N, x.H, x.W, C);
+  run_conv(ex, conv_op_nhwc(nrm, nullptr, t), wqk, c->ps);
+  bf16* prob = static_cast<bf16*>(ex.alloc_raw(sizeof(bf16) * (int64_t)N * S * S));
+  GemmTcOp sc;
+  sc.A = t.p, sc.B = nrm.p, sc.C = prob, sc.M = S, sc.N = S, sc.K = C, sc.batch = N;
+  sc.lda = sc.ldb = C, sc.sA = sc.sB = (int64_t)S * C, sc.ldc = S, sc.sC = (int64_t)S * S;
+  sc.alpha = 1.0f / std::sqrt((float)C), sc.c_f32 = 0, sc.row_softmax = 1;
+  ex.run([&] { return gemm_tc(sc, ex.stream); });
+  ex.release(t);
+  ex.release(nrm);
+  Act y = ex.alloc_act(N, x.H, x.W, C);
+  GemmTcOp pv;
+  pv.A = prob, pv.B = xt, pv.C = y.p, pv.M = S, pv.N = C, pv.K = S, pv.batch = N;
+  pv.lda = S, pv.sA = (int64_t)S * S, pv.ldb = S, pv.sB = (int64_t)C * S, pv.ldc = C, pv.sC = (int64_t)S * C, pv.c_f32 = 0;
+  ex.run([&] { return gemm_tc(pv, ex.stream); });
+  ex.release_raw(prob);
+  ex.release_raw(xt);
+  ConvOp op = conv_op_nhwc(y, nullptr, out);
+  op.resid = x.p;
+  run_conv(ex, op, wov, c->ps);
+  ex.release(y);
+  return true;
+}
+
+// The same with q, k, v materialised (A/B reference for the folded form; shapes whose rows do not fit one softmax tile).
+// Every contraction is a K-major
 // "NT" GEMM: the V projection is computed transposed (V^T = W_v X^T) so that O = P V contracts over contiguous keys.
 bool attention_tc(hsidm_ctx* c, const ResW& r, const Act& x, Act& out) {
   Exec& ex = c->ex;
@@ -251,6 +332,7 @@ bool attention_tc(hsidm_ctx* c, const ResW& r, const Act& x, Act& out) {
 // Same on CUDA cores (F32 mode, or shapes the tensor-core GEMM does not take).  Writes into `out`.
 void attention(hsidm_ctx* c, const ResW& r, const Act& x, Act& out) {
   Exec& ex = c->ex;
+  if (attention_folded(c, r, x, out)) return;
   if (attention_tc(c, r, x, out)) return;
   const int C = x.C, S = x.H * x.W;
   Act nrm = gn_act(c, x, nullptr, r.an_w, r.an_b, false);
@@ -291,13 +373,13 @@ void gn_conv(hsidm_ctx* c, const Act& x, const Act* skip, int gw, int gb, bool s
   Exec& ex = c->ex;
   const int C1 = skip ? skip->C : 0;
   static const bool no_fuse = std::getenv("HSIDM_NO_GNFUSE") != nullptr;   // A/B switch for profiling runs
-  bool fuse = !no_fuse && !(conv_tc_variant() & 8) && ex.prec == HSIDM_BF16 && x.stats && (!skip || skip->stats) && x.C % 64 == 0 && C1 % 64 == 0;
+  bool fuse = !no_fuse && !(conv_tc_variant() & 8) && ex.prec == HSIDM_BF16 && x.C % 64 == 0 && C1 % 64 == 0;
   if (fuse) {
     ConvOp probe = conv_op_nhwc(x, skip, out);
     fill(probe);
     probe.w_bf16 = w.w_bf16, probe.Cout = w.Cout, probe.ksize = w.ks;
     static const float kDummy = 0.f;
-    probe.gn_ab = &kDummy;
+    probe.gn.gamma = &kDummy, probe.gn.stats = &kDummy;
     fuse = probe.w_bf16 && conv_tc_supported(probe, ex.prec) && conv_halo_ok(probe);
   }
   if (!fuse) {
@@ -308,21 +390,30 @@ void gn_conv(hsidm_ctx* c, const Act& x, const Act* skip, int gw, int gb, bool s
     ex.release(a);
     return;
   }
-  const int groups = c->cfg.norm_groups, C = x.C + C1;
-  float* stats = static_cast<float*>(ex.alloc_raw(sizeof(float) * 2 * x.N * groups));
-  float* ab = static_cast<float*>(ex.alloc_raw(sizeof(float) * 2 * (int64_t)x.N * C));
-  const float* s1 = skip ? skip->stats : nullptr;
-  const int sl1 = skip ? skip->slots : 0;
-  ex.run([&] {
-    return gn_finalize(x.stats, x.slots, x.C, s1, sl1, C1, x.N, x.H * x.W, groups, kGnEps, stats, ex.stream, c->ps.dev(gw),
-                       c->ps.dev(gb), ab);
-  });
+  // Statistics: folded by the conv's own transform warps from the producers' partial sums; where those are missing (or
+  // variant 256 asks for it) from a gn_finalize launch / a statistics pass over the tensors - the conv then reads (mean, rstd).
+  GnIn gn;
+  float* stats = nullptr;
+  if (!gn_from_slots(c, x, skip, gw, gb, swish, &gn)) {
+    const int groups = gn.groups;
+    stats = static_cast<float*>(ex.alloc_raw(sizeof(float) * 2 * x.N * groups));
+    if (x.stats && (!skip || skip->stats)) {
+      const float* s1 = skip ? skip->stats : nullptr;
+      const int sl1 = skip ? skip->slots : 0;
+      ex.run([&] { return gn_finalize(x.stats, x.slots, x.C, s1, sl1, C1, x.N, x.H * x.W, groups, kGnEps, stats, ex.stream); });
+    } else {
+      void* scratch = ex.alloc_raw(gn_scratch_bytes(x.C, C1, x.N, x.H * x.W, groups));
+      const void* p1 = skip ? skip->p : nullptr;
+      ex.run([&] { return gn_stats(x.p, x.C, p1, C1, x.N, x.H * x.W, groups, kGnEps, scratch, ex.tickets, stats, ex.prec, ex.stream); });
+      ex.release_raw(scratch);
+    }
+    gn.stats = stats;
+  }
   ConvOp op = conv_op_nhwc(x, skip, out);
   fill(op);
-  op.gn_ab = ab, op.gn_swish = swish ? 1 : 0;
+  op.gn = gn;
   run_conv(ex, op, w, c->ps);
-  ex.release_raw(ab);
-  ex.release_raw(stats);
+  if (stats) ex.release_raw(stats);
 }
 
 // ResnetBlocWithAttn.forward (unet.py:105-111, 155-159) on cat(x, skip), written into `out`.  Inputs are not released.
@@ -664,7 +755,7 @@ int hsidm_ctx_destroy(hsidm_ctx* c) {
   for_each_conv(c, [](ConvW& w) { free_conv(w); });
   for (auto* v : {&c->downs, &c->mid, &c->ups})
     for (auto& L : *v)
-      if (L.kind == LayerW::RES) free_fused(L.rb.fused);
+      if (L.kind == LayerW::RES) free_fused(L.rb.fused), free_attn_fold(L.rb.afold);
   if (c->noise_layers_dev) cudaFree(c->noise_layers_dev);
   if (c->coef_dev) cudaFree(c->coef_dev);
   if (c->levels_dev) cudaFree(c->levels_dev);
@@ -730,6 +821,10 @@ int hsidm_unet_commit(hsidm_ctx* c) {
         if (L.kind == LayerW::RES && status == HSIDM_OK) {
           status = pack_fused(c->ps, L.rb.c2, L.rb.has_res ? &L.rb.rc : nullptr, L.rb.fused);
           c->packed_bytes += L.rb.fused.bytes;
+          if (status == HSIDM_OK && L.rb.attn) {
+            status = pack_attn_fold(c->ps, L.rb.qkv, L.rb.aout, L.rb.afold);
+            c->packed_bytes += L.rb.afold.bytes;
+          }
         }
     };
     fuse(c->downs), fuse(c->mid), fuse(c->ups);

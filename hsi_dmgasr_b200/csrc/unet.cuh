@@ -16,6 +16,7 @@ struct ResW {
   FusedW fused;   // conv2 + shortcut as one tensor-core GEMM (BF16 mode)
   int an_w = -1, an_b = -1;
   ConvW qkv, aout;
+  AttnFoldW afold;   // folded projections (BF16 mode)
 };
 
 struct LayerW {

@@ -11,6 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from hsi_dmgasr_b200 import _lib
+if os.environ.get("HSIDM_AB_LIB"):   # A/B against another build of the library (developer runs only)
+    _lib.LIB_PATH = os.environ["HSIDM_AB_LIB"]
 from tests.gpu_util import conv2d, randn, tc_flag
 
 ap = argparse.ArgumentParser()

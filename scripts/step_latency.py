@@ -3,14 +3,16 @@ N in {1, 5, 11, 176} latent images of 128x128; median of 50 replays after warm-u
 import json, os, statistics, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from hsi_dmgasr_b200 import GaussianDiffusion, UNet, synth
+from hsi_dmgasr_b200 import GaussianDiffusion, UNet, synth, _lib
+if os.environ.get("HSIDM_AB_LIB"):   # A/B against another build of the library (developer runs only)
+    _lib.LIB_PATH = os.environ["HSIDM_AB_LIB"]
 from hsi_dmgasr_b200.spec import UNetConfig
 
 FULL = UNetConfig(in_channel=6, out_channel=3, inner_channel=64, norm_groups=32, channel_mults=(1, 2, 4, 8, 8),
                   attn_res=(16,), res_blocks=2, dropout=0.2, image_size=128)
 dev = torch.device("cuda:0")
 T = 64   # one sampling pass = T graph replays; per-step time = pass time / T, median over passes
-for n in (1, 5, 11, 176):
+for n in [int(v) for v in os.environ.get("STEP_LAT_N", "1,5,11,176").split(",")]:
     net = UNet(in_channel=6, out_channel=3, inner_channel=64, norm_groups=32, channel_mults=(1, 2, 4, 8, 8), attn_res=[16],
                res_blocks=2, dropout=0.2, image_size=128, precision="bf16")
     net.load_state_dict(synth.unet_state_dict(FULL, 0))

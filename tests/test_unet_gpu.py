@@ -133,6 +133,66 @@ def test_fused_input_groupnorm_matches_normalised_copy(tag, hw, n):
         assert err < 1.5e-2, f"{what}: rel-L2 {err:.3e}"
 
 
+@pytest.mark.parametrize("tag,hw,n", [("full32", 128, 2), ("full32", 64, 5), ("full32", 128, 12), ("small", 32, 3)])
+def test_groupnorm_folded_by_consumers_matches_finalize_launches(tag, hw, n):
+    """bf16 mode: every consumer of a GroupNorm (the halo convolution's transform warps, the stand-alone apply kernels)
+    folds the statistics of the images it works on from the partial sums its producers' epilogues left, so no kernel
+    runs between producer and consumer.  Variant 256 restores the gn_finalize launches: same slots, folded in a
+    different (fixed) order, so the outputs agree to the bf16 noise floor; the path itself is bitwise repeatable."""
+    from hsi_dmgasr_b200 import _lib
+    lib = _lib.load()
+    cfg, seed, *_ = UNET_CASES[tag]
+    x = torch.from_numpy(np.random.default_rng(78).standard_normal((n, 6, hw, hw), dtype=np.float32)).cuda()
+    lv = torch.linspace(0.2, 0.9, n).view(n, 1).cuda()
+    outs = {}
+    try:
+        for variant in (256, 0):
+            lib.hsidm_debug_conv_mode(0, variant)
+            net = build(cfg, seed, "bf16")
+            with torch.no_grad():
+                outs[variant] = net(x, lv).clone()
+                if variant == 0:
+                    again = net(x, lv).clone()
+            del net
+    finally:
+        lib.hsidm_debug_conv_mode(0, 0)
+    assert tc_flag() == 0
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(again, outs[0])
+    err = rel_l2(outs[0], outs[256])
+    print(f"consumer-side fold vs finalize launches: rel-L2 {err:.3e}")
+    assert err < 1e-2, f"rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("hw,n", [(128, 2), (64, 3)])
+def test_folded_attention_matches_materialised_qkv(hw, n):
+    """bf16 mode folds the attention projections at commit (scores = (Xn Wk^T Wq) Xn^T, out = (P Xn)(Wout Wv)^T + b: no q, k, v
+    tensors).  Variant 512 materialises q, k, v as the reference does (unet.py:131-142); same mathematics, different
+    bf16 rounding points: both must sit at the same distance from the fp32 path."""
+    from hsi_dmgasr_b200 import _lib
+    lib = _lib.load()
+    cfg, seed, *_ = UNET_CASES["full32"]
+    x = torch.from_numpy(np.random.default_rng(79).standard_normal((n, 6, hw, hw), dtype=np.float32)).cuda()
+    lv = torch.linspace(0.3, 0.8, n).view(n, 1).cuda()
+    outs = {}
+    try:
+        for variant in (512, 0):
+            lib.hsidm_debug_conv_mode(0, variant)
+            net = build(cfg, seed, "bf16")
+            with torch.no_grad():
+                outs[variant] = net(x, lv).clone()
+            del net
+    finally:
+        lib.hsidm_debug_conv_mode(0, 0)
+    assert tc_flag() == 0
+    ref = build(cfg, seed, "fp32")
+    with torch.no_grad():
+        want = ref(x, lv)
+    e_fold, e_mat = rel_l2(outs[0], want), rel_l2(outs[512], want)
+    print(f"vs fp32: folded {e_fold:.3e}, materialised {e_mat:.3e}; folded vs materialised {rel_l2(outs[0], outs[512]):.3e}")
+    assert e_fold < TOL["bf16"] and e_fold < 1.5 * e_mat + 1e-3
+
+
 def test_c4_shape_512_bf16_tracks_fp32():
     """BASELINE config C4: the 64_512 UNet (mults 1-2-4-8-16, one res block, 16 groups, mid attention at 32x32 = 1024
     tokens) on a 512x512 latent.  The CPU oracle needs minutes at this size, so the check is internal: the tensor-core
