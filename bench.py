@@ -474,6 +474,9 @@ def main() -> None:
         # warm-up: W steps on this rank's first batch (builds workspaces, packs weights, captures the step graph)
         gd.set_new_noise_schedule(dict(SCHED, n_timestep=W), dev)
         pipe.super_resolve(tiles_host[lo:min(hi, lo + B)].to(dev), seed=1, first_cube=lo)
+        if world > 1:   # ... and one small gather: NCCL sets up its point-to-point channels on first use
+            from hsi_dmgasr_b200.pipeline import gather_rows
+            gather_rows(torch.zeros((1, 8), device=dev), world, rank, world, dist)
         gd.set_new_noise_schedule(dict(SCHED, n_timestep=K), dev)
         # sampling-only time of this rank (for the K < T extrapolation): CUDA events around every sampling call
         samp_events = []

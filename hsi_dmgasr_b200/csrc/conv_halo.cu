@@ -28,6 +28,7 @@
 //
 // PAIR = true runs the same pipeline on a cluster of two CTAs (cta_group::2): adjacent pixel tiles, one channel tile,
 // the weight rows split between the CTAs, MMAs (M = 256) issued by the leader and completed on both CTAs' barriers.
+#include <cmath>
 #include <cstdlib>
 
 #include "gn_fold.cuh"
@@ -700,19 +701,47 @@ void pick_shape(const ConvOp& op, int* MT, int* BN, bool* pair) {
   auto even_tiles = [&](int mt) { return (((op.Hin / kRows) * (op.Win / (8 * mt))) & 1) == 0; };
   const bool pair_ok = op.ksize == 3 && !op.s2 && host().pairs_ok;
   if (op.s2 && (op.ksize != 3 || op.src[1].C || op.rsrc[0].C || op.up_parity >= 0 || op.gn.on())) return;
-  if (op.Cout % 256 == 0 && op.Win % 8 == 0 && pair_ok && !(var & 32) && even_tiles(1)) {
-    *MT = 1, *BN = 256, *pair = true;   // N = 256 is the only shape whose MMAs run at the tensor pipe's full rate
-  } else if (op.Cout % 128 == 0 && op.Win % 16 == 0) {
-    *MT = 2, *BN = 128, *pair = pair_ok && !(var & 64) && even_tiles(2);
-  } else if (op.Cout % 64 == 0 && op.Win % 32 == 0 && !(var & 16)) {
-    *MT = 4, *BN = 64, *pair = pair_ok && !(var & 128) && even_tiles(4);
-  } else if (op.Cout % 64 == 0 && op.Win % 16 == 0) {
-    // narrow tile with three halo stages: also the test knob (variant bit 16) for the 32-multiple widths, where it
-    // measured 10-30 % slower than <4,64> (half the weight-tile reuse, twice the per-tile overhead)
-    *MT = 2, *BN = 64;
-  } else if (op.Cout <= 16 && op.Win % 32 == 0 && op.ksize == 3 && !op.s2) {
-    *MT = 4, *BN = 16;
+  // Candidates in the order of preference at full batch:
+  //   <1,256> on CTA pairs - the only shape whose MMAs run at the tensor pipe's full rate;
+  //   <2,128>, <4,64> - widest channel tile the layer has, most sub-tiles per weight tile;
+  //   <2,64> - widths that are only a multiple of 16 (also the test knob, variant bit 16: measured 10-30 % slower than
+  //   <4,64> where both apply: half the weight-tile reuse, twice the per-tile overhead);
+  //   <1,128>, <1,64> - small batches only, see below.
+  struct Cand {
+    int mt, bn;
+    bool pair;
+  } cands[6];
+  int nc = 0;
+  const bool k3 = op.ksize == 3 && !op.s2;
+  if (op.Cout % 256 == 0 && op.Win % 8 == 0 && pair_ok && !(var & 32) && even_tiles(1)) cands[nc++] = {1, 256, true};
+  if (op.Cout % 128 == 0 && op.Win % 16 == 0) cands[nc++] = {2, 128, pair_ok && !(var & 64) && even_tiles(2)};
+  if (op.Cout % 64 == 0 && op.Win % 32 == 0 && !(var & 16)) cands[nc++] = {4, 64, pair_ok && !(var & 128) && even_tiles(4)};
+  if (op.Cout % 64 == 0 && op.Win % 16 == 0) cands[nc++] = {2, 64, false};
+  if (k3 && op.Cout % 128 == 0 && op.Win % 8 == 0) cands[nc++] = {1, 128, false};
+  if (k3 && op.Cout % 64 == 0 && op.Win % 8 == 0) cands[nc++] = {1, 64, false};
+  if (nc == 0) {
+    if (op.Cout <= 16 && op.Win % 32 == 0 && op.ksize == 3 && !op.s2) *MT = 4, *BN = 16;
+    return;
   }
+  // Pick by a small cost model: rounds of CTAs x cost of one tile.  A tile costs its MMA work over the rate its N
+  // sustains from shared memory (N = 64: 58 clk against a 32-clk floor, N = 128: 68 / 64, N = 256: full rate - section 4
+  // of DESIGN.md) plus a fixed per-tile overhead (pipeline fill, epilogue tail) that favours the larger tiles.  At 176
+  // latents every layer has tens of tiles per SM and the first candidate stands (the model is only consulted when that
+  // shape yields less than one round of CTAs); with a small batch the launch
+  // becomes as wide as the layer allows (5 latents at 16x16 x 512 channels are 20 <1,256> tiles each walking K = 4608
+  // alone - or 80 <1,64> tiles).
+  auto cost = [&](const Cand& c) {
+    const double ctas = (double)op.N * (op.Hin / kRows) * (op.Win / (8 * c.mt)) * (op.Cout / c.bn), sms = host().num_sms;
+    const double rounds = ctas <= 4 * sms ? std::ceil(ctas / sms) : ctas / sms;
+    const double rate = c.bn >= 256 ? 1.0 : c.bn == 128 ? 0.94 : 0.55;
+    return rounds * (c.mt * c.bn / rate + 40.0);
+  };
+  int best = 0;
+  const bool one_round = (double)op.N * (op.Hin / kRows) * (op.Win / (8 * cands[0].mt)) * (op.Cout / cands[0].bn) < host().num_sms;
+  if (one_round && !(var & 1024))   // the model only decides where the full-batch shape leaves SMs idle
+    for (int i = 1; i < nc; ++i)
+      if (cost(cands[i]) < 0.97 * cost(cands[best])) best = i;   // a later (smaller) tile must win clearly
+  *MT = cands[best].mt, *BN = cands[best].bn, *pair = cands[best].pair;
 }
 
 // Grid and tile partition of a launch: CTAs (pairs), tiles per CTA (quotient / remainder) and the largest number of CTA
@@ -838,6 +867,10 @@ int conv_halo_init() {
   HSIDM_TRY((set_smem<2, 128, 0, false>()));
   HSIDM_TRY((set_smem<4, 64, 0, false>()));
   HSIDM_TRY((set_smem<2, 64, 0, false>()));
+  HSIDM_TRY((set_smem<1, 128, 9, false>()));
+  HSIDM_TRY((set_smem<1, 128, 4, false>()));
+  HSIDM_TRY((set_smem<1, 64, 9, false>()));
+  HSIDM_TRY((set_smem<1, 64, 4, false>()));
   HSIDM_TRY((set_smem<1, 256, 9, true>()));
   HSIDM_TRY((set_smem<1, 256, 4, true>()));
   HSIDM_TRY((set_smem<2, 128, 9, true>()));
@@ -892,6 +925,8 @@ int conv_halo(const ConvOp& op, cudaStream_t stream) {
     if (MT == 4 && BN == 64)
       return one ? launch<4, 64, 1, false>(op, stream) : sub ? launch<4, 64, 4, false>(op, stream) : launch<4, 64, 9, false>(op, stream);
     if (MT == 4 && BN == 16 && !sub && !one) return launch<4, 16, 9, false>(op, stream);
+    if (MT == 1 && BN == 128 && !one) return sub ? launch<1, 128, 4, false>(op, stream) : launch<1, 128, 9, false>(op, stream);
+    if (MT == 1 && BN == 64 && !one) return sub ? launch<1, 64, 4, false>(op, stream) : launch<1, 64, 9, false>(op, stream);
   }
   HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_halo: unsupported shape");
 }

@@ -480,12 +480,15 @@ int conv_tc(const ConvOp& op, cudaStream_t stream) {
     HSIDM_FAIL(HSIDM_UNSUPPORTED_CFG, "conv_tc: fused shortcut sources / sub-pixel upsampling / fused input GroupNorm need the halo kernel, which does not take this shape");
   TcP p;
   tile_geometry(op.Hin, op.Win, &p.bw, &p.bh, &p.bn);
-  const int BN = pick_bn(op.Cout);
+  int BN = pick_bn(op.Cout);
   fill_epilogue(&p.e, op);
   p.M = op.N * op.Hin * op.Win;
   p.tiles_x = op.Win / p.bw;
   p.tiles_y = op.Hin / p.bh;
   p.m_tiles = p.bn > 1 ? (int)ceil_div(op.N, p.bn) : op.N * p.tiles_x * p.tiles_y;
+  // small batches: narrower channel tiles while the grid still fits one wave - a 5-latent 8x8 conv is 3 pixel tiles, and
+  // with BN = 256 six CTAs would walk K = 4608 while 142 SMs idle (the packed weight rows are padded to the widest BN)
+  while (BN > 64 && p.m_tiles * (int)ceil_div(op.Cout, BN) * 2 <= host().num_sms) BN >>= 1;
   p.n_tiles = (int)ceil_div(op.Cout, BN);
   p.taps = op.ksize * op.ksize;
   p.bw_shift = 0, p.ppi_shift = 0;
