@@ -110,6 +110,9 @@ TC_CASES += [
     (24, 128, 64, 64, 64, 128, 3),    # <2,128>: 384 tiles, 3 chunks (odd ring occupancy per tile)
     (40, 64, 0, 32, 32, 64, 1),       # centre-tap form of a short-K 1x1: 160 tiles
     (40, 256, 0, 16, 16, 512, 1),     # per-tap kernel, 80 x 2 tiles, 4 k-blocks
+    # 8x8 images on the halo kernel: two images per tile with interleaved rows (odd batches leave half a tile empty)
+    (301, 64, 64, 8, 8, 128, 3),      # 151 image pairs > SMs: rings wrap; two sources; odd N
+    (7, 128, 0, 8, 8, 64, 3),         # N = 64 tile
 ]
 
 
