@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhsidm_b200.so")
-SOURCES = ["common.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "norm.cu", "misc.cu", "gemm_simt.cu", "gemm_tc.cu", "net.cu", "unet.cu",
+SOURCES = ["common.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "norm.cu", "misc.cu", "gemm_simt.cu", "gemm_tc.cu", "attn_flash.cu", "net.cu", "unet.cu",
            "gae.cu", "prepost.cu", "train.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-cudart", "static"]

@@ -307,6 +307,7 @@ int do_init() {
   HSIDM_CUDA(cudaMalloc(&h.err_flag, sizeof(int)));
   HSIDM_CUDA(cudaMemset(h.err_flag, 0, sizeof(int)));
   HSIDM_TRY(conv_halo_init());
+  HSIDM_TRY(attn_flash_init());
   return gemm_tc_init();
 }
 

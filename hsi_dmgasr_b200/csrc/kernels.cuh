@@ -122,6 +122,22 @@ struct GemmTcOp {
   // one tile: N <= 256, N % 64 == 0, c_f32 == 0.  The scores never leave tensor memory.
   int row_softmax = 0;
 };
+// attn_flash.cu : softmax(alpha * Q K^T) V for up to 256 tokens in one kernel (scores in tensor memory, probabilities in
+// shared memory).  Q, K: [batch][S][Ck] (row pitch ldq / ldk, batch stride sQ / sK), Vt: [batch][Cv][S] (V transposed, row
+// pitch S), Y: [batch][S][Cv] (row pitch ldy); all bf16, element strides.  Cv a multiple of 256, Ck of 64, S in {64, 128, 256}.
+struct AttnFlashOp {
+  const void* Q = nullptr;
+  const void* K = nullptr;
+  const void* Vt = nullptr;
+  void* Y = nullptr;
+  int S = 0, Ck = 0, Cv = 0, batch = 1;
+  int64_t ldq = 0, ldk = 0, ldy = 0, sQ = 0, sK = 0, sVt = 0, sY = 0;
+  float alpha = 1.0f;
+};
+bool attn_flash_supported(const AttnFlashOp& op);
+int attn_flash(const AttnFlashOp& op, cudaStream_t stream);
+int attn_flash_init();
+
 bool gemm_tc_supported(const GemmTcOp& op);
 int gemm_tc(const GemmTcOp& op, cudaStream_t stream);
 int gemm_tc_init();

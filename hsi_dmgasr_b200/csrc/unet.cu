@@ -243,20 +243,29 @@ bool attention_folded(hsidm_ctx* c, const ResW& r, const Act& x, Act& out) {
   if (stats) ex.release_raw(stats);
   Act t = ex.alloc_act(N, x.H, x.W, C);
   run_conv(ex, conv_op_nhwc(nrm, nullptr, t), wqk, c->ps);
-  bf16* prob = static_cast<bf16*>(ex.alloc_raw(sizeof(bf16) * (int64_t)N * S * S));
-  GemmTcOp sc;
-  sc.A = t.p, sc.B = nrm.p, sc.C = prob, sc.M = S, sc.N = S, sc.K = C, sc.batch = N;
-  sc.lda = sc.ldb = C, sc.sA = sc.sB = (int64_t)S * C, sc.ldc = S, sc.sC = (int64_t)S * S;
-  sc.alpha = 1.0f / std::sqrt((float)C), sc.c_f32 = 0, sc.row_softmax = 1;
-  ex.run([&] { return gemm_tc(sc, ex.stream); });
+  Act y = ex.alloc_act(N, x.H, x.W, C);
+  AttnFlashOp fa;
+  fa.Q = t.p, fa.K = nrm.p, fa.Vt = xt, fa.Y = y.p, fa.S = S, fa.Ck = C, fa.Cv = C, fa.batch = N;
+  fa.ldq = fa.ldk = fa.ldy = C, fa.sQ = fa.sK = fa.sY = (int64_t)S * C, fa.sVt = (int64_t)C * S;
+  fa.alpha = 1.0f / std::sqrt((float)C);
+  if (!(conv_tc_variant() & 4096) && attn_flash_supported(fa)) {
+    // scores, softmax and P.Xn in one kernel: the scores stay in tensor memory, the probabilities in shared memory
+    ex.run([&] { return attn_flash(fa, ex.stream); });
+  } else {
+    bf16* prob = static_cast<bf16*>(ex.alloc_raw(sizeof(bf16) * (int64_t)N * S * S));
+    GemmTcOp sc;
+    sc.A = t.p, sc.B = nrm.p, sc.C = prob, sc.M = S, sc.N = S, sc.K = C, sc.batch = N;
+    sc.lda = sc.ldb = C, sc.sA = sc.sB = (int64_t)S * C, sc.ldc = S, sc.sC = (int64_t)S * S;
+    sc.alpha = fa.alpha, sc.c_f32 = 0, sc.row_softmax = 1;
+    ex.run([&] { return gemm_tc(sc, ex.stream); });
+    GemmTcOp pv;
+    pv.A = prob, pv.B = xt, pv.C = y.p, pv.M = S, pv.N = C, pv.K = S, pv.batch = N;
+    pv.lda = S, pv.sA = (int64_t)S * S, pv.ldb = S, pv.sB = (int64_t)C * S, pv.ldc = C, pv.sC = (int64_t)S * C, pv.c_f32 = 0;
+    ex.run([&] { return gemm_tc(pv, ex.stream); });
+    ex.release_raw(prob);
+  }
   ex.release(t);
   ex.release(nrm);
-  Act y = ex.alloc_act(N, x.H, x.W, C);
-  GemmTcOp pv;
-  pv.A = prob, pv.B = xt, pv.C = y.p, pv.M = S, pv.N = C, pv.K = S, pv.batch = N;
-  pv.lda = S, pv.sA = (int64_t)S * S, pv.ldb = S, pv.sB = (int64_t)C * S, pv.ldc = C, pv.sC = (int64_t)S * C, pv.c_f32 = 0;
-  ex.run([&] { return gemm_tc(pv, ex.stream); });
-  ex.release_raw(prob);
   ex.release_raw(xt);
   ConvOp op = conv_op_nhwc(y, nullptr, out);
   op.resid = x.p;

@@ -31,7 +31,8 @@ HSIDM_API int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const
  * 32 = no CTA-pair (cta_group::2) tile for Cout % 256 == 0; 64 / 128 = CTA-pair tiles also for the 128- / 64-channel tiles;
  * 256 = GroupNorm statistics through gn_finalize launches instead of the producing convolution's tail;
  * 512 = self-attention with q, k, v materialised instead of the folded projections (Wk^T Wq, Wout Wv);
- * 1024 = no occupancy-based narrowing of the halo tile at small batches (always the full-batch tile shape). */
+ * 1024 = no occupancy-based narrowing of the halo tile at small batches (always the full-batch tile shape);
+ * 4096 = attention scores + softmax and P.V as two GEMM launches instead of the fused attn_flash kernel. */
 HSIDM_API int hsidm_debug_conv_mode(int no_halo, int variant);
 
 /* Developer probe: when device_counters is non-null every halo-kernel launch writes 8 int64 cycle counters per CTA

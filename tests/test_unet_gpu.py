@@ -224,6 +224,31 @@ def test_small_batch_tile_shapes_match_full_batch_shapes(hw, n):
     assert e_narrow < TOL["bf16"] and e_narrow < 1.5 * e_full + 1e-3
 
 
+@pytest.mark.parametrize("hw,n", [(128, 2), (128, 7), (64, 3)])
+def test_fused_attention_core_is_bitwise_the_two_kernel_form(hw, n):
+    """attn_flash computes softmax(alpha Q K^T) V in one kernel (scores in tensor memory, probabilities in shared memory);
+    variant 4096 runs the same contraction as two GEMM launches with the probabilities in HBM.  Same MMAs in the same
+    K order, same softmax arithmetic, same bf16 rounding points: the network outputs must be bit-identical."""
+    from hsi_dmgasr_b200 import _lib
+    lib = _lib.load()
+    cfg, seed, *_ = UNET_CASES["full32"]
+    x = torch.from_numpy(np.random.default_rng(81).standard_normal((n, 6, hw, hw), dtype=np.float32)).cuda()
+    lv = torch.linspace(0.3, 0.8, n).view(n, 1).cuda()
+    outs = {}
+    try:
+        for variant in (4096, 0):
+            lib.hsidm_debug_conv_mode(0, variant)
+            net = build(cfg, seed, "bf16")
+            with torch.no_grad():
+                outs[variant] = net(x, lv).clone()
+            del net
+    finally:
+        lib.hsidm_debug_conv_mode(0, 0)
+    assert tc_flag() == 0
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[4096]), f"max |diff| {float((outs[0] - outs[4096]).abs().max()):.3e}"
+
+
 def test_c4_shape_512_bf16_tracks_fp32():
     """BASELINE config C4: the 64_512 UNet (mults 1-2-4-8-16, one res block, 16 groups, mid attention at 32x32 = 1024
     tokens) on a 512x512 latent.  The CPU oracle needs minutes at this size, so the check is internal: the tensor-core
