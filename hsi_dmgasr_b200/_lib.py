@@ -86,6 +86,8 @@ SIGNATURES = {
     "hsidm_debug_groupnorm": (C.c_int, [C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
                                         C.c_float, C.c_int, _P]),
     "hsidm_bicubic_upsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hsidm_imresize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p]),
+    "hsidm_quality_assessment": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "hsidm_quality_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hsidm_debug_conv_mode": (C.c_int, [C.c_int, C.c_int]),
     "hsidm_debug_halo_timing": (C.c_int, [C.c_void_p]),

@@ -130,6 +130,38 @@ int hsidm_quality_metrics(const float* truth, const float* pred, int N, int C, i
   return s;
 }
 
+int hsidm_imresize(const float* in, float* out, int planes, int h, int w, int out_h, int out_w, double scale_h, double scale_w,
+                   int method, hsidm_stream stream) {
+  if (!in || !out) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_imresize: null argument");
+  if (planes <= 0 || h <= 0 || w <= 0 || out_h <= 0 || out_w <= 0)
+    HSIDM_FAIL(HSIDM_BAD_SHAPE, "hsidm_imresize: bad shape %d x %dx%d -> %dx%d", planes, h, w, out_h, out_w);
+  if (scale_h < 0.0 || scale_w < 0.0) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_imresize: negative scale");
+  if (scale_h == 0.0) scale_h = (double)out_h / h;
+  if (scale_w == 0.0) scale_w = (double)out_w / w;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* scratch = nullptr;
+  HSIDM_CUDA(cudaMallocAsync(&scratch, (size_t)imresize_scratch_bytes(out_h, out_w, scale_h, scale_w), st));
+  int s = HSIDM_OK;
+  for (long long p0 = 0; p0 < planes && s == HSIDM_OK; p0 += 65535) {   // planes go along gridDim.y
+    const int cnt = (int)std::min<long long>(65535, planes - p0);
+    s = imresize(in + p0 * h * w, out + p0 * (long long)out_h * out_w, cnt, h, w, out_h, out_w, scale_h, scale_w, method, scratch, st);
+  }
+  HSIDM_CUDA(cudaFreeAsync(scratch, st));
+  return s;
+}
+
+int hsidm_quality_assessment(const float* truth, const float* pred, int N, int C, int H, int W, float ratio, float* out,
+                             hsidm_stream stream) {
+  if (!truth || !pred || !out) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_quality_assessment: null argument");
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) HSIDM_FAIL(HSIDM_BAD_SHAPE, "hsidm_quality_assessment: bad shape %d x %d x %dx%d", N, C, H, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* scratch = nullptr;
+  HSIDM_CUDA(cudaMallocAsync(&scratch, (size_t)quality_assessment_scratch_bytes(N, C, H, W), st));
+  const int s = quality_assessment(truth, pred, N, C, H, W, ratio, scratch, out, st);
+  HSIDM_CUDA(cudaFreeAsync(scratch, st));
+  return s;
+}
+
 int hsidm_randn(float* out, int64_t n, uint64_t seed, int64_t first_element, hsidm_stream stream) {
   if (!out || n < 0 || first_element < 0 || first_element % 4) HSIDM_FAIL(HSIDM_BAD_ARG, "hsidm_randn: bad argument");
   // step 0xFFFFFFFF: a Philox stream no loop index of hsidm_sample uses (those are t = 1 .. T-1)

@@ -174,6 +174,15 @@ int upsample2x(const void* x, void* out, int N, int H, int W, int C, int prec, c
 
 // prepost.cu : bicubic pre-upsampling of NCHW fp32 planes and the per-cube MPSNR / SAM metrics
 int bicubic_upsample(const float* src, float* dst, int planes, int h, int w, int scale, int clamp01, cudaStream_t stream);
+// MATLAB-style imresize (imsize.py:116-158) of `planes` fp32 planes h x w -> H x W with the given per-axis scales;
+// method 0 = bicubic, 1 = bilinear.
+int64_t imresize_scratch_bytes(int H, int W, double scale_h, double scale_w);
+int imresize(const float* src, float* dst, int planes, int h, int w, int H, int W, double scale_h, double scale_w, int method,
+             void* scratch, cudaStream_t stream);
+// quality_assessment (eval_hsi.py:217-238): out [N][6] = (MPSNR, MSSIM, ERGAS, SAM, CrossCorrelation, RMSE)
+int64_t quality_assessment_scratch_bytes(int N, int C, int H, int W);
+int quality_assessment(const float* truth, const float* pred, int N, int C, int H, int W, float ratio, void* scratch, float* out,
+                       cudaStream_t stream);
 int64_t quality_metrics_scratch_bytes(int N, int C, int HW);
 int quality_metrics(const float* truth, const float* pred, int N, int C, int HW, float data_range, void* scratch, float* out,
                     cudaStream_t stream);

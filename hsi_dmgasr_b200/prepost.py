@@ -3,12 +3,15 @@
 ``bicubic_upsample`` replaces the dataset code's ``torch.nn.functional.interpolate(img_LR, scale_factor=4,
 mode='bicubic')`` (reference sr_gae.py:72, :118); ``quality_metrics`` replaces the CPU ``compare_mpsnr`` /
 ``compare_sam`` of the validation loop (eval_hsi.py:110-121, :47-65; the latter is a Python double loop over pixels in
-the reference).  Both call the C ABI (hsidm_bicubic_upsample / hsidm_quality_metrics); there is no CPU fallback here -
-``metrics.py`` keeps the numpy forms the parity tests are stated in.
+the reference).  ``imresize`` is the MATLAB-style resize of the dataset classes (GAE/imsize.py:116-158, called by
+HStest.py:44-45 / HStrain.py:61-63 - a different bicubic from torch's: a = -0.5, antialiased when shrinking, mirrored
+borders); ``quality_assessment`` returns all six indices of eval_hsi.py:217-238.  Everything calls the C ABI
+(hsidm_bicubic_upsample / hsidm_imresize / hsidm_quality_metrics / hsidm_quality_assessment); there is no CPU fallback
+here - ``metrics.py`` keeps the numpy forms the parity tests are stated in.
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 
@@ -26,6 +29,68 @@ def bicubic_upsample(lr: torch.Tensor, scale: int = 4, clamp01: bool = False) ->
     _lib.check(_lib.load().hsidm_bicubic_upsample(x.data_ptr(), out.data_ptr(), n, c, h, w, int(scale), int(clamp01),
                                                   _lib.stream_ptr(x.device)))
     return out[0] if squeeze else out
+
+
+_METHODS = {"bicubic": 0, "bilinear": 1}
+
+
+def imresize(img: torch.Tensor, scalar_scale: Optional[float] = None, method: str = "bicubic",
+             output_shape: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """imsize.imresize on the device: img [N,C,h,w], [C,h,w] or [h,w] fp32 CUDA (band planes; the reference's HWC arrays
+    are resized band by band) -> the same rank with the two spatial axes resized.  Same argument rules as the reference:
+    exactly one of ``scalar_scale`` / ``output_shape`` (ValueError otherwise), output size ``ceil(scale * size)``."""
+    if method not in _METHODS:
+        raise ValueError("unidentified kernel method supplied")
+    if (scalar_scale is None) == (output_shape is None):
+        raise ValueError("either scalar_scale OR output_shape should be defined")
+    x = _lib.require_cuda_f32(img, "img")
+    if x.dim() not in (2, 3, 4):
+        raise _lib.HsidmError(-1, f"img must be [N,C,h,w], [C,h,w] or [h,w], got {tuple(img.shape)}")
+    h, w = x.shape[-2:]
+    if scalar_scale is not None:
+        import math
+        sc = float(scalar_scale)
+        oh, ow = int(math.ceil(sc * h)), int(math.ceil(sc * w))
+    else:
+        sc = 0.0                                   # the library derives out / in per axis
+        oh, ow = int(output_shape[0]), int(output_shape[1])
+    planes = int(x.numel() // (h * w))
+    out = torch.empty(tuple(x.shape[:-2]) + (oh, ow), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().hsidm_imresize(x.data_ptr(), out.data_ptr(), planes, h, w, oh, ow, sc, sc, _METHODS[method],
+                                          _lib.stream_ptr(x.device)))
+    return out
+
+
+def degrade_and_preupsample(gt: torch.Tensor, n_scale: int = 4) -> Tuple[torch.Tensor, torch.Tensor]:
+    """HStest.py:44-45 on the device: ms = imresize(gt, gt_size // n_scale), lms = imresize(ms, gt_size)."""
+    h, w = gt.shape[-2:]
+    ms = imresize(gt, output_shape=(h // n_scale, w // n_scale))
+    return ms, imresize(ms, output_shape=(h, w))
+
+
+ASSESSMENT_KEYS = ("MPSNR", "MSSIM", "ERGAS", "SAM", "CrossCorrelation", "RMSE")
+
+
+def quality_assessment(truth: torch.Tensor, pred: torch.Tensor, ratio: float = 4.0) -> torch.Tensor:
+    """truth / pred [N,C,H,W] fp32 CUDA cubes -> [N,6] in the key order of eval_hsi.quality_assessment
+    (``ASSESSMENT_KEYS``), data_range 1, both cubes clamped to [0,1] first like the validation driver does."""
+    a = _lib.require_cuda_f32(truth, "truth")
+    b = _lib.require_cuda_f32(pred, "pred")
+    if a.dim() != 4 or tuple(a.shape) != tuple(b.shape):
+        raise _lib.HsidmError(-1, f"truth {tuple(truth.shape)} and pred {tuple(pred.shape)} must be equal [N,C,H,W] shapes")
+    n, c, h, w = a.shape
+    out = torch.empty((n, 6), device=a.device, dtype=torch.float32)
+    _lib.check(_lib.load().hsidm_quality_assessment(a.data_ptr(), b.data_ptr(), n, c, h, w, float(ratio), out.data_ptr(),
+                                                    _lib.stream_ptr(a.device)))
+    return out
+
+
+def quality_assessment_dict(truth: torch.Tensor, pred: torch.Tensor, ratio: float = 4.0) -> Dict[str, float]:
+    """The reference's return shape for ONE cube pair ([C,H,W] or [1,C,H,W]): {'MPSNR': ..., 'MSSIM': ..., ...}."""
+    t = truth if truth.dim() == 4 else truth.unsqueeze(0)
+    p = pred if pred.dim() == 4 else pred.unsqueeze(0)
+    row = quality_assessment(t, p, ratio)[0].tolist()
+    return dict(zip(ASSESSMENT_KEYS, row))
 
 
 def quality_metrics(truth: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:

@@ -227,6 +227,26 @@ HSIDM_API int hsidm_bicubic_upsample(const float* lr, float* sr, int N, int C, i
  * float64); allocates its scratch with cudaMallocAsync on `stream`. */
 HSIDM_API int hsidm_quality_metrics(const float* truth, const float* pred, int N, int C, int H, int W, float* out, hsidm_stream stream);
 
+/* MATLAB-style imresize of the dataset code (GAE/imsize.py:116-158 `imresize(I, output_shape=...)`, called by
+ * HStest.py:44-45 and HStrain.py:61-63 for the x4 degradation and the pre-upsampling): separable resampling, antialiased
+ * when shrinking (kernel stretched by 1/scale), taps mirrored at the borders, weights and sums in float64.
+ * in [planes,h,w] -> out [planes,out_h,out_w] fp32 device pointers (a plane = one band of one cube; the reference's HWC
+ * arrays are resized band by band, so the layouts are interchangeable).  method: 0 = 'bicubic' (a = -0.5), 1 = 'bilinear'
+ * (both with the reference's kernel width 4).  scale_h / scale_w: the resampling scale per axis - pass 0 for the
+ * `output_shape` form (scale = out / in, imsize.py:10-14); the `scalar_scale` form passes the scalar itself with
+ * out = ceil(scale * in) (imsize.py:3-7), which is not out / in in general.  Allocates its tap tables with cudaMallocAsync
+ * on `stream`. */
+HSIDM_API int hsidm_imresize(const float* in, float* out, int planes, int h, int w, int out_h, int out_w, double scale_h, double scale_w,
+                   int method, hsidm_stream stream);
+
+/* quality_assessment (eval_hsi.py:217-238) per cube on the device, after the driver's clamp of both cubes to [0,1]
+ * (sr_gae.py:474-475).  out [N][6] fp32 in the reference dict's key order: MPSNR (eval_hsi.py:110-121), MSSIM (:124-135,
+ * skimage.metrics.structural_similarity with its defaults for float images: 7x7 uniform window, K1 = .01, K2 = .03, sample
+ * covariance; NaN when H or W < 7), ERGAS (:18-35, `ratio` = the SR factor), SAM in degrees (:47-65), CrossCorrelation
+ * (:58-70), RMSE (:88-96); data_range 1.  truth / pred: [N,C,H,W] fp32 device pointers, N*C <= 65535.  Deterministic. */
+HSIDM_API int hsidm_quality_assessment(const float* truth, const float* pred, int N, int C, int H, int W, float ratio, float* out,
+                             hsidm_stream stream);
+
 /* Overlapping-tile scene driver (the reference only crops non-overlapping 128x128 blocks offline,
  * GAE/crop.py:12-36, HStest.py:33-45): feathered overlap-add of super-resolved tiles back into the scene on the device.
  * tiles [ny*nx, C, tile, tile] fp32 in row-major tile order, tile (iy, ix) at origin (ys[iy], xs[ix]); ys / xs are DEVICE

@@ -8,6 +8,10 @@ This file restates, in plain fp32 PyTorch on the CPU and in a *functional* style
   * p_mean_variance / p_sample / loop      reference model/sr3_modules/diffusion.py:142-201
   * GAE group layout / encode / decode     reference AE.py:256-324, common.py:163-182, 231-271
   * MPSNR / SAM                            reference eval_hsi.py:47-65, 110-121
+  * ERGAS / CC / RMSE / MSSIM              reference eval_hsi.py:18-35, 58-70, 88-96, 124-135 (MSSIM restates the
+                                           published algorithm of skimage.metrics.structural_similarity, a dependency
+                                           absent from this image: that one index is "parity unpinned")
+  * MATLAB-style imresize                  reference GAE/imsize.py:35-59, 116-158
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
 ``bench.py`` may import it; it is the checker, never the product.  The product package
@@ -367,6 +371,100 @@ def sam_deg(x_true: np.ndarray, x_pred: np.ndarray) -> float:
 def bicubic_pre_upsample(lr: torch.Tensor, scale: int = 4) -> torch.Tensor:
     """The dataset code's pre-upsampling, verbatim call (sr_gae.py:72, :118): torch bicubic, align_corners=False."""
     return torch.nn.functional.interpolate(lr, scale_factor=scale, mode="bicubic")
+
+
+def imresize_matlab(img: np.ndarray, output_shape=None, method: str = "bicubic", scalar_scale=None) -> np.ndarray:
+    """imsize.imresize(I, output_shape=... | scalar_scale=...) (imsize.py:116-158) for an HWC or HW array, float64 result.
+    With scalar_scale the scale is the given number and the size ceil(scale * n) (imsize.py:3-7, 131-134); with
+    output_shape the scale is out / in per axis (imsize.py:10-14, 135-137).  Per axis
+    (`contributions`, imsize.py:35-59): kernel stretched by 1/scale when shrinking, P = ceil(width) + 2 taps from
+    floor(u - width/2) - 1, weights normalised, taps mirrored with period 2*length; the axis with the smaller scale goes
+    first (imsize.py:141-152)."""
+    def cubic(x):
+        ax = np.abs(x)
+        return (1.5 * ax ** 3 - 2.5 * ax ** 2 + 1) * (ax <= 1) + (-0.5 * ax ** 3 + 2.5 * ax ** 2 - 4 * ax + 2) * ((1 < ax) & (ax <= 2))
+
+    def triangle(x):
+        return (x + 1) * ((x >= -1) & (x < 0)) + (1 - x) * ((x <= 1) & (x >= 0))
+
+    kern = {"bicubic": cubic, "bilinear": triangle}[method]
+    a = np.asarray(img)
+    b = a[..., None] if a.ndim == 2 else a
+    if scalar_scale is not None:
+        scales = [float(scalar_scale)] * 2
+        output_shape = [int(math.ceil(sc * n)) for sc, n in zip(scales, b.shape[:2])]
+    else:
+        scales = [1.0 * out / n for out, n in zip(output_shape, b.shape[:2])]
+    for dim in np.argsort(np.array(scales)):
+        scale, n_in, n_out = scales[dim], b.shape[dim], int(output_shape[dim])
+        width = 4.0 / scale if scale < 1 else 4.0
+        u = np.arange(1, n_out + 1, dtype=np.float64) / scale + 0.5 * (1 - 1 / scale)
+        left = np.floor(u - width / 2)
+        taps = (left[:, None] + np.arange(int(math.ceil(width)) + 2) - 1).astype(np.int64)
+        arg = u[:, None] - taps - 1
+        wts = scale * kern(scale * arg) if scale < 1 else kern(arg)
+        wts = wts / wts.sum(axis=1, keepdims=True)
+        mirror = np.concatenate([np.arange(n_in), np.arange(n_in - 1, -1, -1)])
+        taps = mirror[np.mod(taps, mirror.size)]
+        moved = np.moveaxis(b.astype(np.float64), dim, 0)                  # [n_in, ...]
+        b = np.moveaxis(np.einsum("op,op...->o...", wts, moved[taps]), 0, dim)
+    return b[..., 0] if a.ndim == 2 else b
+
+
+def ergas(x_true: np.ndarray, x_pred: np.ndarray, ratio: float) -> float:
+    """compare_ergas (eval_hsi.py:18-35) over HWC arrays: (100/ratio) sqrt(mean_bands(MSE_b / mean(true_b)^2))."""
+    a = x_true.astype(np.float32).astype(np.float64).reshape(-1, x_true.shape[2])
+    b = x_pred.astype(np.float32).astype(np.float64).reshape(-1, x_pred.shape[2])
+    return float(100.0 / ratio * np.sqrt(np.mean(((a - b) ** 2).mean(axis=0) / a.mean(axis=0) ** 2)))
+
+
+def cross_correlation(x_true: np.ndarray, x_pred: np.ndarray) -> float:
+    """compare_corr (eval_hsi.py:58-70): Pearson correlation per band, mean over bands."""
+    a = x_true.astype(np.float32).astype(np.float64).reshape(-1, x_true.shape[2])
+    b = x_pred.astype(np.float32).astype(np.float64).reshape(-1, x_pred.shape[2])
+    a = a - a.mean(axis=0)
+    b = b - b.mean(axis=0)
+    return float(((a * b).sum(axis=0) / np.sqrt((a * a).sum(axis=0) * (b * b).sum(axis=0))).mean())
+
+
+def rmse(x_true: np.ndarray, x_pred: np.ndarray) -> float:
+    """compare_rmse (eval_hsi.py:88-96): ||true - pred||_F / sqrt(H W C)."""
+    d = x_true.astype(np.float32).astype(np.float64) - x_pred.astype(np.float32).astype(np.float64)
+    return float(np.sqrt((d ** 2).sum() / d.size))
+
+
+def mssim(x_true: np.ndarray, x_pred: np.ndarray, data_range: float = 1.0) -> float:
+    """compare_mssim (eval_hsi.py:124-135): mean over bands of skimage.metrics.structural_similarity(im1, im2,
+    data_range=...) with skimage's defaults for float images - win_size 7, uniform filter, K1 = 0.01, K2 = 0.03,
+    use_sample_covariance=True, mean of S over the image cropped by (win_size-1)//2 (where the window is inside the
+    image, so the filter's border mode does not matter).  skimage is absent here: restated from its published algorithm,
+    PARITY UNPINNED for this one index."""
+    from scipy.ndimage import uniform_filter
+    win, c1, c2 = 7, (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    cov = win * win / (win * win - 1.0)
+    pad = (win - 1) // 2
+    vals = []
+    for k in range(x_true.shape[2]):
+        x = x_true[:, :, k].astype(np.float32).astype(np.float64)
+        y = x_pred[:, :, k].astype(np.float32).astype(np.float64)
+        ux, uy = uniform_filter(x, win), uniform_filter(y, win)
+        vx = cov * (uniform_filter(x * x, win) - ux * ux)
+        vy = cov * (uniform_filter(y * y, win) - uy * uy)
+        vxy = cov * (uniform_filter(x * y, win) - ux * uy)
+        S = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
+        vals.append(S[pad:-pad, pad:-pad].mean())
+    return float(np.mean(vals))
+
+
+def cube_assessment(truth: torch.Tensor, pred: torch.Tensor, ratio: float = 4.0):
+    """Per-cube rows (MPSNR, MSSIM, ERGAS, SAM, CrossCorrelation, RMSE) of NCHW batches: the validation loop's clamp to
+    [0,1] and HWC layout (sr_gae.py:474-475, 483-484), then quality_assessment's indices (eval_hsi.py:217-238)."""
+    out = []
+    for t, p in zip(truth, pred):
+        th = t.clamp(0, 1).permute(1, 2, 0).numpy()
+        ph = p.clamp(0, 1).permute(1, 2, 0).numpy()
+        out.append((mpsnr(th, ph), mssim(th, ph), ergas(th, ph, ratio), sam_deg(th, ph), cross_correlation(th, ph), rmse(th, ph)))
+    return out
 
 
 def cube_metrics(truth: torch.Tensor, pred: torch.Tensor):

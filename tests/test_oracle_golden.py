@@ -137,3 +137,62 @@ def test_train_step_matches_reference(golden, loss_type):
             assert rel(gr.numpy(), g[f"{loss_type}.grad.{k}"]) < 2e-4, k
             checked += 1
     assert len(grads) == 124 and checked > 50
+
+
+# ---- the steps either side of the path: MATLAB-style imresize and quality_assessment ----------------
+from oracle import make_golden_prepost as GP  # noqa: E402  (case tables and seeded inputs only; never touches the reference here)
+
+
+@pytest.mark.parametrize("name", list(GP.IMRESIZE_CASES))
+def test_imresize_matches_reference_imsize(golden, name):
+    """oracle.imresize_matlab against GAE/imsize.py's outputs for the dataset code's own calls (HStest.py:44-45)."""
+    g = golden("prepost.npz")
+    seed, shape, first, second, method = GP.IMRESIZE_CASES[name]
+    x = GP.imresize_input(seed, shape)
+    ms = O.imresize_matlab(x, first, method)
+    ref = g[f"imresize.{name}.first"]
+    assert ms.shape == ref.shape and ms.dtype == np.float64
+    assert float(np.abs(ms - ref).max()) < 1e-13
+    if second is not None:
+        lms = O.imresize_matlab(ms, second, method)
+        assert float(np.abs(lms - g[f"imresize.{name}.second"]).max()) < 1e-13
+        lms32 = O.imresize_matlab(ms.astype(np.float32), second, method)
+        assert float(np.abs(lms32 - g[f"imresize.{name}.second_from_f32"]).max()) < 1e-13
+
+
+def test_imresize_scalar_scale_shape_rule(golden):
+    g = golden("prepost.npz")
+    x = GP.imresize_input(16, (20, 28, 2))
+    ref = g["imresize.scalar_scale.first"]
+    assert ref.shape == (6, 9, 2)                       # ceil(0.3 * 20), ceil(0.3 * 28)  (imsize.py:3-7)
+    assert float(np.abs(O.imresize_matlab(x, scalar_scale=0.3) - ref).max()) < 1e-13
+
+
+@pytest.mark.parametrize("name", list(GP.ASSESS_CASES))
+def test_assessment_indices_match_reference_eval_hsi(golden, name):
+    """ERGAS / SAM / CrossCorrelation / RMSE of the oracle against eval_hsi.py's own functions (float32 sums there)."""
+    g = golden("prepost.npz")
+    truth, pred = GP.assess_inputs(*GP.ASSESS_CASES[name])
+    rows = O.cube_assessment(torch.from_numpy(truth), torch.from_numpy(pred), 4.0)
+    for (m, ss, e, s, c, r), ref in zip(rows, g[f"assess.{name}"]):
+        assert abs(e - ref[0]) < 2e-4 * ref[0]
+        assert abs(s - ref[1]) < 1e-3
+        assert abs(c - ref[2]) < 1e-5
+        assert abs(r - ref[3]) < 1e-6
+        assert 0.0 < ss < 1.0 and m > 10.0
+
+
+def test_mssim_restatement_properties():
+    """MSSIM is restated from skimage's algorithm (skimage is absent: unpinned); check what the definition implies."""
+    rng = np.random.default_rng(5)
+    a = rng.random((20, 18, 3), dtype=np.float32)
+    assert abs(O.mssim(a, a) - 1.0) < 1e-12
+    b = np.clip(a + 0.1 * rng.standard_normal(a.shape).astype(np.float32), 0, 1)
+    assert O.mssim(a, b) < 1.0 and abs(O.mssim(a, b) - O.mssim(b, a)) < 1e-12
+    # direct evaluation of one window against the formula
+    x, y = a[:7, :7, 0].astype(np.float64), b[:7, :7, 0].astype(np.float64)
+    ux, uy = x.mean(), y.mean()
+    vx, vy, vxy = x.var(ddof=1), y.var(ddof=1), ((x - ux) * (y - uy)).sum() / 48
+    s = ((2 * ux * uy + 1e-4) * (2 * vxy + 9e-4)) / ((ux * ux + uy * uy + 1e-4) * (vx + vy + 9e-4))
+    one = O.mssim(a[:7, :7, :1], b[:7, :7, :1])
+    assert abs(one - s) < 1e-12
