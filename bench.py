@@ -23,7 +23,7 @@ Other workloads (not what the driver runs; lines committed under profiles/):
                   reference's own call pattern; CPU arm run in full.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
-  python bench.py --impl reference [...]                        # reference's CPU implementation (oracle port) on host cores
+  python bench.py --impl reference [...]                        # reference's CPU implementation (oracle/_ref, else the port) on host cores
   torchrun --nproc-per-node N bench.py --gpus N ...             # one rank per GPU, no per-step collective
 """
 from __future__ import annotations
@@ -128,7 +128,10 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_reference_leg(wl: dict, steps: int, warmup: int, full: bool = False) -> dict:
-    """The reference's CPU path (oracle port of unet.py / AE.py / diffusion.py, fp32, all host threads).
+    """The reference's CPU path, fp32, all host threads.  UNet forwards and the sampling loop run through the UNMODIFIED
+    reference modules (model/sr3_modules/unet.py, diffusion.py byte-compiled into oracle/_ref by oracle/build_ref.py:
+    kind "reference"); when oracle/_ref is absent, through the oracle port of the same files (kind "port").  The GAE codec
+    (0.01 % of a patch; AE.py's loops hard-code 'cuda:0') always runs through the oracle port.
 
     Bounded sample (default): `steps` UNet forwards of ONE 128x128 group latent + one cube through GAE encode and decode,
     extrapolated linearly to a full patch (G*T forwards + codec); per-step cost is constant in t.
@@ -137,6 +140,7 @@ def cpu_reference_leg(wl: dict, steps: int, warmup: int, full: bool = False) -> 
     import torch
     from hsi_dmgasr_b200 import synth
     from hsi_dmgasr_b200.spec import GAEGeometry, UNetConfig
+    from oracle import build_ref
     from oracle import hsidm_oracle as O      # the only place bench.py executes the oracle: as the measured CPU baseline
 
     cores = os.cpu_count() or 1
@@ -144,26 +148,52 @@ def cpu_reference_leg(wl: dict, steps: int, warmup: int, full: bool = False) -> 
     cfg, geom = UNetConfig(**UNET), GAEGeometry(*wl["geom"])
     usd, gsd = synth.unet_state_dict(cfg, 0), synth.gae_state_dict(geom, 1)
     T = wl["T"]
+    ref = build_ref.load()
+    kind = "reference" if ref else "port"
+    if ref:
+        unet_mod, diff_mod = ref
+        net = unet_mod.UNet(in_channel=cfg.in_channel, out_channel=cfg.out_channel, norm_groups=cfg.norm_groups,
+                            inner_channel=cfg.inner_channel, channel_mults=list(cfg.channel_mults), attn_res=list(cfg.attn_res),
+                            res_blocks=cfg.res_blocks, dropout=cfg.dropout, image_size=cfg.image_size)
+        net.load_state_dict(usd, strict=True)
+        net.eval()
+        forward = net
+        what = "unmodified reference UNet.forward (oracle/_ref)"
+    else:
+        forward = lambda x, lv: O.unet_forward(usd, cfg.as_dict(), x, lv)   # noqa: E731
+        what = "oracle port of UNet.forward"
     with torch.no_grad():
         if full:
-            tab = O.schedule_tables(O.beta_schedule("cosine", T, 1e-6, 1e-2))
             cube = synth.sr_cube(1, wl["bands"], HW, seed=2)
-            x_T, tape = synth.noise_tape(geom.G, T, 3, HW, HW, seed=3)
-            O.unet_forward(usd, cfg.as_dict(), torch.randn(1, 6, HW, HW), torch.full((1, 1), 0.5))      # warm-up
-            t0 = time.perf_counter()
-            O.sr_cube(usd, cfg.as_dict(), tab, gsd, geom.as_dict(), cube, [x_T[g:g + 1] for g in range(geom.G)],
-                      lambda g, i: tape[g:g + 1, T - 1 - i])
-            per_patch = time.perf_counter() - t0
-            return {"value": 1.0 / per_patch, "unit": "patches/s", "cores": cores, "kind": "port",
-                    "sample": f"one complete patch, not extrapolated: GAE encode, {geom.G} groups x T={T} UNet forwards at batch 1, "
-                              f"GAE decode ({per_patch:.1f} s)", "ms_per_unet_step_per_latent": per_patch * 1e3 / (geom.G * T)}
+            forward(torch.randn(1, 6, HW, HW), torch.full((1, 1), 0.5))      # warm-up
+            if ref:
+                # sr_gae.py:444-467: encode, then per group GaussianDiffusion.super_resolution at batch 1, decode
+                os.environ.setdefault("TQDM_DISABLE", "1")
+                gd = diff_mod.GaussianDiffusion(net, image_size=HW, channels=3, conditional=True)
+                gd.set_new_noise_schedule(dict(schedule="cosine", n_timestep=T, linear_start=1e-6, linear_end=1e-2), "cpu")
+                t0 = time.perf_counter()
+                zs = O.gae_encode(gsd, geom.as_dict(), cube)
+                outs = [gd.super_resolution(z, False) for z in zs]
+                O.gae_decode(gsd, geom.as_dict(), cube, outs)
+                per_patch = time.perf_counter() - t0
+            else:
+                tab = O.schedule_tables(O.beta_schedule("cosine", T, 1e-6, 1e-2))
+                x_T, tape = synth.noise_tape(geom.G, T, 3, HW, HW, seed=3)
+                t0 = time.perf_counter()
+                O.sr_cube(usd, cfg.as_dict(), tab, gsd, geom.as_dict(), cube, [x_T[g:g + 1] for g in range(geom.G)],
+                          lambda g, i: tape[g:g + 1, T - 1 - i])
+                per_patch = time.perf_counter() - t0
+            return {"value": 1.0 / per_patch, "unit": "patches/s", "cores": cores, "kind": kind,
+                    "sample": f"one complete patch, not extrapolated: GAE encode (port), {geom.G} groups x T={T} steps at batch 1 "
+                              f"through {what}, GAE decode (port) ({per_patch:.1f} s)",
+                    "ms_per_unet_step_per_latent": per_patch * 1e3 / (geom.G * T)}
         x = torch.randn(1, 6, HW, HW)
         lv = torch.full((1, 1), 0.5)
         for _ in range(max(1, min(warmup, 3))):
-            O.unet_forward(usd, cfg.as_dict(), x, lv)
+            forward(x, lv)
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.unet_forward(usd, cfg.as_dict(), x, lv)
+            forward(x, lv)
         t_step = (time.perf_counter() - t0) / steps
         cube = synth.sr_cube(1, wl["bands"], HW, seed=2)
         t0 = time.perf_counter()
@@ -171,9 +201,9 @@ def cpu_reference_leg(wl: dict, steps: int, warmup: int, full: bool = False) -> 
         O.gae_decode(gsd, geom.as_dict(), cube, zs)
         t_codec = time.perf_counter() - t0
     per_patch = geom.G * T * t_step + t_codec
-    return {"value": 1.0 / per_patch, "unit": "patches/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} UNet forwards of one 6x{HW}x{HW} group latent ({t_step * 1e3:.1f} ms each) + 1 cube GAE "
-                      f"encode+decode ({t_codec:.2f} s), extrapolated to G={geom.G} x T={T} forwards per patch",
+    return {"value": 1.0 / per_patch, "unit": "patches/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} forwards of one 6x{HW}x{HW} group latent through {what} ({t_step * 1e3:.1f} ms each) + 1 cube GAE "
+                      f"encode+decode through the oracle port ({t_codec:.2f} s), extrapolated to G={geom.G} x T={T} forwards per patch",
             "ms_per_unet_step_per_latent": t_step * 1e3}
 
 

@@ -41,9 +41,12 @@ using namespace tc;
 
 constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter
 constexpr int kFirstEpiWarp = 3;    // warp 0: A (halo) producer, warp 1: B (weights) producer, warp 2: MMA issuer
-constexpr int kXformWarps = 4;      // warps 11..14: GroupNorm(+Swish) of the halo tile in place, when the op asks for it
+// warps 11..: GroupNorm(+Swish) of the halo tile in place, when the op asks for it.  Four of them keep up with the MMAs of
+// the wide tiles; the Cout <= 16 instantiation (the network's last conv) has almost no MMA work per tile, its tile time IS
+// the transform, so it takes eight.
+constexpr int xform_warps(int BN) { return BN == 16 ? 8 : 4; }
 constexpr int kFirstXformWarp = kFirstEpiWarp + kEpiWarps;
-constexpr int kThreads = 32 * (kFirstXformWarp + kXformWarps);
+constexpr int halo_threads(int BN) { return 32 * (kFirstXformWarp + xform_warps(BN)); }
 constexpr int kRows = 16;          // output rows per tile
 constexpr int kHaloRows = kRows + 2;
 
@@ -116,7 +119,7 @@ struct HCfg {
 };
 
 template <int MT, int BN, int NT, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(halo_threads(BN), 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const HaloP p) {
@@ -176,7 +179,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmO);
     for (int s = 0; s < C::kAStages; ++s)
       mbar_init(smem_u32(&a_full[s]), 1), mbar_init(smem_u32(&a_empty[s]), 1),
-          mbar_init(smem_u32(&a_ready[s]), PAIR ? 2 * kXformWarps : kXformWarps);   // a pair's leader hears both CTAs
+          mbar_init(smem_u32(&a_ready[s]), PAIR ? 2 * xform_warps(BN) : xform_warps(BN));   // a pair's leader hears both CTAs
     for (int s = 0; s < C::kBStages; ++s) mbar_init(smem_u32(&b_empty[s]), 1);
     for (int g = 0; g < C::kBGroups; ++g) mbar_init(smem_u32(&b_full[g]), C::kBGroup);
     for (int s = 0; s < 2; ++s)
@@ -321,6 +324,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               tc_fence_after();
             }
             const uint64_t bdesc = bdesc_hi | (uint64_t)(b_lo + bs * (C::kBStage >> 4));
+            // sub-tile outer / k-step inner.  The other order (consecutive MMAs to different accumulators) measures the
+            // same in the micro-benchmark and in the kernel (17.75 vs 17.75 ms per step, profiles/r2_experiments.md).
 #pragma unroll
             for (int s = 0; s < MT; ++s) {
 #pragma unroll
@@ -415,6 +420,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       };
       const int j8 = tid & 7, row0 = tid >> 3;
       constexpr int kRowsTot = kHaloRows * C::kPW;
+      constexpr int kXformWarps = xform_warps(BN);
       constexpr int kRowStep = 32 * kXformWarps / 8;
       const int C0 = p.chunks0 * kBK, C1 = p.chunks1 * kBK;
       // Statistics window: (mean, rstd) of images [win_lo, win_lo + win_n) x groups in shared memory.  This CTA's tiles
@@ -725,6 +731,8 @@ void pick_shape(const ConvOp& op, int* MT, int* BN, bool* pair) {
   if (k3 && op.Cout % 128 == 0 && op.Win % 8 == 0) cands[nc++] = {1, 128, false};
   if (k3 && op.Cout % 64 == 0 && op.Win % 8 == 0) cands[nc++] = {1, 64, false};
   if (nc == 0) {
+    // Cout <= 16 (the network's last conv).  The narrower <2,16> tile with three halo stages was measured slower
+    // (0.44 against 0.35 ms at 176 latents, profiles/r2_experiments.md).
     if (op.Cout <= 16 && op.Win % 32 == 0 && op.ksize == 3 && !op.s2) *MT = 4, *BN = 16;
     return;
   }
@@ -840,11 +848,11 @@ int launch(const ConvOp& op, cudaStream_t stream) {
   if constexpr (PAIR) {
     // one cluster of two CTAs per pair of adjacent pixel tiles; an even grid of at most one CTA per SM
     const int pairs = pt.ctas;
-    HSIDM_CUDA(launch_pdl(conv_halo_kernel<MT, BN, NT, true>, dim3(2 * pairs), dim3(kThreads), C::kSmemBytes, stream, 2, tmA0, tmA1,
+    HSIDM_CUDA(launch_pdl(conv_halo_kernel<MT, BN, NT, true>, dim3(2 * pairs), dim3(halo_threads(BN)), C::kSmemBytes, stream, 2, tmA0, tmA1,
                           tmR0, tmR1, tmB, tmO, p));
   } else {
     const int grid = pt.ctas;
-    HSIDM_CUDA(launch_pdl(conv_halo_kernel<MT, BN, NT, false>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, 1, tmA0, tmA1, tmR0,
+    HSIDM_CUDA(launch_pdl(conv_halo_kernel<MT, BN, NT, false>, dim3(grid), dim3(halo_threads(BN)), C::kSmemBytes, stream, 1, tmA0, tmA1, tmR0,
                           tmR1, tmB, tmO, p));
   }
   return after_launch("conv_halo_kernel");

@@ -180,48 +180,60 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
   }
 }
 
-// one thread per output pixel: 64 bf16 = 128 B per row; the 3x3 neighbourhood of every source plane is read with
-// coalesced loads (x is the fastest index across threads) and three row pointers per plane.
+// one thread per output pixel gathers its row (64 bf16 = 128 B): the 3x3 neighbourhood of every source plane is read with
+// coalesced loads (x is the fastest index across threads) and three row pointers per plane.  The block's 128 rows are
+// contiguous in the output, so they go out through shared memory as whole 512-byte runs per warp instruction (a thread
+// storing its own row writes 16 bytes into each of 32 different lines per instruction: 2.8 TB/s measured).
 template <int CT>
 __global__ void __launch_bounds__(128)
 im2col_small_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, bf16* __restrict__ out,
                     int H, int W, int64_t total) {
+  __shared__ uint4 tile[128][8];   // [row][16-byte chunk ^ (row & 7)]
   griddep_wait();
   griddep_launch();
   const int64_t plane = (int64_t)H * W;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const int64_t n = i / plane;
-    const bool xl = x > 0, xr = x + 1 < W, yt = y > 0, yb = y + 1 < H;
-    float nb[9][CT];   // [tap][channel]
+  const int tid = threadIdx.x;
+  for (int64_t base = blockIdx.x * (int64_t)128; base < total; base += (int64_t)gridDim.x * 128) {
+    const int64_t i = base + tid;
+    if (i < total) {
+      const int x = (int)(i % W);
+      const int y = (int)((i / W) % H);
+      const int64_t n = i / plane;
+      const bool xl = x > 0, xr = x + 1 < W, yt = y > 0, yb = y + 1 < H;
+      float nb[9][CT];   // [tap][channel]
 #pragma unroll
-    for (int c = 0; c < CT; ++c) {
-      const float* p = (c < C0 ? x0 + (n * C0 + c) * plane : x1 + (n * C1 + (c - C0)) * plane) + (int64_t)y * W + x;
-      nb[0][c] = (yt && xl) ? __ldg(p - W - 1) : 0.f;
-      nb[1][c] = yt ? __ldg(p - W) : 0.f;
-      nb[2][c] = (yt && xr) ? __ldg(p - W + 1) : 0.f;
-      nb[3][c] = xl ? __ldg(p - 1) : 0.f;
-      nb[4][c] = __ldg(p);
-      nb[5][c] = xr ? __ldg(p + 1) : 0.f;
-      nb[6][c] = (yb && xl) ? __ldg(p + W - 1) : 0.f;
-      nb[7][c] = yb ? __ldg(p + W) : 0.f;
-      nb[8][c] = (yb && xr) ? __ldg(p + W + 1) : 0.f;
-    }
-    const float* flat = &nb[0][0];   // k = tap*CT + c, exactly the packed weight order
-    uint4* o = reinterpret_cast<uint4*>(out + i * 64);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      uint32_t w[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = q * 8 + 2 * j;
-        const float a = k < 9 * CT ? flat[k] : 0.f, b = k + 1 < 9 * CT ? flat[k + 1] : 0.f;
-        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      for (int c = 0; c < CT; ++c) {
+        const float* p = (c < C0 ? x0 + (n * C0 + c) * plane : x1 + (n * C1 + (c - C0)) * plane) + (int64_t)y * W + x;
+        nb[0][c] = (yt && xl) ? __ldg(p - W - 1) : 0.f;
+        nb[1][c] = yt ? __ldg(p - W) : 0.f;
+        nb[2][c] = (yt && xr) ? __ldg(p - W + 1) : 0.f;
+        nb[3][c] = xl ? __ldg(p - 1) : 0.f;
+        nb[4][c] = __ldg(p);
+        nb[5][c] = xr ? __ldg(p + 1) : 0.f;
+        nb[6][c] = (yb && xl) ? __ldg(p + W - 1) : 0.f;
+        nb[7][c] = yb ? __ldg(p + W) : 0.f;
+        nb[8][c] = (yb && xr) ? __ldg(p + W + 1) : 0.f;
       }
-      o[q] = make_uint4(w[0], w[1], w[2], w[3]);
+      const float* flat = &nb[0][0];   // k = tap*CT + c, exactly the packed weight order
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = q * 8 + 2 * j;
+          const float a = k < 9 * CT ? flat[k] : 0.f, b = k + 1 < 9 * CT ? flat[k + 1] : 0.f;
+          __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+          w[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        tile[tid][q ^ (tid & 7)] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
+    __syncthreads();
+    const int rows = (int)(total - base < 128 ? total - base : 128);
+    uint4* o = reinterpret_cast<uint4*>(out + base * 64);
+#pragma unroll 4
+    for (int r = tid >> 3; r < rows; r += 16) o[r * 8 + (tid & 7)] = tile[r][(tid & 7) ^ (r & 7)];
+    __syncthreads();
   }
 }
 

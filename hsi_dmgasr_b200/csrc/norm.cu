@@ -224,7 +224,7 @@ gn_apply_t_kernel(const bf16* __restrict__ x, int S, int C, const GnFoldP fold, 
   __shared__ float2 gs[64];       // (mean, rstd) of the groups this block's 64 channels belong to
   griddep_wait();
   griddep_launch();
-  const int n = blockIdx.z, p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int n = blockIdx.z, c0 = blockIdx.y * 64;
   const int tid = threadIdx.x;
   const int j8 = tid & 7;          // 16-byte chunk (8 channels) of a pixel's 64-channel row
   const int cpg = C / groups, g_lo = c0 / cpg, g_n = (c0 + 63) / cpg - g_lo + 1;
@@ -241,27 +241,32 @@ gn_apply_t_kernel(const bf16* __restrict__ x, int S, int C, const GnFoldP fold, 
     A[j] = st.y * __ldg(gamma + c);
     B[j] = __ldg(beta + c) - st.x * A[j];
   }
+  // the block walks the 64-pixel tiles blockIdx.x, blockIdx.x + gridDim.x, ... of its channel slice: the statistics fold
+  // and the coefficients above are paid once per block, not once per 8 KB tile
+  for (int p0 = blockIdx.x * 64; p0 < S; p0 += gridDim.x * 64) {
 #pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int px = (tid >> 3) + 32 * it;
-    const int64_t off = ((int64_t)n * S + p0 + px) * C + c0 + j8 * 8;
-    float f[8];
-    load8(x + off, f);
+    for (int it = 0; it < 2; ++it) {
+      const int px = (tid >> 3) + 32 * it;
+      const int64_t off = ((int64_t)n * S + p0 + px) * C + c0 + j8 * 8;
+      float f[8];
+      load8(x + off, f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], A[j], B[j]);
-    store8(y + off, f);
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], A[j], B[j]);
+      store8(y + off, f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) tile[j8 * 8 + j][px] = __float2bfloat16_rn(f[j]);
-  }
-  __syncthreads();
+      for (int j = 0; j < 8; ++j) tile[j8 * 8 + j][px] = __float2bfloat16_rn(f[j]);
+    }
+    __syncthreads();
 #pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int ch = (tid >> 3) + 32 * it;
-    uint4 o;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+    for (int it = 0; it < 2; ++it) {
+      const int ch = (tid >> 3) + 32 * it;
+      uint4 o;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = __halves2bfloat162(tile[ch][j8 * 8 + 2 * j], tile[ch][j8 * 8 + 2 * j + 1]);
-    *reinterpret_cast<uint4*>(yt + ((int64_t)n * C + c0 + ch) * S + p0 + j8 * 8) = o;
+      for (int j = 0; j < 4; ++j) h[j] = __halves2bfloat162(tile[ch][j8 * 8 + 2 * j], tile[ch][j8 * 8 + 2 * j + 1]);
+      *reinterpret_cast<uint4*>(yt + ((int64_t)n * C + c0 + ch) * S + p0 + j8 * 8) = o;
+    }
+    __syncthreads();   // the tile is rewritten by the next pixel tile
   }
 }
 
@@ -290,7 +295,12 @@ int gn_apply_transposed(const void* x, int N, int S, const GnIn& gn, void* y, vo
   char tag[64];
   snprintf(tag, sizeof(tag), "apply+T c%d hw%d n%d", C, S, N);
   ProfScope prof(PROF_GN_APPLY, 3.0 * N * S * C * 2, stream, tag);
-  HSIDM_CUDA(launch_pdl(gn_apply_t_kernel, dim3(S / 64, C / 64, N), dim3(256), 0, stream, 1, (const bf16*)x, S, C, f, gn.stats, gn.groups,
+  // enough blocks to fill the machine a few times over, as few pixel tiles per image as that allows (variant 16384: one
+  // block per 64x64 tile, the round-2 form)
+  int gx = S / 64;
+  if (!(conv_tc_variant() & 16384))
+    while (gx > 1 && gx % 2 == 0 && (int64_t)(gx / 2) * (C / 64) * N >= 8 * 148) gx /= 2;
+  HSIDM_CUDA(launch_pdl(gn_apply_t_kernel, dim3(gx, C / 64, N), dim3(256), 0, stream, 1, (const bf16*)x, S, C, f, gn.stats, gn.groups,
                         gn.gamma, gn.beta, (bf16*)y, (bf16*)yt));
   return after_launch("gn_apply_t_kernel");
 }

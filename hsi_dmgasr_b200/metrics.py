@@ -1,7 +1,8 @@
 """MPSNR and SAM exactly as the reference's validation computes them (eval_hsi.py:110-121 and :47-65), vectorised.
 
 Inputs are HWC arrays after the driver's clamp to [0,1] (sr_gae.py:474-475, 483-484). These two are the metrics the
-parity gates are stated in; the remaining indices of quality_assessment (SSIM, ERGAS, CC, RMSE) are out of scope."""
+parity gates are stated in; all six indices of quality_assessment run on the device through
+``prepost.quality_assessment`` (hsidm_quality_assessment)."""
 from __future__ import annotations
 
 import numpy as np

@@ -32,7 +32,8 @@ HSIDM_API int hsidm_debug_groupnorm(int precision, const void* x0, int c0, const
  * 256 = GroupNorm statistics through gn_finalize launches instead of the producing convolution's tail;
  * 512 = self-attention with q, k, v materialised instead of the folded projections (Wk^T Wq, Wout Wv);
  * 1024 = no occupancy-based narrowing of the halo tile at small batches (always the full-batch tile shape);
- * 4096 = attention scores + softmax and P.V as two GEMM launches instead of the fused attn_flash kernel. */
+ * 4096 = attention scores + softmax and P.V as two GEMM launches instead of the fused attn_flash kernel;
+ * 16384 = the attention's transposing GroupNorm with one block per 64x64 tile instead of blocks walking several tiles. */
 HSIDM_API int hsidm_debug_conv_mode(int no_halo, int variant);
 
 /* Developer probe: when device_counters is non-null every halo-kernel launch writes 8 int64 cycle counters per CTA

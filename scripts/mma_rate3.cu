@@ -312,6 +312,9 @@ int main() {
   for (int v = 0; v < 6; ++v) run<128, 2>(v, d);
   for (int v : {0, 4}) run<256, 1>(v, d);
   for (int v : {0, 1, 2}) run<64, 2>(v, d);
+  for (int v : {0, 1}) run<16, 4>(v, d);
+  for (int v : {0, 1}) run<32, 4>(v, d);
+  for (int v : {0, 1}) run<16, 2>(v, d);
   run64<256>(0, d);
   run64<128>(0, d);
   run64<64>(0, d);

@@ -196,3 +196,29 @@ def test_mssim_restatement_properties():
     s = ((2 * ux * uy + 1e-4) * (2 * vxy + 9e-4)) / ((ux * ux + uy * uy + 1e-4) * (vx + vy + 9e-4))
     one = O.mssim(a[:7, :7, :1], b[:7, :7, :1])
     assert abs(one - s) < 1e-12
+
+
+def test_compiled_reference_modules_agree_with_the_oracle():
+    """oracle/_ref holds the unmodified reference's unet.py / diffusion.py as sourceless bytecode (oracle/build_ref.py,
+    run by __graft_entry__.build() where /root/reference exists); bench.py's reference arm times them.  They and the
+    oracle port must be the same function."""
+    from oracle import build_ref
+    ref = build_ref.load()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference at build time)")
+    unet_mod, diff_mod = ref
+    cfg = SMALL
+    sd = synth.unet_state_dict(cfg, 3)
+    net = unet_mod.UNet(in_channel=cfg.in_channel, out_channel=cfg.out_channel, norm_groups=cfg.norm_groups,
+                        inner_channel=cfg.inner_channel, channel_mults=list(cfg.channel_mults), attn_res=list(cfg.attn_res),
+                        res_blocks=cfg.res_blocks, dropout=cfg.dropout, image_size=cfg.image_size).eval()
+    net.load_state_dict(sd, strict=True)
+    x, lv = rand((2, 6, 16, 16), 5), torch.tensor([[0.3], [0.9]])
+    with torch.no_grad():
+        want = net(x, lv)
+        got = O.unet_forward(sd, cfg.as_dict(), x, lv)
+    assert rel(got, want) < 2e-6
+    gd = diff_mod.GaussianDiffusion(net, image_size=16, channels=3, conditional=True)
+    gd.set_new_noise_schedule(dict(schedule="cosine", n_timestep=20, linear_start=1e-6, linear_end=1e-2), "cpu")
+    tab = O.schedule_tables(O.beta_schedule("cosine", 20, 1e-6, 1e-2))
+    assert np.array_equal(gd.betas.numpy(), tab["betas"].astype(np.float32))
