@@ -7,6 +7,8 @@ latent images it is given.  ``p_sample`` / ``p_mean_variance`` keep the referenc
 """
 from __future__ import annotations
 
+import hashlib
+
 import ctypes as C
 import os
 from typing import Optional
@@ -62,7 +64,9 @@ class GaussianDiffusion(nn.Module):
         h = self.denoise_fn.native(device)
         if self._betas64 is None:
             raise _lib.HsidmError(-7, "set_new_noise_schedule has not been called")
-        sig = (self._betas64.ctypes.data, self.num_timesteps, float(self._betas64.sum()))
+        # content, not address: setting the same schedule again (the reference's drivers do, per cube) must not cost a
+        # table rebuild and a graph re-capture
+        sig = (self.num_timesteps, hashlib.sha1(self._betas64.tobytes()).hexdigest())
         if h.schedule_sig != sig:
             lib = _lib.load()
             _lib.check(lib.hsidm_set_schedule(h.ptr, self._betas64.ctypes.data_as(C.POINTER(C.c_double)),

@@ -1,8 +1,8 @@
 """Recipe for oracle/_ref/: the UNMODIFIED reference modules of the hot path, compiled where they lie.
 
 TEST / BASELINE INFRASTRUCTURE.  The reference is pure Python, so "compiling" it means byte-compiling
-``model/sr3_modules/unet.py`` and ``model/sr3_modules/diffusion.py`` from /root/reference into sourceless ``.pyc`` files
-under ``oracle/_ref/`` (git-ignored, so no reference source enters the history; not gpurun-ignored, so the files travel to
+``model/sr3_modules/unet.py`` and ``model/sr3_modules/diffusion.py`` from /root/reference into sourceless bytecode files
+(``*.bc``: the ``.pyc`` format under another extension, so that tools which skip ``*.pyc`` still ship them) under ``oracle/_ref/`` (git-ignored, so no reference source enters the history; not gpurun-ignored, so the files travel to
 the GPU box, which has this same interpreter but no /root/reference).  ``bench.py --impl reference`` and the
 ``cpu_baseline`` leg load them (``load()`` below) and time the reference's own ``UNet.forward`` /
 ``GaussianDiffusion.super_resolution`` on the host cores (``kind: "reference"``); when the directory is missing they fall
@@ -33,7 +33,7 @@ def build(reference: str = "/root/reference") -> list:
     written = []
     for name, rel in MODULES.items():
         src = os.path.join(reference, rel)
-        dst = os.path.join(OUT, f"{name}.pyc")
+        dst = os.path.join(OUT, f"{name}.bc")
         # unchecked-hash pyc: valid without the source file next to it; dfile keeps reference paths in tracebacks
         py_compile.compile(src, cfile=dst, dfile=f"<reference>/{rel}", doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
@@ -46,7 +46,7 @@ def load():
     built by another interpreter version)."""
     mods = []
     for name in MODULES:
-        path = os.path.join(OUT, f"{name}.pyc")
+        path = os.path.join(OUT, f"{name}.bc")
         if not os.path.isfile(path):
             return None
         try:

@@ -3,7 +3,7 @@ bench lines, ncu launch list per kernel, ncu --set full tables with per-shape DR
 protocol, layer profiles.  Usage: python scripts/make_r2_profiles.py [tag]   (default tag r2f)"""
 import collections, csv, io, json, os, re, shutil, sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r2f"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2z"
 src = f"gpurun_out/{tag}"
 os.makedirs("profiles", exist_ok=True)
 
@@ -97,7 +97,9 @@ captures = [("h464", "conv_halo_kernel<4,64,9,single CTA> (64-channel 128x128 la
             ("h2128", "conv_halo_kernel<2,128,9,single CTA> (128-channel 64x64 layers)"),
             ("h1256p", "conv_halo_kernel<1,256,9,CTA pair> (256/512-channel layers)"),
             ("pertap", "conv_tc_kernel<256> (per-tap kernel: 8x8 stage, attention projections)"),
-            ("gemm", "gemm_tc_kernel<256> (attention scores + softmax, P.Xn)"),
+            ("flash", "attn_flash_kernel (attention scores + softmax + P.Xn in one kernel)"),
+            ("i2c", "im2col_small_kernel (first conv's K = 64 rows)"),
+            ("fin", "conv_halo_kernel<4,16,9,single CTA> (last conv, 64 -> 3)"),
             ("applyt", "gn_apply_t_kernel (attention GroupNorm + transposed copy)"),
             ("post", "posterior_kernel")]
 per_tag = {}

@@ -315,6 +315,8 @@ int main() {
   for (int v : {0, 1}) run<16, 4>(v, d);
   for (int v : {0, 1}) run<32, 4>(v, d);
   for (int v : {0, 1}) run<16, 2>(v, d);
+  run<192, 2>(0, d);   // three horizontal taps stacked as one N = 192 MMA per A window
+  run<128, 3>(0, d);
   run64<256>(0, d);
   run64<128>(0, d);
   run64<64>(0, d);

@@ -58,7 +58,7 @@ def test_loss_and_gradients_match_reference(golden, loss_type):
     loss = l_pix.sum() / int(B * 3 * HW * HW)                              # model.py:53-55
     loss.backward()
     want_sum, want = float(g[f"{loss_type}.loss_sum"]), float(g[f"{loss_type}.loss"])
-    assert abs(float(l_pix) - want_sum) < 1e-5 * abs(want_sum) and abs(float(loss) - want) < 1e-5
+    assert abs(float(l_pix.detach()) - want_sum) < 1e-5 * abs(want_sum) and abs(float(loss.detach()) - want) < 1e-5
     worst, checked, n = 0.0, 0, 0
     for k, p in gd.denoise_fn.named_parameters():
         assert p.grad is not None and p.grad.shape == p.shape, k
