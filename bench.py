@@ -352,7 +352,12 @@ def roofline_leg(lib, gd, z, K, n_lat, ms_per_step, pk) -> dict:
             "note": "achieved = the reference's algorithmic FLOPs / kernel time; *_executed counts the FLOPs the kernels really issue "
                     "(the sub-pixel upsample convs execute 16/36 of the reference's)",
             "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)",
-            "traffic": traffic.get("dram_bytes_per_launch"), "traffic_note": traffic.get("source"),
+            # DRAM bytes of ONE launch (ncu --set full) next to that launch's algorithmic bytes; the mean over the captured
+            # launches of different layers is kept for continuity with round 1
+            "traffic": traffic.get("dram_bytes_first_layer") or traffic.get("dram_bytes_per_launch"),
+            "traffic_algorithmic": traffic.get("algorithmic_bytes_first_layer"), "traffic_layer": traffic.get("first_layer"),
+            "traffic_layers": traffic.get("layers"), "traffic_mean_over_captures": traffic.get("dram_bytes_per_launch"),
+            "traffic_note": traffic.get("source"),
             "launches_per_step": tc["launches"], "algorithmic_flop_per_step": tc["work"], "kernel_ms_per_step": tc["ms"],
             "step_breakdown_ms": {k: round(v["ms"], 3) for k, v in fam.items()},
             "per_shape": per_shape[:40], "hbm_kernels": hbm, "hbm_peak_gbs": pk["hbm_gbs"],

@@ -122,14 +122,30 @@ with open("profiles/r2_ncu_full.md", "w") as f:
             f.write(f"| {what} | {i} | {val(r, col, 'gpu__time_duration.sum'):.1f} | "
                     f"{val(r, col, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'):.1f} | "
                     f"{val(r, col, 'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed'):.1f} | {rd:.1f} | {wr:.1f} | "
-                    f"{val(r, col, 'dram__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+                    f"{val(r, col, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed' if 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed' in col else 'FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
                     f"{val(r, col, 'lts__t_sectors_srcunit_tex_op_read.sum'):.3g} | {val(r, col, 'launch__registers_per_thread'):.0f} | "
-                    f"{val(r, col, 'launch__shared_mem_per_block_dynamic') / 1024 if 'launch__shared_mem_per_block_dynamic' in col else float('nan'):.0f} |\n")
+                    f"{val(r, col, 'launch__shared_mem_per_block_dynamic') * {'Kbyte/block': 1.0, 'byte/block': 1 / 1024, 'Mbyte/block': 1024.0}.get(units[col['launch__shared_mem_per_block_dynamic']], 1.0) if 'launch__shared_mem_per_block_dynamic' in col else float('nan'):.0f} |\n")
     f.write("\nAlgorithmic bytes for comparison (bf16 NHWC, 176 latents): a 64-channel 128x128 tensor is 369 MB, a 128-channel 64x64 tensor 185 MB, "
             "a 256-channel 32x32 tensor 92 MB, a 512-channel 16x16 tensor 46 MB; a conv reads its input(s) once and writes its output once, so e.g. "
             "a 64 -> 64 conv at 128x128 has 738 MB of algorithmic traffic (+ 369 MB residual where it has one).  DRAM traffic close to or BELOW that "
             "figure means no wasted re-reads (the deeper layers stay far below: their operands still sit in the 126 MB L2).\n")
+# The h464 capture skips four launches of conv_halo_kernel<4,64,9> (the two down blocks' conv1 / conv2) and takes the next
+# three: conv1 and conv2 of the first 128x128 up block and conv1 of the second (unet.cu res_block order).  Algorithmic bytes
+# = inputs read once + output written once, bf16 NHWC, 176 latents: a 64-channel 128x128 tensor is 369.1 MB.
+T64 = 176 * 128 * 128 * 64 * 2
+H464_LAYERS = [("halo MT4 BN64 cin128+64 cout64 128x128 n176 +nb +st +gn", "up block 1 conv1: reads 128 + 64 channels, writes 64", 3 * T64 + T64),
+               ("halo MT4 BN64 cin64+0 cout64 128x128 n176 +st +gn", "up block 1 conv2 with the res_conv folded in: reads 64 channels + the 192-channel block input, writes 64", T64 + 3 * T64 + T64),
+               ("halo MT4 BN64 cin64+64 cout64 128x128 n176 +nb +st +gn", "up block 2 conv1: reads 64 + 64 channels, writes 64", 2 * T64 + T64)]
+layers, per_shape_tag = [], {}
+if len(per_tag.get("h464", [])) == len(H464_LAYERS):
+    for (ltag, what, alg), meas in zip(H464_LAYERS, per_tag["h464"]):
+        layers.append({"tag": ltag, "layer": what, "dram_bytes": meas, "algorithmic_bytes": alg, "ratio": round(meas / alg, 3)})
+        per_shape_tag[ltag] = meas
 json.dump({"source": f"ncu --set full, {tag}: dram__bytes_read.sum + dram__bytes_write.sum per launch",
+           "layers": layers, "per_tag": per_shape_tag,
+           "dram_bytes_first_layer": layers[0]["dram_bytes"] if layers else None,
+           "algorithmic_bytes_first_layer": layers[0]["algorithmic_bytes"] if layers else None,
+           "first_layer": (layers[0]["tag"] + " - " + layers[0]["layer"]) if layers else None,
            "per_capture_bytes_per_launch": {k: sum(v) / len(v) for k, v in per_tag.items()},
            "dram_bytes_per_launch": (sum(per_tag["h464"]) / len(per_tag["h464"])) if "h464" in per_tag else None,
            "kernel": "conv_halo_kernel<4,64,9> (the 64-channel 128x128 layers: largest share of the step)"},
