@@ -251,3 +251,40 @@ def test_synthetic_inputs_are_reproducible():
     assert x.shape == (3, 3, 8, 8) and tape.shape == (3, 5, 3, 8, 8)
     sd = synth.unet_state_dict(SMALL, 1)
     assert list(sd.keys()) == list(unet_param_shapes(SMALL).keys())
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's CPU arm): one JSON line with the contract's keys, `impl: reference`, a
+    cpu_baseline describing this run, e2e = the line's own value with zero copy bytes, and - when oracle/_ref has been
+    built - the unmodified reference modules as the thing that was timed."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "patches/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["e2e"] == {"value": line["value"], "unit": "patches/s", "h2d_bytes_per_step": 0,
+                                                  "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["value"] == line["value"] and cb["cores"] >= 1 and "workload" in line["config"]
+    from oracle import build_ref
+    assert cb["kind"] == ("reference" if build_ref.load() else "port")
+    assert line["gpu_launches"] == 0
+
+
+def test_bench_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun only rank 0 runs and prints the reference arm; the other ranks exit 0 without work."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
