@@ -81,13 +81,14 @@ class SRPipeline:
 
 
 @torch.no_grad()
-def validate(pipeline: SRPipeline, loader, device: torch.device, **kw) -> dict:
+def validate(pipeline: SRPipeline, loader, device: torch.device, ratio: float = 4.0, **kw) -> dict:
     """The reference's validation loop (sr_gae.py:436-497) over an iterable of ``{'HR': [B,C,H,W], 'SR': [B,C,H,W]}``
-    batches: encode -> sample -> decode -> clamp to [0,1] -> metrics, with the indices the parity gates are stated in
-    (MPSNR, SAM) computed on the device and averaged over cubes like ``sum_dict`` / ``idx`` do.  The GAE is loaded once
+    batches: encode -> sample -> decode -> clamp to [0,1] -> ``quality_assessment(gt, y, data_range=1., ratio=4)``
+    (sr_gae.py:487-491) with all six indices computed on the device (hsidm_quality_assessment) and averaged over cubes
+    like ``sum_dict`` / ``idx`` do.  MPSNR and SAM are the indices the parity gates are stated in.  The GAE is loaded once
     (the reference re-reads the pickle per cube, sr_gae.py:444); results stay on the device until the final averages."""
     from . import prepost
-    total = torch.zeros(2, device=device, dtype=torch.float64)
+    total = torch.zeros(len(prepost.ASSESSMENT_KEYS), device=device, dtype=torch.float64)
     count = 0
     for batch in loader:
         sr = batch["SR"].to(device, non_blocking=True)
@@ -95,12 +96,12 @@ def validate(pipeline: SRPipeline, loader, device: torch.device, **kw) -> dict:
         if sr.dim() == 3:
             sr, hr = sr.unsqueeze(0), hr.unsqueeze(0)
         y = pipeline.super_resolve(sr.float().contiguous(), clamp=True, **kw)
-        total += prepost.quality_metrics(hr.float().contiguous(), y).double().sum(dim=0)
+        total += prepost.quality_assessment(hr.float().contiguous(), y, ratio=ratio).double().sum(dim=0)
         count += sr.shape[0]
     if count == 0:
-        return {"MPSNR": float("nan"), "SAM": float("nan"), "cubes": 0}
+        return {**{k: float("nan") for k in prepost.ASSESSMENT_KEYS}, "cubes": 0}
     mean = (total / count).cpu()
-    return {"MPSNR": float(mean[0]), "SAM": float(mean[1]), "cubes": count}
+    return {**{k: float(mean[i]) for i, k in enumerate(prepost.ASSESSMENT_KEYS)}, "cubes": count}
 
 
 def run_sharded(pipeline: SRPipeline, cubes_host: torch.Tensor, device: torch.device, rank: int, world: int,

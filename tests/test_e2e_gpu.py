@@ -109,6 +109,7 @@ def test_validation_driver_matches_per_cube_metrics():
     over the cubes equal the numpy eval_hsi metrics of the individually super-resolved, clamped cubes."""
     from hsi_dmgasr_b200 import metrics
     from hsi_dmgasr_b200.pipeline import validate
+    from oracle import hsidm_oracle as O
     pipe, geom = build("fp32", 5)
     sr = synth.sr_cube(3, 31, 16, seed=70)
     hr = (sr + 0.03 * torch.from_numpy(np.random.default_rng(71).standard_normal(tuple(sr.shape), dtype=np.float32))).clamp(0, 1)
@@ -117,7 +118,7 @@ def test_validation_driver_matches_per_cube_metrics():
     draws = iter([(x_T[:2 * geom.G], tape[:2 * geom.G]), (x_T[2 * geom.G:], tape[2 * geom.G:])])
 
     # per-cube reference numbers, batch by batch with the matching slice of the injected noise
-    want_m, want_s = [], []
+    want_m, want_s, want_all = [], [], []
     for b, (xt, tp) in zip(loader, draws):
         s = b["SR"] if b["SR"].dim() == 4 else b["SR"].unsqueeze(0)
         h = b["HR"] if b["HR"].dim() == 4 else b["HR"].unsqueeze(0)
@@ -125,6 +126,11 @@ def test_validation_driver_matches_per_cube_metrics():
         for i in range(y.shape[0]):
             want_m.append(metrics.mpsnr(h[i].permute(1, 2, 0).numpy(), y[i].permute(1, 2, 0).numpy()))
             want_s.append(metrics.sam_degrees(h[i].permute(1, 2, 0).numpy(), y[i].permute(1, 2, 0).numpy()))
+        want_all += O.cube_assessment(h, y, 4.0)          # (MPSNR, MSSIM, ERGAS, SAM, CrossCorrelation, RMSE) per cube
     got = validate(pipe, [{"HR": hr, "SR": sr}], torch.device("cuda"), x_T=x_T.cuda(), noise_tape=tape.cuda())
     assert got["cubes"] == 3
     assert abs(got["MPSNR"] - float(np.mean(want_m))) < 1e-3 and abs(got["SAM"] - float(np.mean(want_s))) < 1e-3
+    # the reference loop sums every index of quality_assessment(gt, y, data_range=1., ratio=4) (sr_gae.py:487-491)
+    mean_all = np.mean(np.asarray(want_all, dtype=np.float64), axis=0)
+    for i, key in enumerate(("MPSNR", "MSSIM", "ERGAS", "SAM", "CrossCorrelation", "RMSE")):
+        assert abs(got[key] - mean_all[i]) < 1e-3 * max(1.0, abs(mean_all[i])), (key, got[key], mean_all[i])
