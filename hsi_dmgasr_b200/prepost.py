@@ -80,8 +80,14 @@ def quality_assessment(truth: torch.Tensor, pred: torch.Tensor, ratio: float = 4
         raise _lib.HsidmError(-1, f"truth {tuple(truth.shape)} and pred {tuple(pred.shape)} must be equal [N,C,H,W] shapes")
     n, c, h, w = a.shape
     out = torch.empty((n, 6), device=a.device, dtype=torch.float32)
-    _lib.check(_lib.load().hsidm_quality_assessment(a.data_ptr(), b.data_ptr(), n, c, h, w, float(ratio), out.data_ptr(),
-                                                    _lib.stream_ptr(a.device)))
+    if c > 65535:
+        raise _lib.HsidmError(-1, f"quality_assessment: {c} bands exceed the 65535 planes of one launch")
+    step = max(1, 65535 // c)                       # one launch takes at most 65535 (cube, band) planes
+    lib, st = _lib.load(), _lib.stream_ptr(a.device)
+    for n0 in range(0, n, step):
+        cnt = min(step, n - n0)
+        _lib.check(lib.hsidm_quality_assessment(a[n0:n0 + cnt].data_ptr(), b[n0:n0 + cnt].data_ptr(), cnt, c, h, w, float(ratio),
+                                                out[n0:n0 + cnt].data_ptr(), st))
     return out
 
 
