@@ -222,3 +222,33 @@ def test_compiled_reference_modules_agree_with_the_oracle():
     gd.set_new_noise_schedule(dict(schedule="cosine", n_timestep=20, linear_start=1e-6, linear_end=1e-2), "cpu")
     tab = O.schedule_tables(O.beta_schedule("cosine", 20, 1e-6, 1e-2))
     assert np.array_equal(gd.betas.numpy(), tab["betas"].astype(np.float32))
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference"), reason="needs the reference tree (build container only)")
+def test_oracle_prepost_against_live_reference_on_random_shapes():
+    """Where the reference tree is mounted (the build container) the restatements meet the reference itself, not only
+    the committed vectors: imresize over random sizes / scales / both kernels, ERGAS / CC / RMSE / SAM on random cubes."""
+    import sys
+    from oracle import make_golden as MG
+    _, eval_hsi, _, _ = MG.import_reference()
+    sys.path.insert(0, __import__("os").path.join(MG.REF, "GAE"))
+    import imsize
+    rng = np.random.default_rng(2024)
+    for _ in range(12):
+        h, w, c = int(rng.integers(5, 40)), int(rng.integers(5, 40)), int(rng.integers(1, 4))
+        oh, ow = int(rng.integers(2, 60)), int(rng.integers(2, 60))
+        method = ["bicubic", "bilinear"][int(rng.integers(0, 2))]
+        x = rng.random((h, w, c), dtype=np.float32)
+        assert float(np.abs(O.imresize_matlab(x, (oh, ow), method) - imsize.imresize(x, output_shape=(oh, ow), method=method)).max()) < 1e-12
+        sc = float(rng.uniform(0.2, 3.0))
+        assert float(np.abs(O.imresize_matlab(x, scalar_scale=sc, method=method) - imsize.imresize(x, scalar_scale=sc, method=method)).max()) < 1e-12
+    x2 = rng.random((9, 11), dtype=np.float32)                                   # 2-D input keeps its rank (imsize.py:147-156)
+    assert O.imresize_matlab(x2, (18, 5)).shape == imsize.imresize(x2, output_shape=(18, 5)).shape == (18, 5)
+    for _ in range(4):
+        h, w, c = int(rng.integers(8, 24)), int(rng.integers(8, 24)), int(rng.integers(2, 12))
+        t = rng.random((h, w, c), dtype=np.float32)
+        p = np.clip(t + 0.1 * rng.standard_normal((h, w, c)).astype(np.float32), 0, 1)
+        assert abs(O.ergas(t, p, 4) - eval_hsi.compare_ergas(t, p, 4)) < 3e-4 * eval_hsi.compare_ergas(t, p, 4)
+        assert abs(O.cross_correlation(t, p) - eval_hsi.compare_corr(t, p)) < 1e-5
+        assert abs(O.rmse(t, p) - eval_hsi.compare_rmse(t, p)) < 1e-6
+        assert abs(O.sam_deg(t, p) - eval_hsi.compare_sam(t, p)) < 1e-3
